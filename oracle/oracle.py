@@ -1,0 +1,257 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- see uav_oracle.h / dqn_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package never does.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("uav_oracle.c", "dqn_oracle.c", "uav_oracle.h", "dqn_oracle.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", HERE, "-B"])
+    return LIB_PATH
+
+
+class Loc(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("z", C.c_double)]
+
+
+class City(C.Structure):
+    _fields_ = [("len", C.c_double), ("width", C.c_double), ("h", C.c_double),
+                ("n_buildings", C.c_int32), ("buildings", C.POINTER(C.c_double))]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kmax", C.c_int32)] + \
+        [(k, C.POINTER(C.c_double)) for k in ("px", "py", "pz", "vx", "vy", "V")] + \
+        [(k, C.POINTER(C.c_int32)) for k in ("step", "cursor", "n_sub")] + \
+        [(k, C.POINTER(C.c_uint8)) for k in ("done", "alias0")] + \
+        [(k, C.POINTER(C.c_double)) for k in ("score", "total_score", "path_len", "goal", "sub")]
+
+
+class Net(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("n_hidden", C.c_int32), ("hidden", C.c_int32 * 4),
+                ("n_actions", C.c_int32), ("dueling", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ora_distance.restype = C.c_double
+        _lib.ora_distance.argtypes = [Loc, Loc]
+        _lib.ora_angle.restype = C.c_double
+        _lib.ora_angle.argtypes = [Loc, Loc]
+        _lib.ora_threaten_rate.restype = C.c_int32
+        _lib.ora_threaten_rate.argtypes = [C.POINTER(City), Loc]
+        _lib.ora_fly_power.restype = C.c_double
+        _lib.ora_fly_power.argtypes = [C.c_double] * 10
+        _lib.ora_net_param_count.restype = C.c_int64
+        _lib.ora_dqn_update.restype = C.c_float
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+ACT_CONTINUOUS, ACT_DISCRETE27 = 0, 1
+ALGO_DQN, ALGO_DDQN, ALGO_DUELING = 0, 1, 2
+INFO_NAMES = ("normal", "success", "lose")
+
+
+class OracleCity:
+    """City = box dims + cylinder table [n,5] (cx, cy, cz, R, H)."""
+
+    def __init__(self, length, width, h, buildings):
+        self.buildings = np.ascontiguousarray(buildings, dtype=np.float64).reshape(-1, 5)
+        self.c = City(float(length), float(width), float(h), self.buildings.shape[0],
+                      _p(self.buildings, C.c_double))
+
+    def threaten_rate(self, pts):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        L = lib()
+        return np.array([L.ora_threaten_rate(C.byref(self.c), Loc(*p)) for p in pts], dtype=np.uint8)
+
+
+class UavParams:
+    def __init__(self, max_v=1.0, min_v=0.6, steering=np.pi / 6, climb_rate=1.0, max_step=150):
+        self.max_v, self.min_v, self.steering = float(max_v), float(min_v), float(steering)
+        self.climb_rate, self.max_step = float(climb_rate), int(max_step)
+
+
+class OracleBatch:
+    """SoA state of n UAVs, stepped by the C oracle (ora_batch_step)."""
+
+    F64 = ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len")
+
+    def __init__(self, city, params, n, kmax):
+        self.city, self.p, self.n, self.kmax = city, params, n, kmax
+        for k in self.F64:
+            setattr(self, k, np.zeros(n, np.float64))
+        self.step = np.zeros(n, np.int32)
+        self.cursor = np.zeros(n, np.int32)
+        self.n_sub = np.zeros(n, np.int32)
+        self.done = np.zeros(n, np.uint8)
+        self.alias0 = np.zeros(n, np.uint8)
+        self.goal = np.zeros((n, 3), np.float64)
+        self.sub = np.zeros((n, kmax, 3), np.float64)
+
+    def reset(self, start, goal, heading, sub, n_sub, alias0=None):
+        """UAV.reset() (Agents/UAV.py:335-366) with the random draws supplied by the caller."""
+        n = self.n
+        start = np.asarray(start, np.float64).reshape(n, 3)
+        self.px[:], self.py[:], self.pz[:] = start[:, 0], start[:, 1], start[:, 2]
+        heading = np.asarray(heading, np.float64).reshape(n)
+        # UAV.py:344-348 with python-float (libm) arithmetic, then Calc_V (UAV.py:246-253)
+        for e in range(n):
+            self.vx[e] = self.p.max_v * math.cos(float(heading[e]))
+            self.vy[e] = self.p.max_v * math.sin(float(heading[e]))
+            V = math.sqrt(float(self.vx[e]) ** 2 + float(self.vy[e]) ** 2 + 0.0 ** 2)
+            if V > self.p.max_v:
+                self.vx[e] = self.vx[e] * (self.p.max_v / V)
+                self.vy[e] = self.vy[e] * (self.p.max_v / V)
+                V = self.p.max_v
+            self.V[e] = V
+        self.step[:] = 0
+        self.cursor[:] = 0
+        self.done[:] = 0
+        self.score[:] = 0
+        self.total_score[:] = 0
+        self.path_len[:] = 0
+        self.goal[:] = np.asarray(goal, np.float64).reshape(n, 3)
+        self.sub[:] = 0
+        sub = np.asarray(sub, np.float64)
+        self.sub[:, :sub.shape[1], :] = sub
+        self.n_sub[:] = np.asarray(n_sub, np.int32)
+        self.alias0[:] = 1 if alias0 is None else np.asarray(alias0, np.uint8)
+
+    def _struct(self):
+        b = Batch()
+        b.n, b.kmax = self.n, self.kmax
+        for k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len"):
+            setattr(b, k, _p(getattr(self, k), C.c_double))
+        b.goal = _p(self.goal, C.c_double)
+        b.sub = _p(self.sub, C.c_double)
+        for k in ("step", "cursor", "n_sub"):
+            setattr(b, k, _p(getattr(self, k), C.c_int32))
+        b.done = _p(self.done, C.c_uint8)
+        b.alias0 = _p(self.alias0, C.c_uint8)
+        return b
+
+    def step_(self, actions, act_mode=ACT_CONTINUOUS, want_obs=True):
+        n = self.n
+        actions = np.ascontiguousarray(actions, np.float64).reshape(n)
+        rew = np.zeros(n, np.float64)
+        done = np.zeros(n, np.uint8)
+        info = np.zeros(n, np.uint8)
+        coll = np.zeros(n, np.uint8)
+        obs = np.zeros((n, 100), np.float32) if want_obs else None
+        b = self._struct()
+        lib().ora_batch_step(C.byref(self.city.c), C.byref(b), C.c_double(self.p.max_v),
+                             C.c_double(self.p.min_v), C.c_double(self.p.steering),
+                             C.c_double(self.p.climb_rate), C.c_int32(self.p.max_step),
+                             C.c_int32(act_mode), _p(actions, C.c_double), _p(rew, C.c_double),
+                             _p(done, C.c_uint8), _p(info, C.c_uint8), _p(coll, C.c_uint8),
+                             _p(obs, C.c_float) if want_obs else None)
+        return rew, done, info, coll, obs
+
+    def state(self, want64=False):
+        obs = np.zeros((self.n, 100), np.float32)
+        obs64 = np.zeros((self.n, 100), np.float64) if want64 else None
+        b = self._struct()
+        lib().ora_batch_state(C.byref(self.city.c), C.byref(b), C.c_double(self.p.max_v),
+                              C.c_double(self.p.min_v), C.c_double(self.p.steering),
+                              C.c_double(self.p.climb_rate), C.c_int32(self.p.max_step),
+                              _p(obs, C.c_float), _p(obs64, C.c_double) if want64 else None)
+        return (obs, obs64) if want64 else obs
+
+
+def angle(p1, p2):
+    return lib().ora_angle(Loc(*p1), Loc(*p2))
+
+
+def distance(p1, p2):
+    return lib().ora_distance(Loc(*p1), Loc(*p2))
+
+
+# ------------------------------------------------------------------ learner math
+def make_net(in_dim, hidden, n_actions, dueling):
+    n = Net()
+    n.in_dim, n.n_hidden, n.n_actions, n.dueling = in_dim, len(hidden), n_actions, int(dueling)
+    for i, h in enumerate(hidden):
+        n.hidden[i] = h
+    return n
+
+
+def net_param_count(net):
+    return int(lib().ora_net_param_count(C.byref(net)))
+
+
+def net_forward(net, params, x):
+    x = np.ascontiguousarray(x, np.float32)
+    params = np.ascontiguousarray(params, np.float32)
+    q = np.zeros((x.shape[0], net.n_actions), np.float32)
+    lib().ora_net_forward(C.byref(net), _p(params, C.c_float), _p(x, C.c_float),
+                          C.c_int32(x.shape[0]), _p(q, C.c_float))
+    return q
+
+
+def act(net, params, x, eps, u, rand_action, is_train=1):
+    x = np.ascontiguousarray(x, np.float32)
+    params = np.ascontiguousarray(params, np.float32)
+    u = np.ascontiguousarray(u, np.float32)
+    rand_action = np.ascontiguousarray(rand_action, np.int32)
+    B = x.shape[0]
+    a = np.zeros(B, np.int32)
+    q = np.zeros((B, net.n_actions), np.float32)
+    lib().ora_act(C.byref(net), _p(params, C.c_float), _p(x, C.c_float), C.c_int32(B),
+                  C.c_float(eps), C.c_int32(is_train), _p(u, C.c_float), _p(rand_action, C.c_int32),
+                  _p(a, C.c_int32), _p(q, C.c_float))
+    return a, q
+
+
+class OracleLearner:
+    """local/target params + Adam state, updated by ora_dqn_update."""
+
+    def __init__(self, net, algo, params, gamma=0.99, lr=5e-4, update_loop=3):
+        self.net, self.algo = net, algo
+        self.local = np.array(params, np.float32).copy()
+        self.target = self.local.copy()
+        self.m = np.zeros_like(self.local)
+        self.v = np.zeros_like(self.local)
+        self.t = C.c_int64(0)
+        self.gamma, self.lr, self.update_loop = gamma, lr, update_loop
+        self.epoch = 0
+
+    def update(self, s, a, r, s2, d):
+        """DuelingDQN_Trainer.update :150-184 (epoch += 1, step, hard update every Update_loop)."""
+        self.epoch += 1
+        s = np.ascontiguousarray(s, np.float32)
+        s2 = np.ascontiguousarray(s2, np.float32)
+        a = np.ascontiguousarray(a, np.int32)
+        r = np.ascontiguousarray(r, np.float32)
+        d = np.ascontiguousarray(d, np.float32)
+        grads = np.zeros_like(self.local)
+        loss = lib().ora_dqn_update(
+            C.byref(self.net), C.c_int32(self.algo), _p(self.local, C.c_float),
+            _p(self.target, C.c_float), _p(self.m, C.c_float), _p(self.v, C.c_float),
+            C.byref(self.t), _p(s, C.c_float), _p(a, C.c_int32), _p(r, C.c_float),
+            _p(s2, C.c_float), _p(d, C.c_float), C.c_int32(s.shape[0]), C.c_float(self.gamma),
+            C.c_float(self.lr), _p(grads, C.c_float))
+        if self.epoch % self.update_loop == 0:
+            self.target[:] = self.local          # hard_update, :199-202
+        return float(loss), grads
