@@ -1,0 +1,458 @@
+// env.cu -- batched PathPlan_City UAV step + observation kernel (sm_100a) and its C ABI.
+//
+// Replaces, for N independent UAV instances in lockstep:
+//   BaseEnv.Move_Agent           BaseClass/BaseEnv.py:123-137
+//   UAV.update_PathPlan          Agents/UAV.py:397-513
+//   UAV.state_PathPlan           Agents/UAV.py:515-567   (80 Threaten_rate probes)
+//   PathPlan_City.Threaten_rate  Envs/PathPlan_City.py:215-223
+//   building.check_threaten      Obstacles/building.py:20-26
+//   UAV.reset (draws supplied)   Agents/UAV.py:335-366
+//
+// Kernel shape (DESIGN.md section "env_step"):  one CTA = 32 envs, 128 threads.
+//   phase 1  warp 0, one lane per env: SoA state -> registers (coalesced 8-byte columns), the
+//            fp64 kinematics / reward / termination chain, optional auto-reset from the scenario
+//            pool, state write-back, 20 real-valued observation entries -> smem tile, and the
+//            exact-culling candidate mask (cylinders whose bounding box meets the probe window).
+//   phase 2  all 4 warps: 32 x 80 occupancy probes, each against its env's candidate cylinders only
+//            (typically 0-2 of the 26), sqrt-free guard-banded fast path with the reference's exact
+//            `sqrt(s) < R` only inside the guard band -> results identical to the brute-force
+//            80 x 26 loop.
+//   phase 3  the CTA's 32 x 100 fp32 observation tile (12.8 KB, contiguous in HBM) is written
+//            with 16-byte stores, fully coalesced; this is the only large traffic of the step.
+#include "env.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace uavrl {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+__device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
+{
+    const double *st = d.pool_start + (size_t)scen * 3;
+    const double *gl = d.pool_goal + (size_t)scen * 3;
+    const double *v0 = d.pool_v0 + (size_t)scen * 3;
+    s.px = st[0]; s.py = st[1]; s.pz = st[2];
+    s.gx = gl[0]; s.gy = gl[1]; s.gz = gl[2];
+    s.vx = v0[0]; s.vy = v0[1]; s.V = v0[2];
+    s.score = 0.0; s.total = 0.0; s.path_len = 0.0;
+    s.step = 0; s.cursor = 0; s.done = 0;
+    s.n_sub = d.pool_nsub[scen];
+    s.alias = d.pool_alias[scen];
+}
+
+__device__ __forceinline__ unsigned long long cull_mask(const EnvDev &d, const Cyl *cyl, double px, double py)
+{
+    unsigned long long m = 0ull;
+    for (int c = 0; c < d.k.n_cyl; ++c) {
+        const double reach = cyl[c].R + d.cull_w;
+        const bool near_x = fabs(px - cyl[c].cx) <= reach;
+        const bool near_y = fabs(py - cyl[c].cy) <= reach;
+        if (near_x && near_y) m |= (1ull << c);
+    }
+    return m;
+}
+
+__device__ __forceinline__ int threat_masked(const EnvConst &k, const Cyl *cyl, unsigned long long m,
+                                             double x, double y, double z)
+{
+    if (out_of_bounds(k, x, y, z)) return 1;
+    while (m) {
+        const int c = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (cyl_hit(cyl[c], x, y, z)) return 1;
+    }
+    return 0;
+}
+
+template <bool DO_STEP>
+__global__ void __launch_bounds__(kEnvThreads)
+env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *__restrict__ obs,
+           float *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
+           uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
+{
+    __shared__ Cyl s_cyl[kMaxCyl];
+    __shared__ __align__(16) float s_obs[kEnvsPerBlock][kObsDim];
+    __shared__ double s_pos[3][kEnvsPerBlock];
+    __shared__ unsigned long long s_mask[kEnvsPerBlock];
+
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * kEnvsPerBlock;
+    for (int i = tid; i < d.k.n_cyl * 6; i += kEnvThreads)
+        reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
+    __syncthreads();
+
+    if (tid < 32) {
+        const int e = e0 + tid;
+        const bool valid = e < d.n;
+        unsigned long long mask = 0ull;
+        double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
+        int n_stepped = 0, n_ended = 0, n_coll = 0;
+        if (valid) {
+            EnvRegs s;
+            s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
+            s.vx = d.vx[e]; s.vy = d.vy[e]; s.V = d.V[e];
+            s.score = d.score[e]; s.total = d.total[e]; s.path_len = d.path_len[e];
+            s.gx = d.gx[e]; s.gy = d.gy[e]; s.gz = d.gz[e];
+            s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
+            s.done = d.done[e]; s.alias = d.alias[e];
+            int scen = d.scen[e];
+            mask = cull_mask(d, s_cyl, s.px, s.py);
+            if (DO_STEP) {
+                double act;
+                if (action_kind == UAVRL_ACT_CONT_F32) act = (double)static_cast<const float *>(actions)[e];
+                else if (action_kind == UAVRL_ACT_CONT_F64) act = static_cast<const double *>(actions)[e];
+                else act = (double)static_cast<const int32_t *>(actions)[e];
+                const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
+                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
+                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                const Cyl *cyl = s_cyl;
+                const EnvConst kk = d.k;
+                auto threat = [&kk, cyl, mask](double x, double y, double z) {
+                    return threat_masked(kk, cyl, mask, x, y, z);
+                };
+                StepOut o;
+                step_core(d.k, s, mode, act, sub, threat, o);
+                rew = o.reward;
+                n_stepped = 1; n_coll = o.coll; n_ended = s.done;
+                if (reward) reward[e] = (float)o.reward;
+                d.rew64[e] = o.reward;
+                if (done_out) done_out[e] = (uint8_t)o.done_ret;
+                if (info_out) info_out[e] = (uint8_t)o.info;
+                if (coll_out) coll_out[e] = (uint8_t)o.coll;
+                if (ended_out) ended_out[e] = (uint8_t)s.done;
+                if (d.auto_reset && s.done) {                      // UAV.reset() at the episode boundary
+                    scen = (int)(((long long)scen + d.n) % d.P);
+                    load_scenario(d, scen, s);
+                    mask = cull_mask(d, s_cyl, s.px, s.py);
+                    d.scen[e] = scen;
+                    d.gx[e] = s.gx; d.gy[e] = s.gy; d.gz[e] = s.gz;
+                    d.n_sub[e] = s.n_sub;
+                }
+                d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
+                d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V;
+                d.score[e] = s.score; d.total[e] = s.total; d.path_len[e] = s.path_len;
+                d.step[e] = s.step; d.cursor[e] = s.cursor;
+                d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
+            }
+            if (obs) {
+                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
+                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                obs_scalars(s, sub, &s_obs[tid][0]);
+            }
+            px = s.px; py = s.py; pz = s.pz;
+        }
+        s_pos[0][tid] = px; s_pos[1][tid] = py; s_pos[2][tid] = pz;
+        s_mask[tid] = mask;
+        if (DO_STEP) {
+            const unsigned full = 0xffffffffu;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                n_stepped += __shfl_xor_sync(full, n_stepped, off);
+                n_ended += __shfl_xor_sync(full, n_ended, off);
+                n_coll += __shfl_xor_sync(full, n_coll, off);
+                rew += __shfl_xor_sync(full, rew, off);
+            }
+            if (tid == 0 && n_stepped) {
+                atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
+                if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
+                if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);
+                atomicAdd(d.stat_reward, rew);
+            }
+        }
+    }
+    if (!obs) return;
+    __syncthreads();
+
+    // phase 2: occupancy probes
+    for (int idx = tid; idx < kEnvsPerBlock * 80; idx += kEnvThreads) {
+        const int le = idx / 80, p = idx - 80 * le;
+        if (e0 + le >= d.n) break;
+        double x, y, z;
+        int slot;
+        probe_point(p, s_pos[0][le], s_pos[1][le], s_pos[2][le], x, y, z, slot);
+        s_obs[le][slot] = threat_masked(d.k, s_cyl, s_mask[le], x, y, z) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+
+    // phase 3: coalesced 16-byte stores of the contiguous [nvalid][100] tile
+    const int nvalid = min(kEnvsPerBlock, d.n - e0);
+    const int nvec = nvalid * (kObsDim / 4);
+    float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)e0 * kObsDim);
+    const float4 *src = reinterpret_cast<const float4 *>(&s_obs[0][0]);
+    for (int i = tid; i < nvec; i += kEnvThreads) dst[i] = src[i];
+}
+
+__global__ void env_reset_kernel(EnvDev d, int first)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.n) return;
+    const int scen = (int)(((long long)first + e) % d.P);
+    EnvRegs s;
+    load_scenario(d, scen, s);
+    d.scen[e] = scen;
+    d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
+    d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V;
+    d.gx[e] = s.gx; d.gy[e] = s.gy; d.gz[e] = s.gz;
+    d.score[e] = 0.0; d.total[e] = 0.0; d.path_len[e] = 0.0; d.rew64[e] = 0.0;
+    d.step[e] = 0; d.cursor[e] = 0; d.n_sub[e] = s.n_sub;
+    d.done[e] = 0; d.alias[e] = (uint8_t)s.alias;
+}
+
+__global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, uint8_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    int hit = out_of_bounds(d.k, x, y, z);
+    for (int c = 0; c < d.k.n_cyl && !hit; ++c) hit = cyl_hit(d.cyl[c], x, y, z);
+    out[i] = (uint8_t)hit;
+}
+
+int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
+                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st)
+{
+    const int blocks = (d.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    env_kernel<true><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st)
+{
+    const int blocks = (d.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    env_kernel<false><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+}  // namespace uavrl
+
+using namespace uavrl;
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *uavrl_last_error(void) { return g_last_error.c_str(); }
+const char *uavrl_version(void) { return "uavrl-b200 0.1 (sm_100a)"; }
+int64_t uavrl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
+{
+    if (!cfg || !out) return fail(UAVRL_ERR_INVALID, "uavrl_env_create: null argument");
+    if (cfg->n_envs <= 0 || cfg->max_subgoals <= 0) return fail(UAVRL_ERR_INVALID, "n_envs and max_subgoals must be > 0");
+    if (cfg->n_buildings < 0 || cfg->n_buildings > kMaxCyl)
+        return fail(UAVRL_ERR_INVALID, "n_buildings must be in [0,64] (candidate sets are 64-bit masks)");
+    if (cfg->n_buildings > 0 && !cfg->buildings_host) return fail(UAVRL_ERR_INVALID, "buildings_host is null");
+    if (cfg->max_step <= 0 || !(cfg->max_v > 0)) return fail(UAVRL_ERR_INVALID, "max_step and max_v must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(UAVRL_ERR_CUDA, "no CUDA device: the UAV step has no CPU fallback");
+    UAVRL_CUDA(cudaSetDevice(cfg->device));
+
+    uavrl_env *env = new uavrl_env();
+    env->cfg = *cfg;
+    env->cfg.buildings_host = nullptr;
+    EnvDev &d = env->d;
+    memset(&d, 0, sizeof(d));
+    d.k.width = cfg->width; d.k.h = cfg->h;
+    d.k.max_v = cfg->max_v; d.k.min_v = cfg->min_v; d.k.steering = cfg->steering_angle;
+    d.k.climb = cfg->climb_rate; d.k.max_step = cfg->max_step; d.k.n_cyl = cfg->n_buildings;
+    d.n = cfg->n_envs; d.K = cfg->max_subgoals; d.P = 0; d.auto_reset = cfg->auto_reset;
+    d.cull_w = 20.0 + cfg->max_v + 0.5;
+
+    std::vector<Cyl> cyl((size_t)(cfg->n_buildings > 0 ? cfg->n_buildings : 1));
+    for (int i = 0; i < cfg->n_buildings; ++i) {
+        const double *b = cfg->buildings_host + 5 * i;
+        Cyl c;
+        c.cx = b[0]; c.cy = b[1]; c.R = b[3]; c.H = b[4];      // b[2] = base z: only ever subtracted from itself
+        const double r2 = c.R * c.R;
+        c.r2lo = r2 * (1.0 - 1e-12); c.r2hi = r2 * (1.0 + 1e-12);
+        cyl[i] = c;
+    }
+    Cyl *dcyl = nullptr;
+    UAVRL_CUDA(cudaMalloc((void **)&dcyl, cyl.size() * sizeof(Cyl)));
+    UAVRL_CUDA(cudaMemcpy(dcyl, cyl.data(), cyl.size() * sizeof(Cyl), cudaMemcpyHostToDevice));
+    d.cyl = dcyl;
+
+    const size_t n = (size_t)d.n;
+    double **f64[] = { &d.px, &d.py, &d.pz, &d.vx, &d.vy, &d.V, &d.score, &d.total, &d.path_len,
+                       &d.gx, &d.gy, &d.gz, &d.rew64 };
+    for (auto p : f64) { int rc = dev_alloc(p, n); if (rc) return rc; }
+    int32_t **i32[] = { &d.step, &d.cursor, &d.n_sub, &d.scen };
+    for (auto p : i32) { int rc = dev_alloc(p, n); if (rc) return rc; }
+    { int rc = dev_alloc(&d.done, n); if (rc) return rc; }
+    { int rc = dev_alloc(&d.alias, n); if (rc) return rc; }
+    { int rc = dev_alloc(&d.stat_counts, 4); if (rc) return rc; }
+    { int rc = dev_alloc(&d.stat_reward, 1); if (rc) return rc; }
+    UAVRL_CUDA(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+    *out = env;
+    return 0;
+}
+
+static void free_pool(EnvDev &d)
+{
+    cudaFree((void *)d.pool_start); cudaFree((void *)d.pool_goal); cudaFree((void *)d.pool_v0);
+    cudaFree((void *)d.pool_sub); cudaFree((void *)d.pool_nsub); cudaFree((void *)d.pool_alias);
+    d.pool_start = d.pool_goal = d.pool_v0 = d.pool_sub = nullptr;
+    d.pool_nsub = nullptr; d.pool_alias = nullptr;
+}
+
+int uavrl_env_destroy(uavrl_env *env)
+{
+    if (!env) return 0;
+    EnvDev &d = env->d;
+    cudaSetDevice(env->cfg.device);
+    void *ptrs[] = { (void *)d.cyl, d.px, d.py, d.pz, d.vx, d.vy, d.V, d.score, d.total, d.path_len, d.gx, d.gy,
+                     d.gz, d.rew64, d.step, d.cursor, d.n_sub, d.scen, d.done, d.alias, d.stat_counts,
+                     d.stat_reward, env->h_act_dev, env->h_obs_dev, env->h_rew_dev, env->h_flags_dev };
+    for (void *p : ptrs) cudaFree(p);
+    free_pool(d);
+    if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    delete env;
+    return 0;
+}
+
+int uavrl_env_set_pool(uavrl_env *env, int32_t P, const double *start, const double *goal,
+                       const double *heading, const double *sub, const int32_t *n_sub, const uint8_t *alias0)
+{
+    if (!env || P <= 0 || !start || !goal || !heading || !sub || !n_sub)
+        return fail(UAVRL_ERR_INVALID, "uavrl_env_set_pool: null/empty argument");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    EnvDev &d = env->d;
+    for (int i = 0; i < P; ++i)
+        if (n_sub[i] < 0 || n_sub[i] > d.K) return fail(UAVRL_ERR_INVALID, "n_sub exceeds max_subgoals");
+    // UAV.py:344-348: V_vector = Max_V*(cos, sin)(heading); V = Calc_V().  Done on the host with libm so
+    // the initial velocity is the reference's bit pattern.
+    std::vector<double> v0((size_t)P * 3);
+    std::vector<uint8_t> al((size_t)P, 1);
+    for (int i = 0; i < P; ++i) {
+        double vx = env->cfg.max_v * cos(heading[i]), vy = env->cfg.max_v * sin(heading[i]);
+        double V = sqrt(vx * vx + vy * vy + 0.0);
+        if (V > env->cfg.max_v) { vx = vx * (env->cfg.max_v / V); vy = vy * (env->cfg.max_v / V); V = env->cfg.max_v; }
+        v0[3 * i] = vx; v0[3 * i + 1] = vy; v0[3 * i + 2] = V;
+        if (alias0) al[i] = alias0[i];
+    }
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    free_pool(d);
+    double *ps, *pg, *pv, *pq; int32_t *pn; uint8_t *pa;
+    const size_t sub_n = (size_t)P * d.K * 3;
+    UAVRL_CUDA(cudaMalloc((void **)&ps, (size_t)P * 3 * sizeof(double)));
+    UAVRL_CUDA(cudaMalloc((void **)&pg, (size_t)P * 3 * sizeof(double)));
+    UAVRL_CUDA(cudaMalloc((void **)&pv, (size_t)P * 3 * sizeof(double)));
+    UAVRL_CUDA(cudaMalloc((void **)&pq, sub_n * sizeof(double)));
+    UAVRL_CUDA(cudaMalloc((void **)&pn, (size_t)P * sizeof(int32_t)));
+    UAVRL_CUDA(cudaMalloc((void **)&pa, (size_t)P));
+    UAVRL_CUDA(cudaMemcpy(ps, start, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(pg, goal, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(pv, v0.data(), (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(pq, sub, sub_n * sizeof(double), cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(pn, n_sub, (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(pa, al.data(), (size_t)P, cudaMemcpyHostToDevice));
+    d.pool_start = ps; d.pool_goal = pg; d.pool_v0 = pv; d.pool_sub = pq; d.pool_nsub = pn; d.pool_alias = pa;
+    d.P = P;
+    env->pool_set = true;
+    env->reset_done = false;
+    return 0;
+}
+
+int uavrl_env_reset(uavrl_env *env, int32_t first, void *stream)
+{
+    if (!env) return fail(UAVRL_ERR_INVALID, "null env");
+    if (!env->pool_set) return fail(UAVRL_ERR_STATE, "uavrl_env_reset before uavrl_env_set_pool");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    const int threads = 128, blocks = (env->d.n + threads - 1) / threads;
+    env_reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->d, first);
+    UAVRL_LAUNCHED();
+    env->reset_done = true;
+    return 0;
+}
+
+int uavrl_env_observe(uavrl_env *env, float *obs_dev, void *stream)
+{
+    if (!env || !obs_dev) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_observe before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    return launch_env_observe(env->d, obs_dev, (cudaStream_t)stream);
+}
+
+int uavrl_env_step(uavrl_env *env, int32_t action_kind, const void *actions_dev, float *next_obs_dev,
+                   float *reward_dev, uint8_t *done_dev, uint8_t *info_dev, uint8_t *collision_dev,
+                   uint8_t *ended_dev, void *stream)
+{
+    if (!env || !actions_dev) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (action_kind < 0 || action_kind > 2) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_step before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    return launch_env_step(env->d, action_kind, actions_dev, next_obs_dev, reward_dev, done_dev, info_dev,
+                           collision_dev, ended_dev, (cudaStream_t)stream);
+}
+
+int uavrl_env_step_host(uavrl_env *env, int32_t action_kind, const void *actions_host, float *obs_host,
+                        float *reward_host, uint8_t *done_host, uint8_t *info_host, uint8_t *coll_host,
+                        uint8_t *ended_host)
+{
+    if (!env || !actions_host) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (action_kind < 0 || action_kind > 2) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_step_host before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    const size_t n = (size_t)env->d.n;
+    if (!env->h_act_dev) {
+        UAVRL_CUDA(cudaMalloc(&env->h_act_dev, n * sizeof(double)));
+        UAVRL_CUDA(cudaMalloc((void **)&env->h_obs_dev, n * kObsDim * sizeof(float)));
+        UAVRL_CUDA(cudaMalloc((void **)&env->h_rew_dev, n * sizeof(float)));
+        UAVRL_CUDA(cudaMalloc((void **)&env->h_flags_dev, n * 4));
+    }
+    cudaStream_t st = env->own_stream;
+    const size_t asz = (action_kind == UAVRL_ACT_CONT_F64) ? 8 : 4;
+    UAVRL_CUDA(cudaMemcpyAsync(env->h_act_dev, actions_host, n * asz, cudaMemcpyHostToDevice, st));
+    uint8_t *f = env->h_flags_dev;
+    int rc = launch_env_step(env->d, action_kind, env->h_act_dev, obs_host ? env->h_obs_dev : nullptr,
+                             env->h_rew_dev, f, f + n, f + 2 * n, f + 3 * n, st);
+    if (rc) return rc;
+    if (obs_host) UAVRL_CUDA(cudaMemcpyAsync(obs_host, env->h_obs_dev, n * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (reward_host) UAVRL_CUDA(cudaMemcpyAsync(reward_host, env->h_rew_dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) UAVRL_CUDA(cudaMemcpyAsync(done_host, f, n, cudaMemcpyDeviceToHost, st));
+    if (info_host) UAVRL_CUDA(cudaMemcpyAsync(info_host, f + n, n, cudaMemcpyDeviceToHost, st));
+    if (coll_host) UAVRL_CUDA(cudaMemcpyAsync(coll_host, f + 2 * n, n, cudaMemcpyDeviceToHost, st));
+    if (ended_host) UAVRL_CUDA(cudaMemcpyAsync(ended_host, f + 3 * n, n, cudaMemcpyDeviceToHost, st));
+    UAVRL_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int uavrl_env_get_state(uavrl_env *env, const uavrl_env_state_host *o)
+{
+    if (!env || !o) return fail(UAVRL_ERR_INVALID, "null argument");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    const EnvDev &d = env->d;
+    const size_t n = (size_t)d.n;
+    struct { void *dst; const void *src; size_t sz; } cp[] = {
+        { o->px, d.px, 8 }, { o->py, d.py, 8 }, { o->pz, d.pz, 8 }, { o->vx, d.vx, 8 }, { o->vy, d.vy, 8 },
+        { o->V, d.V, 8 }, { o->score, d.score, 8 }, { o->total_score, d.total, 8 },
+        { o->path_len, d.path_len, 8 }, { o->reward64, d.rew64, 8 }, { o->step, d.step, 4 },
+        { o->cursor, d.cursor, 4 }, { o->scenario, d.scen, 4 }, { o->done, d.done, 1 } };
+    for (auto &c : cp)
+        if (c.dst) UAVRL_CUDA(cudaMemcpy(c.dst, c.src, n * c.sz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_env_threaten_rate(uavrl_env *env, int32_t n, const double *pts_host, uint8_t *out_host)
+{
+    if (!env || n <= 0 || !pts_host || !out_host) return fail(UAVRL_ERR_INVALID, "null/empty argument");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    double *dp = nullptr; uint8_t *dout = nullptr;
+    UAVRL_CUDA(cudaMalloc((void **)&dp, (size_t)n * 3 * sizeof(double)));
+    UAVRL_CUDA(cudaMalloc((void **)&dout, (size_t)n));
+    UAVRL_CUDA(cudaMemcpy(dp, pts_host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    threat_kernel<<<(n + 127) / 128, 128>>>(env->d, n, dp, dout);
+    UAVRL_LAUNCHED();
+    UAVRL_CUDA(cudaMemcpy(out_host, dout, (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(dout);
+    return 0;
+}
+
+}  // extern "C"

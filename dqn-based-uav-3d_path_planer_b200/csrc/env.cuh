@@ -1,0 +1,50 @@
+// env.cuh -- device-side view of a batch of UAV environments (SoA, fp64 state) + host handle.
+#pragma once
+#include "common.cuh"
+#include "env_core.cuh"
+
+namespace uavrl {
+
+constexpr int kEnvsPerBlock = 32;      // one warp steps 32 envs; 4 warps share their 2560 probes
+constexpr int kEnvThreads = 128;
+constexpr int kMaxCyl = 64;            // candidate sets are 64-bit masks
+
+// Everything a kernel needs, passed by value.
+struct EnvDev {
+    EnvConst k;
+    int32_t n, K, P;
+    int32_t auto_reset;
+    double cull_w;                      // half-width of the probe window incl. one step of motion
+    const Cyl *cyl;
+    // per-env state, structure of arrays
+    double *px, *py, *pz, *vx, *vy, *V, *score, *total, *path_len, *gx, *gy, *gz, *rew64;
+    int32_t *step, *cursor, *n_sub, *scen;
+    uint8_t *done, *alias;
+    // scenario pool (read-only during stepping)
+    const double *pool_start, *pool_goal, *pool_v0, *pool_sub;
+    const int32_t *pool_nsub;
+    const uint8_t *pool_alias;
+    // running statistics: [0] env steps, [1] episodes ended, [2] collisions ; sum_reward separately
+    unsigned long long *stat_counts;
+    double *stat_reward;
+};
+
+}  // namespace uavrl
+
+struct uavrl_env {
+    uavrl_env_config cfg;
+    uavrl::EnvDev d;
+    bool pool_set = false, reset_done = false;
+    // staging for the host-buffer entry point
+    void *h_act_dev = nullptr;
+    float *h_obs_dev = nullptr, *h_rew_dev = nullptr;
+    uint8_t *h_flags_dev = nullptr;      // done | info | collision | ended, each [n]
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace uavrl {
+// launched by env.cu and by the fused training loop (train.cu)
+int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
+                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st);
+int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st);
+}  // namespace uavrl

@@ -1,0 +1,273 @@
+// env_core.cuh -- per-UAV step / observation arithmetic of the PathPlan_City hot path.
+//
+// One instance of this code runs per env inside env_step_kernel (env.cu).  It is written as
+// host/device inline functions so the *same source* can also be compiled for the host by the
+// CPU-side logic test (tests/host_shim) and by the host scenario generator's collision test;
+// the product's step path is the CUDA kernel only.
+//
+// Arithmetic contract (DESIGN.md "numerics"): state and reward in fp64 like the Python reference;
+// every +,-,*,/,sqrt that feeds an integer predicate (collision, bounds, termination) is an
+// explicitly rounded IEEE op (no FMA contraction) in the reference's operation order, so given
+// identical inputs the masks are bit-identical to the reference's.  Transcendentals
+// (atan2/sin/cos) come from the CUDA math library (<= 2 ulp from glibc's): positions agree to
+// ~1e-15 relative, far inside the 1e-5 tolerance.
+//
+// Reference: Agents/UAV.py:397-567, Envs/PathPlan_City.py:215-223, Obstacles/building.py:20-26,
+// BaseClass/CalMod.py:64-65,89-102.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define UAVRL_HD __host__ __device__ __forceinline__
+#else
+#define UAVRL_HD inline
+#endif
+
+namespace uavrl {
+
+#if defined(__CUDA_ARCH__)
+UAVRL_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+UAVRL_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+UAVRL_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+UAVRL_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+UAVRL_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+#else
+// host build: compiled with -ffp-contract=off
+UAVRL_HD double dadd(double a, double b) { return a + b; }
+UAVRL_HD double dsub(double a, double b) { return a - b; }
+UAVRL_HD double dmul(double a, double b) { return a * b; }
+UAVRL_HD double ddiv(double a, double b) { return a / b; }
+UAVRL_HD double dsqrt(double a) { return sqrt(a); }
+#endif
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr int kObsDim = 100;
+
+struct Cyl {            // building.py:8-11 plus a guard band around R^2 for the sqrt-free fast path
+    double cx, cy, R, H, r2lo, r2hi;
+};
+
+struct EnvConst {
+    double width, h;                    // PathPlan_City.py:218 tests x AND y against `width`
+    double max_v, min_v, steering, climb;
+    int32_t max_step;
+    int32_t n_cyl;
+};
+
+struct EnvRegs {
+    double px, py, pz, vx, vy, V, score, total, path_len, gx, gy, gz;
+    int32_t step, cursor, n_sub;
+    int32_t done, alias;
+};
+
+struct StepOut {
+    double reward;
+    int32_t done_ret, info, coll;
+};
+
+struct P3 { double x, y, z; };
+
+// CalMod.py:64-65  sqrt((dx)**2 + (dy)**2 + (dz)**2), left-to-right
+UAVRL_HD double dist3(double ax, double ay, double az, double bx, double by, double bz)
+{
+    const double dx = dsub(ax, bx), dy = dsub(ay, by), dz = dsub(az, bz);
+    return dsqrt(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
+}
+
+// CalMod.py:89-102 (mod=1): atan2 -> degrees -> (a + 360) % 360 / 180 * pi.
+// a+360 lies in [180,540], where Python's float % 360 is exactly "subtract 360 if >= 360".
+UAVRL_HD double angle_xy(double dx, double dy)
+{
+    double a = atan2(dy, dx);
+    a = dmul(a, 180.0 / kPi);
+    double t = dadd(a, 360.0);
+    t = (t >= 360.0) ? dsub(t, 360.0) : t;
+    return dmul(ddiv(t, 180.0), kPi);
+}
+
+// building.py:20-26 -- strict `z > H` and strict `dist < R`
+UAVRL_HD int cyl_hit(const Cyl &c, double x, double y, double z)
+{
+    if (z > c.H) return 0;
+    const double dx = dsub(x, c.cx), dy = dsub(y, c.cy);
+    const double s = dadd(dmul(dx, dx), dmul(dy, dy));      // (+ 0.0**2 for the z term: exact no-op)
+    if (s < c.r2lo) return 1;
+    if (s > c.r2hi) return 0;
+    return dsqrt(s) < c.R;                                   // the reference's exact predicate
+}
+
+// PathPlan_City.py:218 (inclusive upper bounds, y against width)
+UAVRL_HD int out_of_bounds(const EnvConst &k, double x, double y, double z)
+{
+    return (x < 0.0) | (x > k.width) | (y < 0.0) | (y > k.width) | (z < 0.0) | (z > k.h);
+}
+
+// UAV.py:246-253 Calc_V
+UAVRL_HD double calc_v(const EnvConst &k, double &vx, double &vy)
+{
+    double V = dsqrt(dadd(dadd(dmul(vx, vx), dmul(vy, vy)), 0.0));
+    if (V > k.max_v) {
+        const double f = ddiv(k.max_v, V);
+        vx = dmul(vx, f);
+        vy = dmul(vy, f);
+        V = k.max_v;
+    }
+    return V;
+}
+
+// UAV.py:397-513 update_PathPlan.  sub(i) returns entry i of this env's sub-goal queue;
+// threat(x,y,z) is PathPlan_City.Threaten_rate.  act_mode: 0 continuous (action = a0), 1 discrete-27.
+template <class SubFn, class ThreatFn>
+UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double action, SubFn sub,
+                        ThreatFn threat, StepOut &o)
+{
+    double r = 0.0;
+    o.coll = 0;
+    if (s.n_sub - s.cursor == 0) {                                   // :400-406
+        s.done = 1;
+        r = dadd(r, (double)(k.max_step - s.step));
+        s.score = dadd(s.score, r);
+        o.reward = r; o.done_ret = 1; o.info = 1;
+        return;
+    }
+    double a0 = action, dz = 0.0, speed = k.max_v;
+    if (act_mode == 1) {
+        const int kk = (int)action;
+        const int i = kk / 9, j = (kk / 3) % 3, l = kk % 3;
+        a0 = (double)(i - 1);
+        dz = dmul((double)(j - 1), k.climb);
+        speed = (l == 0) ? k.min_v : (l == 1) ? ddiv(dadd(k.min_v, k.max_v), 2.0) : k.max_v;
+    }
+    const bool alias = s.alias && s.cursor == 0;                     // sub_goals[0] IS position (RRT.py:69)
+    P3 sg = sub(s.cursor);
+    if (alias) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }
+
+    s.step += 1;                                                     // :408
+    const double ox = s.px, oy = s.py, oz = s.pz;                    // :409
+    const double seta_old = angle_xy(s.vx, s.vy);                    // :411
+    const double dis_old = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);        // :412
+    const double dg_old = dist3(s.px, s.py, s.pz, s.gx, s.gy, s.gz);         // :413
+    const double seta_new = dadd(seta_old, dmul(a0, k.steering));    // :414
+    double sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincos(seta_new, &sn, &cs);
+#else
+    sn = sin(seta_new); cs = cos(seta_new);
+#endif
+    s.vx = dmul(speed, cs);                                          // :415
+    s.vy = dmul(speed, sn);                                          // :416
+    s.V = calc_v(k, s.vx, s.vy);                                     // :417
+    s.px = dadd(s.px, s.vx);                                         // :419
+    s.py = dadd(s.py, s.vy);                                         // :420
+    if (act_mode == 1) s.pz = dadd(s.pz, dz);
+    if (alias) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }            // the aliased sub-goal moved too
+    const double tri_goal = angle_xy(dsub(sg.x, s.px), dsub(sg.y, s.py));    // :422
+    double tri_V = angle_xy(s.vx, s.vy);                             // :423
+    if (threat(s.px, s.py, s.pz)) {                                  // :425
+        r = dsub(r, 0.3);
+        s.px = ox; s.py = oy; s.pz = oz;                             // :427
+        tri_V = angle_xy(dsub(sg.x, s.px), dsub(sg.y, s.py));        // :428
+        o.coll = 1;
+    }
+    const double dis_new = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);        // :429
+    const double dg_new = dist3(s.px, s.py, s.pz, s.gx, s.gy, s.gz);         // :430
+    r = dsub(r, dmul(0.13, fabs(a0)));                               // :434
+    r = dadd(r, dmul(0.2, cos(fabs(dsub(tri_goal, tri_V)))));        // :435
+    r = dadd(r, dmul(0.4, dsub(dis_old, dis_new)));                  // :436
+    r = dadd(r, dmul(0.4, dsub(dg_old, dg_new)));                    // :437
+    r = dsub(r, 0.1);                                                // :438
+    r = dsub(r, dmul(0.01, fabs(dsub(s.pz, sg.z))));                 // :440
+    s.path_len = dadd(s.path_len, s.V);                              // :443
+    // :448-453 APF: zero-velocity obstacles are skipped (UAV.py:180-182) -> the term is exactly 0.
+
+    if (s.step >= k.max_step) {                                      // :456-465
+        s.done = 1;
+        r = dadd(r, dsub(50.0, dis_new));
+        s.score = dadd(s.score, r); s.total = dadd(s.total, r);
+        o.reward = r; o.done_ret = 1; o.info = 2;
+    } else if (dis_new < 7.0 || dg_new < dist3(sg.x, sg.y, sg.z, s.gx, s.gy, s.gz)) {   // :466
+        r = dadd(r, dsub(50.0, dis_new));                            // :468
+        s.cursor += 1;                                               // :469
+        if (s.n_sub - s.cursor == 0) {                               // :470-483
+            r = dadd(r, 50.0);
+            s.done = 1;
+            r = dadd(r, (double)(k.max_step - s.step));
+            s.score = dadd(s.score, r); s.total = dadd(s.total, r);
+            o.reward = r; o.done_ret = 1; o.info = 1;
+        } else {                                                     // :484-495
+            s.step = 0; s.score = 0.0;                               // local reset :329-332
+            s.V = calc_v(k, s.vx, s.vy);
+            const P3 ng = sub(s.cursor);
+            const double tg = angle_xy(dsub(ng.x, s.px), dsub(ng.y, s.py));   // :488
+            const double tv = angle_xy(s.vx, s.vy);                  // :489
+            r = dadd(r, dmul(0.2, cos(fabs(dsub(tg, tv)))));         // :490
+            r = dadd(r, (double)(k.max_step - s.step));              // :491
+            s.score = dadd(s.score, r); s.total = dadd(s.total, r);
+            o.reward = r; o.done_ret = 1; o.info = 1;
+        }
+    } else if (dg_new < 7.0) {                                       // :496-509
+        s.done = 1;
+        r = dadd(r, 50.0);
+        r = dadd(r, (double)(k.max_step - s.step));
+        s.score = dadd(s.score, r); s.total = dadd(s.total, r);
+        o.reward = r; o.done_ret = 1; o.info = 1;
+    } else {                                                         // :510-513
+        s.score = dadd(s.score, r); s.total = dadd(s.total, r);
+        o.reward = r; o.done_ret = 0; o.info = 0;
+    }
+    s.alias = 0;
+}
+
+// UAV.py:515-531,557-560: the 20 real-valued entries of the observation (probes are separate).
+// `o` points at this env's 100 floats (stride 1).
+template <class SubFn>
+UAVRL_HD void obs_scalars(const EnvRegs &s, SubFn sub, float *o)
+{
+    const int nleft = s.n_sub - s.cursor;
+    o[0] = (float)ddiv((double)s.step, 100.0);                       // :518
+    float o1 = 0.f, o2 = 0.f, o3 = 0.f, o8 = 0.f, o9 = 0.f, o10 = 0.f;
+    if (nleft >= 1) {                                                // :519-522
+        P3 sg = sub(s.cursor);
+        if (s.alias && s.cursor == 0) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }
+        o1 = (float)ddiv(dsub(sg.x, s.px), 10.0);
+        o2 = (float)ddiv(dsub(sg.y, s.py), 10.0);
+        o3 = (float)ddiv(dsub(sg.z, s.pz), 10.0);
+    }
+    if (nleft >= 2) {                                                // :528-531
+        const P3 s1 = sub(s.cursor + 1);
+        o8 = (float)ddiv(dsub(s1.x, s.px), 10.0);
+        o9 = (float)ddiv(dsub(s1.y, s.py), 10.0);
+        o10 = (float)ddiv(dsub(s1.z, s.pz), 10.0);
+    }
+    o[1] = o1; o[2] = o2; o[3] = o3;
+    o[4] = (float)s.V;                                               // :523
+    o[5] = (float)s.vx; o[6] = (float)s.vy;
+    o[7] = (float)angle_xy(s.vx, s.vy);                              // :526
+    o[8] = o8; o[9] = o9; o[10] = o10;
+    o[86] = (float)ddiv(dsub(s.gx, s.px), 10.0);                     // :557-559
+    o[87] = (float)ddiv(dsub(s.gy, s.py), 10.0);
+    o[88] = (float)ddiv(dsub(s.gz, s.pz), 10.0);
+    o[89] = (float)ddiv(s.pz, 10.0);                                 // :560
+    o[95] = 0.f; o[96] = 0.f; o[97] = 0.f; o[98] = 0.f; o[99] = 0.f;
+}
+
+// probe p in 0..79 -> test point and observation slot (UAV.py:533-555,562-566)
+UAVRL_HD void probe_point(int p, double px, double py, double pz, double &x, double &y, double &z, int &slot)
+{
+    if (p < 75) {
+        const int g = p / 25, ij = p - 25 * g, i = ij / 5, j = ij - 5 * i;
+        const int sc = (g == 0) ? 1 : (g == 1) ? 5 : 10;
+        x = dadd(px, (double)(sc * (i - 2)));
+        y = dadd(py, (double)(sc * (j - 2)));
+        z = pz;
+        slot = 11 + p;
+    } else {
+        const int kdn = p - 75;
+        x = px; y = py;
+        z = dsub(pz, (double)(kdn + 1));
+        slot = 90 + kdn;
+    }
+}
+
+}  // namespace uavrl

@@ -1,0 +1,891 @@
+// learner.cu -- DQN-family learner on device: Q-net forward + eps-greedy, replay ring, sampled
+// TD update (forward local/target, MSE, backward), Adam, hard target update.  sm_100a.
+//
+// Replaces:
+//   Trainer.get_action        Trainer/DuelingDQN_Trainer.py:86-97
+//   ReplayMemory.add/sample2  BaseClass/replay_buffer.py:41-51
+//   Trainer.update            Trainer/DuelingDQN_Trainer.py:150-190, Trainer/DDQN_Trainer.py:72-117,
+//                             Trainer/DQN_Trainer.py:85-136
+//   networks                  BaseClass/BaseCNN.py:93-102,120-217,329-343
+//   torch.optim.Adam step + hard_update (DuelingDQN_Trainer.py:176-184,199-202)
+//
+// This file is the fp32 CUDA-core path: the whole network (<= 23 k parameters) is staged TRANSPOSED in
+// shared memory once per CTA, a CTA owns a tile of 32 samples, lanes walk output units and each
+// warp carries 4 samples, so every weight fetch is a conflict-free LDS and every activation fetch
+// a broadcast LDS.128.  Gradients leave the CTA as one coalesced partial vector; the optimiser
+// kernel reduces the partials in a fixed order (deterministic) and applies Adam.
+#include "learner.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+namespace uavrl {
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ network description (host)
+static int build_net(const uavrl_learner_config &c, NetDev &n)
+{
+    memset(&n, 0, sizeof(n));
+    if (c.in_dim <= 0 || c.in_dim > kMaxDim) return fail(UAVRL_ERR_INVALID, "in_dim must be in [1,128]");
+    if (c.n_hidden < 1 || c.n_hidden > UAVRL_MAX_HIDDEN) return fail(UAVRL_ERR_INVALID, "n_hidden must be in [1,4]");
+    if (c.n_actions < 1 || c.n_actions > 31) return fail(UAVRL_ERR_INVALID, "n_actions must be in [1,31]");
+    n.in_dim = c.in_dim; n.n_actions = c.n_actions; n.dueling = c.dueling ? 1 : 0;
+    n.n_layers = c.n_hidden + 1;
+    int in = c.in_dim, poff = 0, soff = 0;
+    for (int l = 0; l < n.n_layers; ++l) {
+        LayerDev &L = n.L[l];
+        const bool head = (l == c.n_hidden);
+        const int out_real = head ? c.n_actions : c.hidden[l];
+        if (out_real <= 0 || out_real > kMaxDim) return fail(UAVRL_ERR_INVALID, "hidden width must be in [1,128]");
+        L.in = in;
+        L.out = out_real + ((head && n.dueling) ? 1 : 0);
+        L.w_off = poff; poff += out_real * in;
+        L.b_off = poff; poff += out_real;
+        L.w2_off = L.b2_off = -1;
+        if (head && n.dueling) { L.w2_off = poff; poff += in; L.b2_off = poff; poff += 1; }
+        const int ldw = (L.out % 2 == 0) ? L.out + 1 : L.out;
+        L.smem_w = soff; soff += round_up(in, 4) * ldw;
+        L.smem_b = soff; soff += round_up(L.out, 4);
+        in = out_real;
+    }
+    n.P = poff;
+    n.smem_w_floats = round_up(soff, 4);
+    int off = n.smem_w_floats;
+    // activation planes: X0 (input), H1..Hn (trunk outputs); ld = round_up(dim,32)
+    for (int i = 0; i <= c.n_hidden; ++i) {
+        const int dim = (i == 0) ? c.in_dim : c.hidden[i - 1];
+        n.act_ld[i] = round_up(dim, 32);
+        n.act_off[i] = off; off += kTile * n.act_ld[i];
+    }
+    n.smem_total_floats = off;   // kernels append their own extra planes after this
+    return 0;
+}
+
+// ------------------------------------------------------------------ device building blocks
+__device__ __forceinline__ int ldw_of(int out) { return (out & 1) ? out : out + 1; }
+
+// Stage one network's weights into smem, transposed: Wt[k][o] = W[o][k]; pad rows (k >= in) zeroed.
+__device__ void load_weights(const NetDev &net, const float *__restrict__ params, float *sw)
+{
+    for (int l = 0; l < net.n_layers; ++l) {
+        const LayerDev &L = net.L[l];
+        const int ldw = ldw_of(L.out), in = L.in, in_pad = round_up(in, 4);
+        const int out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
+        float *Wt = sw + L.smem_w, *bs = sw + L.smem_b;
+        for (int i = threadIdx.x; i < out_main * in; i += blockDim.x) {
+            const int o = i / in, k = i - o * in;
+            Wt[k * ldw + o] = params[L.w_off + i];
+        }
+        if (L.w2_off >= 0)
+            for (int k = threadIdx.x; k < in; k += blockDim.x) Wt[k * ldw + out_main] = params[L.w2_off + k];
+        for (int i = threadIdx.x; i < (in_pad - in) * ldw; i += blockDim.x) Wt[in * ldw + i] = 0.f;
+        for (int o = threadIdx.x; o < out_main; o += blockDim.x) bs[o] = params[L.b_off + o];
+        if (L.w2_off >= 0 && threadIdx.x == 0) bs[out_main] = params[L.b2_off];
+    }
+}
+
+// Y[b][o] = act(sum_k X[b][k] * Wt[k][o] + bias[o]), b < 32.  lane -> o, warp -> 4 samples.
+__device__ void layer_forward(const float *__restrict__ X, int ldx, const float *__restrict__ Wt,
+                              const float *__restrict__ bias, float *__restrict__ Y, int ldy, int in,
+                              int out, bool relu)
+{
+    const int lane = threadIdx.x & 31, b0 = (threadIdx.x >> 5) * 4;
+    const int ldw = ldw_of(out), in_pad = round_up(in, 4);
+    for (int oc = 0; oc < out; oc += 64) {
+        const int o0 = oc + lane, o1 = oc + lane + 32;
+        const bool v0 = o0 < out, v1 = o1 < out;
+        const int c0 = v0 ? o0 : 0, c1 = v1 ? o1 : 0;
+        float acc[4][2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[b][0] = 0.f; acc[b][1] = 0.f; }
+        for (int k = 0; k < in_pad; k += 4) {
+            float4 x[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[b] = *reinterpret_cast<const float4 *>(X + (b0 + b) * ldx + k);
+            float w0[4], w1[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) { w0[kk] = Wt[(k + kk) * ldw + c0]; w1[kk] = Wt[(k + kk) * ldw + c1]; }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                acc[b][0] = fmaf(x[b].x, w0[0], acc[b][0]); acc[b][1] = fmaf(x[b].x, w1[0], acc[b][1]);
+                acc[b][0] = fmaf(x[b].y, w0[1], acc[b][0]); acc[b][1] = fmaf(x[b].y, w1[1], acc[b][1]);
+                acc[b][0] = fmaf(x[b].z, w0[2], acc[b][0]); acc[b][1] = fmaf(x[b].z, w1[2], acc[b][1]);
+                acc[b][0] = fmaf(x[b].w, w0[3], acc[b][0]); acc[b][1] = fmaf(x[b].w, w1[3], acc[b][1]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (v0) { float y = acc[b][0] + bias[o0]; Y[(b0 + b) * ldy + o0] = (relu && y < 0.f) ? 0.f : y; }
+            if (v1) { float y = acc[b][1] + bias[o1]; Y[(b0 + b) * ldy + o1] = (relu && y < 0.f) ? 0.f : y; }
+        }
+    }
+    // the next layer reads round_up(out,4) columns with 16-byte loads: keep the pad columns zero
+    const int pad = round_up(out, 4) - out;
+    if (lane < pad)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Y[(b0 + b) * ldy + out + lane] = 0.f;
+}
+
+// dX[b][k] = (sum_o dY[b][o] * Wt[k][o]) * (Xact[b][k] > 0).  lane -> k, warp -> 4 samples.
+// dY columns [out, round_up(out,4)) must be zero.
+__device__ void layer_backward_dx(const float *__restrict__ dY, int lddy, const float *__restrict__ Wt,
+                                  const float *__restrict__ Xact, int ldx, float *__restrict__ dX,
+                                  int lddx, int in, int out)
+{
+    const int lane = threadIdx.x & 31, b0 = (threadIdx.x >> 5) * 4;
+    const int ldw = ldw_of(out), out4 = round_up(out, 4);
+    for (int kc = 0; kc < in; kc += 64) {
+        const int k0 = kc + lane, k1 = kc + lane + 32;
+        const bool v0 = k0 < in, v1 = k1 < in;
+        const int c0 = v0 ? k0 : 0, c1 = v1 ? k1 : 0;
+        float acc[4][2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[b][0] = 0.f; acc[b][1] = 0.f; }
+        for (int o = 0; o < out4; o += 4) {
+            float4 dy[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dy[b] = *reinterpret_cast<const float4 *>(dY + (b0 + b) * lddy + o);
+            float w0[4], w1[4];
+#pragma unroll
+            for (int oo = 0; oo < 4; ++oo) {
+                const bool vo = (o + oo) < out;
+                w0[oo] = vo ? Wt[c0 * ldw + o + oo] : 0.f;
+                w1[oo] = vo ? Wt[c1 * ldw + o + oo] : 0.f;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                acc[b][0] = fmaf(dy[b].x, w0[0], acc[b][0]); acc[b][1] = fmaf(dy[b].x, w1[0], acc[b][1]);
+                acc[b][0] = fmaf(dy[b].y, w0[1], acc[b][0]); acc[b][1] = fmaf(dy[b].y, w1[1], acc[b][1]);
+                acc[b][0] = fmaf(dy[b].z, w0[2], acc[b][0]); acc[b][1] = fmaf(dy[b].z, w1[2], acc[b][1]);
+                acc[b][0] = fmaf(dy[b].w, w0[3], acc[b][0]); acc[b][1] = fmaf(dy[b].w, w1[3], acc[b][1]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (v0) dX[(b0 + b) * lddx + k0] = (Xact[(b0 + b) * ldx + k0] > 0.f) ? acc[b][0] : 0.f;
+            if (v1) dX[(b0 + b) * lddx + k1] = (Xact[(b0 + b) * ldx + k1] > 0.f) ? acc[b][1] : 0.f;
+        }
+    }
+}
+
+// gW[o][k] (+)= sum_b dY[b][o] * X[b][k];  gb[o] (+)= sum_b dY[b][o], into this CTA's partial vector.
+// k = tid % 128, two 16-row groups per pass.  dY must be zero in columns [out, round_up(out,32)).
+__device__ void layer_backward_dw(const float *__restrict__ dY, int lddy, const float *__restrict__ X,
+                                  int ldx, float *__restrict__ gpart, const LayerDev &L, bool accumulate)
+{
+    const int in = L.in, out = L.out;
+    const int out_main = (L.w2_off >= 0) ? out - 1 : out;
+    const int k = threadIdx.x & 127, og = threadIdx.x >> 7;
+    const bool kv = k < in;
+    for (int oc = 0; oc < out; oc += 32) {
+        const int obase = oc + og * 16;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        if (kv && obase < out) {
+            for (int b = 0; b < kTile; ++b) {
+                const float x = X[b * ldx + k];
+                const float4 *dy = reinterpret_cast<const float4 *>(dY + b * lddy + obase);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 d = dy[q];
+                    acc[4 * q + 0] = fmaf(d.x, x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(d.y, x, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(d.z, x, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(d.w, x, acc[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int o = obase + j;
+                if (o < out) {
+                    float *dst = (o < out_main) ? gpart + L.w_off + o * in + k : gpart + L.w2_off + k;
+                    *dst = accumulate ? *dst + acc[j] : acc[j];
+                }
+            }
+        }
+    }
+    for (int o = threadIdx.x; o < out; o += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < kTile; ++b) s += dY[b * lddy + o];
+        float *dst = (o < out_main) ? gpart + L.b_off + o : gpart + L.b2_off;
+        *dst = accumulate ? *dst + s : s;
+    }
+}
+
+// Full forward of one network over the 32-sample tile in plane 0.  keep_planes: trunk outputs go to
+// planes 1..n (kept for backward); otherwise they ping-pong through scratch planes sA/sB.
+// Raw head output (A rows + V row when dueling) lands in `head` [32][32]; then Q is formed in place.
+__device__ void net_forward(const NetDev &net, const float *sw, const float *X0, int ld0, float *smem,
+                            bool keep_planes, float *sA, float *sB, float *head)
+{
+    const float *cur = X0; int ldc = ld0;
+    const int nh = net.n_layers - 1;
+    for (int l = 0; l < nh; ++l) {
+        const LayerDev &L = net.L[l];
+        float *dst; int ldd;
+        if (keep_planes) { dst = smem + net.act_off[l + 1]; ldd = net.act_ld[l + 1]; }
+        else { dst = (l & 1) ? sB : sA; ldd = kMaxDim; }
+        layer_forward(cur, ldc, sw + L.smem_w, sw + L.smem_b, dst, ldd, L.in, L.out, true);
+        __syncthreads();
+        cur = dst; ldc = ldd;
+    }
+    const LayerDev &H = net.L[nh];
+    layer_forward(cur, ldc, sw + H.smem_w, sw + H.smem_b, head, 32, H.in, H.out, false);
+    __syncthreads();
+    if (net.dueling) {                                   // Q = V + A - mean(A)   (BaseCNN.py:138)
+        if (threadIdx.x < kTile) {
+            float *row = head + threadIdx.x * 32;
+            const int nA = net.n_actions;
+            float s = 0.f;
+            for (int a = 0; a < nA; ++a) s += row[a];
+            const float mean = s / (float)nA, V = row[nA];
+            for (int a = 0; a < nA; ++a) row[a] = V + row[a] - mean;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int argmax_row(const float *row, int n)
+{
+    int best = 0; float bv = row[0];
+    for (int a = 1; a < n; ++a) if (row[a] > bv) { bv = row[a]; best = a; }
+    return best;
+}
+
+// load 32 rows of `in` floats (row pointers in rows[]; nullptr -> zeros) into a plane, 16-byte loads
+__device__ void load_rows(const float *const *rows, float *plane, int ld, int in)
+{
+    const int vec = in / 4;           // in % 4 == 0 is checked on the host for the vector path
+    for (int i = threadIdx.x; i < kTile * vec; i += blockDim.x) {
+        const int b = i / vec, q = i - b * vec;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rows[b]) v = __ldg(reinterpret_cast<const float4 *>(rows[b]) + q);
+        *reinterpret_cast<float4 *>(plane + b * ld + 4 * q) = v;
+    }
+    const int in_pad = round_up(in, 4);
+    if (in_pad != in)
+        for (int i = threadIdx.x; i < kTile * (in_pad - in); i += blockDim.x)
+            plane[(i / (in_pad - in)) * ld + in + i % (in_pad - in)] = 0.f;
+}
+
+// scalar variant for in % 4 != 0
+__device__ void load_rows_scalar(const float *const *rows, float *plane, int ld, int in)
+{
+    const int in_pad = round_up(in, 4);
+    for (int i = threadIdx.x; i < kTile * in_pad; i += blockDim.x) {
+        const int b = i / in_pad, k = i - b * in_pad;
+        plane[b * ld + k] = (rows[b] && k < in) ? rows[b][k] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ eps-greedy action kernel
+__global__ void __launch_bounds__(kNetThreads)
+act_kernel(NetDev net, const float *__restrict__ params, const float *__restrict__ obs, int n, float eps,
+           int is_train, const float *__restrict__ u_tape, const int32_t *__restrict__ rand_tape,
+           uint64_t key, uint64_t call, int32_t *__restrict__ actions, int32_t *__restrict__ actions2,
+           float *__restrict__ q_out, int n_tiles)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;
+    float *sA = smem + net.smem_total_floats;
+    float *sB = sA + kTile * kMaxDim;
+    float *head = sB + kTile * kMaxDim;
+    __shared__ const float *rows[kTile];
+    load_weights(net, params, sw);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int e0 = t * kTile;
+        if (threadIdx.x < kTile) rows[threadIdx.x] = (e0 + threadIdx.x < n) ? obs + (size_t)(e0 + threadIdx.x) * net.in_dim : nullptr;
+        __syncthreads();
+        if (net.in_dim % 4 == 0) load_rows(rows, smem + net.act_off[0], net.act_ld[0], net.in_dim);
+        else load_rows_scalar(rows, smem + net.act_off[0], net.act_ld[0], net.in_dim);
+        __syncthreads();
+        net_forward(net, sw, smem + net.act_off[0], net.act_ld[0], smem, false, sA, sB, head);
+        if (threadIdx.x < kTile && e0 + threadIdx.x < n) {
+            const int e = e0 + threadIdx.x;
+            const float *row = head + threadIdx.x * 32;
+            float u; int ra;
+            if (u_tape) { u = u_tape[e]; ra = rand_tape ? rand_tape[e] : 0; }
+            else {
+                uint32_t r[4];
+                Philox::gen(key, call, (uint64_t)e, r);
+                u = Philox::u01(r[0]);
+                ra = (int)(((uint64_t)r[1] * (uint64_t)net.n_actions) >> 32);
+            }
+            // DuelingDQN_Trainer.py:89-97: sample > eps or not training -> greedy, else random
+            const int a = (u > eps || !is_train) ? argmax_row(row, net.n_actions) : ra;
+            actions[e] = a;
+            if (actions2) actions2[e] = a;
+            if (q_out) for (int k = 0; k < net.n_actions; ++k) q_out[(size_t)e * net.n_actions + k] = row[k];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ replay index sampling
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// i-th element of a keyed pseudo-random permutation of [0, M): 4-round Feistel on 2*h bits with
+// cycle walking.  perm(0..B-1) = B distinct uniform indices = random.sample(range(M), B)
+// (BaseClass/replay_buffer.py:49).
+__device__ uint64_t perm_index(uint64_t i, uint64_t M, const uint32_t key[4])
+{
+    int bits = 1;
+    while ((1ull << bits) < M) ++bits;
+    const int h = (bits + 1) / 2;
+    const uint32_t mask = (h >= 32) ? 0xffffffffu : ((1u << h) - 1u);
+    uint64_t x = i;
+    do {
+        uint32_t Lh = (uint32_t)(x >> h) & mask, Rh = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t f = mix32(Rh ^ key[r]) & mask;
+            const uint32_t nl = Rh;
+            Rh = Lh ^ f;
+            Lh = nl;
+        }
+        x = ((uint64_t)Lh << h) | Rh;
+    } while (x >= M);
+    return x;
+}
+
+// ------------------------------------------------------------------ TD update kernel
+struct UpdateArgs {
+    const float *local, *target;
+    float *partials, *loss_partials;
+    int B, n_tiles, algo;
+    float gamma, inv_global_b;
+};
+
+__global__ void __launch_bounds__(kNetThreads)
+update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;
+    float *X0 = smem + net.act_off[0];
+    const int ld0 = net.act_ld[0];
+    float *X2 = smem + net.smem_total_floats;            // next-state plane
+    float *sA = X2 + kTile * ld0;                        // scratch / gradient ping
+    float *sB = sA + kTile * kMaxDim;                    // scratch / gradient pong
+    float *Q = sB + kTile * kMaxDim;                     // [32][32] Q_local(s)
+    float *Qt = Q + kTile * 32;                          // [32][32] Q_target(s')
+    float *Ql2 = Qt + kTile * 32;                        // [32][32] Q_local(s')
+    __shared__ const float *rows_s[kTile];
+    __shared__ const float *rows_s2[kTile];
+    __shared__ int s_act[kTile];
+    __shared__ float s_rew[kTile], s_done[kTile], s_loss[kTile];
+
+    float *gpart = ua.partials + (size_t)blockIdx.x * net.P;
+    float loss_acc = 0.f;
+    int iter = 0;
+    uint32_t pkey[4];
+    Philox::gen(src.key, src.epoch, 0x5A17ull, pkey);
+
+    for (int t = blockIdx.x; t < ua.n_tiles; t += gridDim.x, ++iter) {
+        // ---- resolve the tile's transitions
+        if (threadIdx.x < kTile) {
+            const int gb = t * kTile + threadIdx.x;
+            const float *ps = nullptr, *ps2 = nullptr;
+            int a = 0; float r = 0.f, d = 0.f;
+            if (gb < ua.B) {
+                if (src.mode == kBatchExplicit) {
+                    ps = src.frames + (size_t)gb * net.in_dim;
+                    ps2 = src.s2_rows + (size_t)gb * net.in_dim;
+                    a = src.act[gb]; r = src.rew[gb]; d = src.done_f32[gb];
+                } else {
+                    const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb]
+                                                    : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
+                    int64_t slot, row, row2;
+                    if (src.mode == kReplayLockstep) {
+                        const int64_t f = (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
+                        const int64_t e = (int64_t)(j % src.n_envs);
+                        slot = f * src.n_envs + e; row = slot;
+                        row2 = ((f + 1) % src.cap) * src.n_envs + e;
+                    } else {
+                        slot = (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+                    }
+                    ps = src.frames + (size_t)row * net.in_dim;
+                    ps2 = src.frames + (size_t)row2 * net.in_dim;
+                    a = src.act[slot]; r = src.rew[slot]; d = src.done_u8[slot] ? 1.f : 0.f;
+                }
+            }
+            rows_s[threadIdx.x] = ps; rows_s2[threadIdx.x] = ps2;
+            s_act[threadIdx.x] = a; s_rew[threadIdx.x] = r; s_done[threadIdx.x] = d;
+        }
+        __syncthreads();
+        if (net.in_dim % 4 == 0) { load_rows(rows_s, X0, ld0, net.in_dim); load_rows(rows_s2, X2, ld0, net.in_dim); }
+        else { load_rows_scalar(rows_s, X0, ld0, net.in_dim); load_rows_scalar(rows_s2, X2, ld0, net.in_dim); }
+        // ---- target network on s'
+        load_weights(net, ua.target, sw);
+        __syncthreads();
+        net_forward(net, sw, X2, ld0, smem, false, sA, sB, Qt);
+        // ---- local network on s' (double-DQN action selection) and on s (kept for backward)
+        load_weights(net, ua.local, sw);
+        __syncthreads();
+        if (ua.algo != UAVRL_ALGO_DQN) net_forward(net, sw, X2, ld0, smem, false, sA, sB, Ql2);
+        net_forward(net, sw, X0, ld0, smem, true, sA, sB, Q);
+        // ---- TD target, loss, dLoss/dHead  (head gradient plane = sA, [32][kMaxDim], zero padded)
+        const int nA = net.n_actions;
+        const LayerDev &H = net.L[net.n_layers - 1];
+        if (threadIdx.x < kTile) {
+            const int b = threadIdx.x;
+            float *g = sA + b * kMaxDim;
+            for (int o = 0; o < 32; ++o) g[o] = 0.f;
+            float lossb = 0.f;
+            if (t * kTile + b < ua.B) {
+                const float *qt = Qt + b * 32;
+                float nq;
+                if (ua.algo == UAVRL_ALGO_DQN) nq = qt[argmax_row(qt, nA)];           // DQN_Trainer.py:109
+                else nq = qt[argmax_row(Ql2 + b * 32, nA)];                          // DDQN_Trainer.py:94-95
+                const float y = s_rew[b] + (ua.gamma * nq * (1.f - s_done[b]));      // :99 / :114 / :171
+                const int a = s_act[b];
+                const float diff = Q[b * 32 + a] - y;
+                lossb = diff * diff;
+                const float gq = 2.f * diff * ua.inv_global_b;
+                if (net.dueling) {
+                    const float inv = 1.f / (float)nA;
+                    for (int o = 0; o < nA; ++o) g[o] = gq * ((o == a ? 1.f : 0.f) - inv);
+                    g[nA] = gq;
+                } else {
+                    g[a] = gq;
+                }
+            }
+            s_loss[b] = lossb;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { float s = 0.f; for (int b = 0; b < kTile; ++b) s += s_loss[b]; loss_acc += s; }
+        // ---- backward, head first.  gradient planes ping-pong sA <-> sB
+        float *dY = sA, *dXb = sB;
+        for (int l = net.n_layers - 1; l >= 0; --l) {
+            const LayerDev &L = net.L[l];
+            const float *Xin = smem + net.act_off[l];
+            const int ldx = net.act_ld[l];
+            layer_backward_dw(dY, kMaxDim, Xin, ldx, gpart, L, iter > 0);
+            if (l > 0) {
+                layer_backward_dx(dY, kMaxDim, sw + L.smem_w, Xin, ldx, dXb, kMaxDim, L.in, L.out);
+                // zero the pad columns [in, round_up(in,32)) the next dW pass will read
+                const int pad0 = L.in, pad1 = round_up(L.in, 32);
+                for (int i = threadIdx.x; i < kTile * (pad1 - pad0); i += blockDim.x)
+                    dXb[(i / (pad1 - pad0)) * kMaxDim + pad0 + i % (pad1 - pad0)] = 0.f;
+            }
+            __syncthreads();
+            float *tmp = dY; dY = dXb; dXb = tmp;
+        }
+        (void)H;
+    }
+    if (threadIdx.x == 0) ua.loss_partials[blockIdx.x] = loss_acc;
+}
+
+// ------------------------------------------------------------------ reduce partials + Adam + target copy
+struct AdamArgs {
+    int P, nparts, apply, hard, world;
+    float step_size, beta1_c, beta2, beta2_c, eps, bc2_sqrt, inv_b;
+};
+
+__global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
+                                   float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m,
+                                   float *__restrict__ v, float *__restrict__ target, float *__restrict__ loss_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.P) {
+        float g;
+        if (a.nparts > 0) {
+            g = 0.f;
+            for (int c = 0; c < a.nparts; ++c) g += partials[(size_t)c * a.P + i];
+            grad[i] = g;
+        } else {
+            g = grad[i];                                  // already reduced (and all-reduced) by the caller
+        }
+        if (a.apply) {
+            // torch.optim.Adam single-tensor step: lerp, mul/addcmul, sqrt/div/add, addcdiv
+            float mi = m[i], vi = v[i], p = local[i];
+            mi = mi + (g - mi) * a.beta1_c;
+            vi = vi * a.beta2 + a.beta2_c * g * g;
+            const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+            p = p - a.step_size * (mi / denom);
+            m[i] = mi; v[i] = vi; local[i] = p;
+            if (a.hard) target[i] = p;                    // hard_update (DuelingDQN_Trainer.py:199-202)
+        }
+    }
+    if (i == 0 && loss_out && a.nparts > 0) {
+        float s = 0.f;
+        for (int c = 0; c < a.nparts; ++c) s += loss_partials[c];
+        *loss_out = s * a.inv_b;
+    }
+}
+
+__global__ void copy_kernel(int n, const float *__restrict__ src, float *__restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// generic replay push (paired rows)
+__global__ void push_kernel(int n, int in, int64_t head, int64_t cap, const float *__restrict__ obs,
+                            const int32_t *__restrict__ act, const float *__restrict__ rew,
+                            const float *__restrict__ next_obs, const uint8_t *__restrict__ done,
+                            float *__restrict__ frames, int32_t *__restrict__ r_act, float *__restrict__ r_rew,
+                            uint8_t *__restrict__ r_done)
+{
+    const int64_t total = (int64_t)n * in;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i / in, k = i - t * in;
+        const int64_t slot = (head + t) % cap;
+        frames[(2 * slot) * in + k] = obs[i];
+        frames[(2 * slot + 1) * in + k] = next_obs[i];
+        if (k == 0) { r_act[slot] = act[t]; r_rew[slot] = rew[t]; r_done[slot] = done[t]; }
+    }
+}
+
+// ------------------------------------------------------------------ host launchers
+static size_t act_smem_bytes(const NetDev &n) { return (size_t)(n.smem_total_floats + 2 * kTile * kMaxDim + kTile * 32) * 4; }
+static size_t upd_smem_bytes(const NetDev &n)
+{
+    return (size_t)(n.smem_total_floats + kTile * n.act_ld[0] + 2 * kTile * kMaxDim + 3 * kTile * 32) * 4;
+}
+
+int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
+               const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st)
+{
+    const int n_tiles = (n + kTile - 1) / kTile;
+    const int grid = n_tiles < 4 * 148 ? n_tiles : 4 * 148;
+    act_kernel<<<grid, kNetThreads, act_smem_bytes(l->net), st>>>(l->net, l->local, obs, n, eps, is_train, u_tape,
+                                                                rand_tape, l->cfg.seed ^ 0xAC7ull, l->act_calls++,
+                                                                actions, nullptr, q_out, n_tiles);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
+                  cudaStream_t st)
+{
+    const int n_tiles = (B + kTile - 1) / kTile;
+    const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
+    UpdateArgs ua;
+    ua.local = l->local; ua.target = l->target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
+    ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma;
+    ua.inv_global_b = 1.0f / (float)global_batch;
+    update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net), st>>>(l->net, src, ua);
+    UAVRL_LAUNCHED();
+    l->last_nparts = grid;
+    l->last_global_batch = global_batch;
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = l->net.P; a.nparts = grid; a.apply = apply ? 1 : 0; a.world = l->world;
+    a.inv_b = 1.0f / (float)global_batch;
+    if (apply) {
+        l->adam_t += 1;
+        const double b1 = 0.9, b2 = 0.999;
+        const double bc1 = 1.0 - pow(b1, (double)l->adam_t), bc2 = 1.0 - pow(b2, (double)l->adam_t);
+        a.step_size = (float)((double)l->cfg.lr / bc1);
+        a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
+        a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
+        a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
+    }
+    const int threads = 256, blocks = (a.P + threads - 1) / threads;
+    reduce_adam_kernel<<<blocks, threads, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
+                                                  l->target, loss_out ? loss_out : l->loss_dev);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+BatchSrc replay_source(uavrl_learner *l, const int32_t *idx_tape)
+{
+    BatchSrc s;
+    memset(&s, 0, sizeof(s));
+    s.mode = l->mode; s.frames = l->frames; s.act = l->r_act; s.rew = l->r_rew; s.done_u8 = l->r_done;
+    s.idx_tape = idx_tape; s.count = l->count;
+    s.key = l->cfg.seed ^ 0x5EEDull; s.epoch = (uint64_t)l->epoch;
+    if (l->mode == kReplayLockstep) {
+        const int64_t N = l->cfg.lockstep_envs, nf = l->count / N;
+        s.cap = l->ring_frames; s.n_envs = (int32_t)N;
+        s.oldest = ((l->head - nf) % l->ring_frames + l->ring_frames) % l->ring_frames;
+    } else {
+        s.cap = l->slots;
+        s.oldest = ((l->head - l->count) % l->slots + l->slots) % l->slots;
+    }
+    return s;
+}
+
+// lockstep ring: frame `head` holds obs_t.  Returns where this iteration's outputs go.
+int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **act, float **rew, uint8_t **done)
+{
+    const int64_t N = l->cfg.lockstep_envs, in = l->net.in_dim;
+    const int64_t f = l->head, fn = (l->head + 1) % l->ring_frames;
+    *obs_t = l->frames + f * N * in;
+    *obs_next = l->frames + fn * N * in;
+    *act = l->r_act + f * N; *rew = l->r_rew + f * N; *done = l->r_done + f * N;
+    return 0;
+}
+
+void lockstep_commit(uavrl_learner *l)
+{
+    const int64_t N = l->cfg.lockstep_envs;
+    l->head = (l->head + 1) % l->ring_frames;
+    const int64_t max_count = (l->ring_frames - 1) * N;
+    l->count = (l->count + N > max_count) ? max_count : l->count + N;
+}
+
+}  // namespace uavrl
+
+using namespace uavrl;
+
+extern "C" {
+
+int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
+{
+    if (!cfg || !out) return fail(UAVRL_ERR_INVALID, "uavrl_learner_create: null argument");
+    if (cfg->batch_size <= 0 || cfg->replay_capacity <= 0) return fail(UAVRL_ERR_INVALID, "batch_size and replay_capacity must be > 0");
+    if (cfg->algo < 0 || cfg->algo > 2) return fail(UAVRL_ERR_INVALID, "unknown algo");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(UAVRL_ERR_CUDA, "no CUDA device: the learner has no CPU fallback");
+    UAVRL_CUDA(cudaSetDevice(cfg->device));
+    uavrl_learner *l = new uavrl_learner();
+    l->cfg = *cfg;
+    int rc = build_net(*cfg, l->net);
+    if (rc) { delete l; return rc; }
+    const size_t P = (size_t)l->net.P;
+    l->max_ctas = 4 * 148;
+    if ((rc = dev_alloc(&l->local, P)) || (rc = dev_alloc(&l->target, P)) || (rc = dev_alloc(&l->m, P)) ||
+        (rc = dev_alloc(&l->v, P)) || (rc = dev_alloc(&l->grad, P)) ||
+        (rc = dev_alloc(&l->partials, P * (size_t)l->max_ctas)) || (rc = dev_alloc(&l->loss_partials, (size_t)l->max_ctas)) ||
+        (rc = dev_alloc(&l->loss_dev, 1)) || (rc = dev_alloc(&l->flags, 64)))
+        return rc;
+    const size_t in = (size_t)cfg->in_dim;
+    if (cfg->lockstep_envs > 0) {
+        const int64_t N = cfg->lockstep_envs;
+        int64_t cap_frames = (cfg->replay_capacity + N - 1) / N;
+        if (cap_frames < 2) cap_frames = 2;
+        l->mode = kReplayLockstep;
+        l->ring_frames = cap_frames + 1;
+        l->slots = l->ring_frames * N;
+        if ((rc = dev_alloc(&l->frames, (size_t)l->slots * in))) return rc;
+    } else {
+        l->mode = kReplayPaired;
+        l->slots = cfg->replay_capacity;
+        if ((rc = dev_alloc(&l->frames, (size_t)l->slots * 2 * in))) return rc;
+    }
+    if ((rc = dev_alloc(&l->r_act, (size_t)l->slots)) || (rc = dev_alloc(&l->r_rew, (size_t)l->slots)) ||
+        (rc = dev_alloc(&l->r_done, (size_t)l->slots)))
+        return rc;
+    UAVRL_CUDA(cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem_bytes(l->net)));
+    UAVRL_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(l->net)));
+    *out = l;
+    return 0;
+}
+
+int uavrl_learner_destroy(uavrl_learner *l)
+{
+    if (!l) return 0;
+    cudaSetDevice(l->cfg.device);
+    void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
+                     l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev };
+    for (void *p : ptrs) cudaFree(p);
+    delete l;
+    return 0;
+}
+
+int64_t uavrl_learner_param_count(const uavrl_learner *l) { return l ? l->net.P : 0; }
+
+static float *which_buf(uavrl_learner *l, int which)
+{
+    switch (which) {
+    case 0: return l->local; case 1: return l->target; case 2: return l->m; case 3: return l->v; case 4: return l->grad;
+    default: return nullptr;
+    }
+}
+
+int uavrl_learner_set_params(uavrl_learner *l, int32_t which, const float *h)
+{
+    if (!l || !h || !which_buf(l, which)) return fail(UAVRL_ERR_INVALID, "bad argument");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    UAVRL_CUDA(cudaMemcpy(which_buf(l, which), h, (size_t)l->net.P * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int uavrl_learner_get_params(uavrl_learner *l, int32_t which, float *h)
+{
+    if (!l || !h || !which_buf(l, which)) return fail(UAVRL_ERR_INVALID, "bad argument");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    UAVRL_CUDA(cudaMemcpy(h, which_buf(l, which), (size_t)l->net.P * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_learner_set_counters(uavrl_learner *l, int64_t epoch, int64_t adam_step)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    l->epoch = epoch; l->adam_t = adam_step;
+    return 0;
+}
+
+int uavrl_learner_get_counters(uavrl_learner *l, int64_t *epoch, int64_t *adam_step)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    if (epoch) *epoch = l->epoch;
+    if (adam_step) *adam_step = l->adam_t;
+    return 0;
+}
+
+int uavrl_learner_act(uavrl_learner *l, const float *obs_dev, int32_t n, float eps, int32_t is_train,
+                      const float *u_tape_dev, const int32_t *rand_tape_dev, int32_t *actions_dev, float *q_out_dev,
+                      void *stream)
+{
+    if (!l || !obs_dev || !actions_dev || n <= 0) return fail(UAVRL_ERR_INVALID, "bad argument");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    return launch_act(l, obs_dev, n, eps, is_train, u_tape_dev, rand_tape_dev, actions_dev, q_out_dev, (cudaStream_t)stream);
+}
+
+int uavrl_replay_push(uavrl_learner *l, int32_t n, const float *obs, const int32_t *act, const float *rew,
+                      const float *next_obs, const uint8_t *done, void *stream)
+{
+    if (!l || n <= 0 || !obs || !act || !rew || !next_obs || !done) return fail(UAVRL_ERR_INVALID, "bad argument");
+    if (l->mode != kReplayPaired) return fail(UAVRL_ERR_STATE, "uavrl_replay_push needs lockstep_envs == 0 (the lockstep ring is fed by uavrl_train_run)");
+    if (n > l->slots) return fail(UAVRL_ERR_INVALID, "push larger than the replay capacity");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    const int64_t total = (int64_t)n * l->net.in_dim;
+    const int threads = 256;
+    int blocks = (int)((total + threads - 1) / threads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    push_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(n, l->net.in_dim, l->head, l->slots, obs, act, rew, next_obs,
+                                                             done, l->frames, l->r_act, l->r_rew, l->r_done);
+    UAVRL_LAUNCHED();
+    l->head = (l->head + n) % l->slots;
+    l->count = (l->count + n > l->slots) ? l->slots : l->count + n;
+    return 0;
+}
+
+int64_t uavrl_replay_size(const uavrl_learner *l) { return l ? l->count : 0; }
+
+int uavrl_replay_gather(uavrl_learner *l, int32_t n, const int64_t *idx, float *s, int32_t *a, float *r, float *s2,
+                        uint8_t *d)
+{
+    if (!l || n <= 0 || !idx) return fail(UAVRL_ERR_INVALID, "bad argument");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    const BatchSrc src = replay_source(l, nullptr);
+    const size_t in = (size_t)l->net.in_dim;
+    for (int i = 0; i < n; ++i) {
+        const int64_t j = idx[i];
+        if (j < 0 || j >= l->count) return fail(UAVRL_ERR_INVALID, "logical index out of range");
+        int64_t slot, row, row2;
+        if (src.mode == kReplayLockstep) {
+            const int64_t f = (src.oldest + j / src.n_envs) % src.cap, e = j % src.n_envs;
+            slot = f * src.n_envs + e; row = slot; row2 = ((f + 1) % src.cap) * src.n_envs + e;
+        } else {
+            slot = (src.oldest + j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+        }
+        if (s) UAVRL_CUDA(cudaMemcpy(s + i * in, l->frames + row * in, in * 4, cudaMemcpyDeviceToHost));
+        if (s2) UAVRL_CUDA(cudaMemcpy(s2 + i * in, l->frames + row2 * in, in * 4, cudaMemcpyDeviceToHost));
+        if (a) UAVRL_CUDA(cudaMemcpy(a + i, l->r_act + slot, 4, cudaMemcpyDeviceToHost));
+        if (r) UAVRL_CUDA(cudaMemcpy(r + i, l->r_rew + slot, 4, cudaMemcpyDeviceToHost));
+        if (d) UAVRL_CUDA(cudaMemcpy(d + i, l->r_done + slot, 1, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+static int do_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_dev, bool apply, void *stream)
+{
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    return launch_update(l, src, B, global_batch, loss_dev, apply, (cudaStream_t)stream);
+}
+
+int uavrl_learner_update(uavrl_learner *l, const int32_t *idx_tape_dev, float *loss_dev, void *stream)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    l->epoch += 1;                                              // DuelingDQN_Trainer.py:152
+    if (l->count <= l->cfg.batch_size) return 0;                // PathPlan_City.py:383: nothing sampled yet
+    BatchSrc src = replay_source(l, idx_tape_dev);
+    return do_update(l, src, l->cfg.batch_size, l->cfg.batch_size, loss_dev, true, stream);
+}
+
+int uavrl_learner_update_batch(uavrl_learner *l, int32_t B, const float *s, const int32_t *a, const float *r,
+                               const float *s2, const float *d, float *loss_dev, void *stream)
+{
+    if (!l || B <= 0 || !s || !a || !r || !s2 || !d) return fail(UAVRL_ERR_INVALID, "bad argument");
+    l->epoch += 1;
+    BatchSrc src;
+    memset(&src, 0, sizeof(src));
+    src.mode = kBatchExplicit; src.frames = s; src.s2_rows = s2; src.act = a; src.rew = r; src.done_f32 = d;
+    return do_update(l, src, B, B, loss_dev, true, stream);
+}
+
+int uavrl_learner_compute_grads(uavrl_learner *l, const int32_t *idx_tape_dev, int32_t global_batch, float *loss_dev,
+                                void *stream)
+{
+    if (!l || global_batch <= 0) return fail(UAVRL_ERR_INVALID, "bad argument");
+    l->epoch += 1;
+    if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay holds <= batch_size transitions");
+    BatchSrc src = replay_source(l, idx_tape_dev);
+    return do_update(l, src, l->cfg.batch_size, global_batch, loss_dev, false, stream);
+}
+
+float *uavrl_learner_grad_ptr(uavrl_learner *l) { return l ? l->grad : nullptr; }
+
+int uavrl_learner_apply_grads(uavrl_learner *l, void *stream)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = l->net.P; a.nparts = 0; a.apply = 1;
+    l->adam_t += 1;
+    const double b1 = 0.9, b2 = 0.999;
+    const double bc1 = 1.0 - pow(b1, (double)l->adam_t), bc2 = 1.0 - pow(b2, (double)l->adam_t);
+    a.step_size = (float)((double)l->cfg.lr / bc1);
+    a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
+    a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
+    a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
+    const int threads = 256, blocks = (a.P + threads - 1) / threads;
+    reduce_adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a, l->partials, l->loss_partials, l->grad, l->local,
+                                                                    l->m, l->v, l->target, nullptr);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+int uavrl_learner_hard_update(uavrl_learner *l, void *stream)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    const int threads = 256, blocks = (l->net.P + threads - 1) / threads;
+    copy_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(l->net.P, l->local, l->target);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+int uavrl_learner_comm_buffers(uavrl_learner *l, void **grad_dev, void **flag_dev, size_t *grad_bytes, size_t *flag_bytes)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    if (grad_dev) *grad_dev = l->grad;
+    if (flag_dev) *flag_dev = l->flags;
+    if (grad_bytes) *grad_bytes = (size_t)l->net.P * 4;
+    if (flag_bytes) *flag_bytes = 64 * sizeof(unsigned);
+    return 0;
+}
+
+int uavrl_learner_set_peers(uavrl_learner *l, int32_t rank, int32_t world, void *const *peer_grad_ptrs,
+                            void *const *peer_flag_ptrs)
+{
+    if (!l || world < 1 || rank < 0 || rank >= world) return fail(UAVRL_ERR_INVALID, "bad rank/world");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    l->rank = rank; l->world = world;
+    if (peer_grad_ptrs && peer_flag_ptrs) {
+        cudaFree(l->peer_grads_dev); cudaFree(l->peer_flags_dev);
+        UAVRL_CUDA(cudaMalloc((void **)&l->peer_grads_dev, sizeof(void *) * world));
+        UAVRL_CUDA(cudaMalloc((void **)&l->peer_flags_dev, sizeof(void *) * world));
+        UAVRL_CUDA(cudaMemcpy(l->peer_grads_dev, peer_grad_ptrs, sizeof(void *) * world, cudaMemcpyHostToDevice));
+        UAVRL_CUDA(cudaMemcpy(l->peer_flags_dev, peer_flag_ptrs, sizeof(void *) * world, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// learner.cuh -- Q-network / replay / optimiser state of one learner (device-resident) + host handle.
+#pragma once
+#include "common.cuh"
+
+namespace uavrl {
+
+constexpr int kTile = 32;             // samples per CTA tile
+constexpr int kNetThreads = 256;      // 8 warps: lane -> output unit, warp -> 4 samples
+constexpr int kMaxDim = 128;          // every layer width (and in_dim) <= 128
+constexpr int kMaxLayers = UAVRL_MAX_HIDDEN + 1;   // trunk layers + (combined) head
+
+// One dense layer as the kernels see it.  Weights live in smem transposed: Wt[k][o], ld = out+1
+// (odd when out is even -> conflict-free whether lanes walk o or k).
+struct LayerDev {
+    int32_t in, out;                  // out of the head = n_actions (+1 value row when dueling)
+    int32_t w_off, b_off;             // offsets in the flat state_dict-ordered parameter vector
+    int32_t w2_off, b2_off;           // dueling head only: fc_V.weight / fc_V.bias (row `out-1`)
+    int32_t smem_w, smem_b;           // offsets (floats) inside the smem weight area
+};
+
+struct NetDev {
+    int32_t in_dim, n_layers, n_actions, dueling;
+    int32_t P;                        // parameter count
+    int32_t smem_w_floats;            // total smem floats for Wt + biases
+    int32_t act_off[kMaxLayers + 1];  // smem offsets of the activation planes X0, H1.. (floats)
+    int32_t act_ld[kMaxLayers + 1];
+    int32_t smem_total_floats;        // whole dynamic smem carve-up for the update kernel
+    LayerDev L[kMaxLayers];
+};
+
+enum ReplayMode { kReplayPaired = 0, kReplayLockstep = 1, kBatchExplicit = 2 };
+
+// where the rows of a batch come from
+struct BatchSrc {
+    int32_t mode;
+    const float *frames;              // replay observation rows [rows][in_dim]
+    const int32_t *act;               // [slots]
+    const float *rew;                 // [slots]
+    const uint8_t *done_u8;           // [slots]  (replay)          } one of the two
+    const float *done_f32;            // [B]      (explicit batch)  }
+    const float *s2_rows;             // explicit: next-state rows [B][in]
+    const int32_t *idx_tape;          // optional injected logical indices [B]
+    int64_t count, oldest;            // valid transitions, logical index of the oldest
+    int64_t cap;                      // paired: slots ; lockstep: frames in the ring
+    int32_t n_envs;                   // lockstep only
+    uint64_t key, epoch;              // Philox key / counter for sampling
+};
+
+}  // namespace uavrl
+
+struct uavrl_learner {
+    uavrl_learner_config cfg;
+    uavrl::NetDev net;
+    // parameters and optimiser state (flat, state_dict order)
+    float *local = nullptr, *target = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
+    float *partials = nullptr;        // [max_ctas][P] per-CTA gradient partials
+    float *loss_partials = nullptr;   // [max_ctas]
+    float *loss_dev = nullptr;        // [1]
+    int32_t max_ctas = 0;
+    int64_t epoch = 0, adam_t = 0;
+    // replay
+    int32_t mode = 0;
+    float *frames = nullptr;
+    int32_t *r_act = nullptr;
+    float *r_rew = nullptr;
+    uint8_t *r_done = nullptr;
+    int64_t slots = 0;                // paired: capacity ; lockstep: (ring_frames)*N
+    int64_t ring_frames = 0;          // lockstep: frames in the ring (= capacity_frames + 1)
+    int64_t head = 0;                 // paired: next slot to write ; lockstep: frame holding obs_t
+    int64_t count = 0;                // valid transitions
+    bool frame0_valid = false;
+    uint64_t act_calls = 0;
+    // data-parallel
+    int32_t rank = 0, world = 1;
+    void **peer_grads_dev = nullptr;  // device array of `world` pointers
+    void **peer_flags_dev = nullptr;
+    unsigned *flags = nullptr;        // [64] own flag words (symmetric)
+    unsigned flag_epoch = 0;
+    int last_nparts = 0;
+    int last_global_batch = 0;
+};
+
+namespace uavrl {
+int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
+               const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
+int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,
+                  bool apply, cudaStream_t st);
+int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **act, float **rew, uint8_t **done);
+void lockstep_commit(uavrl_learner *l);
+BatchSrc replay_source(uavrl_learner *l, const int32_t *idx_tape);
+}  // namespace uavrl

@@ -1,0 +1,69 @@
+// train.cu -- the fused lockstep training loop over the env batch and the learner.
+//
+// Replaces PathPlan_City.run_thread_OffPolicy + PathPlan_City.update (Envs/PathPlan_City.py:364-385,
+// 757-776) for N envs: state -> get_action -> Move_Agent -> replay add -> sample -> Trainer.update.
+// Observations are produced once by the env kernel, directly into the replay frame ring: the
+// frame written as "next_obs" of iteration t is the "obs" the policy reads at t+1 (no copy, no
+// separate push kernel; 412 B per stored transition instead of 812 B).
+#include "env.cuh"
+#include "learner.cuh"
+
+using namespace uavrl;
+
+extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, int32_t updates_per_iter,
+                               int32_t do_update, uavrl_train_stats *stats_host, void *stream)
+{
+    if (!env || !l || n_iters < 0) return fail(UAVRL_ERR_INVALID, "bad argument");
+    if (l->mode != kReplayLockstep || l->cfg.lockstep_envs != env->d.n)
+        return fail(UAVRL_ERR_INVALID, "learner.lockstep_envs must equal env.n_envs");
+    if (l->net.in_dim != kObsDim) return fail(UAVRL_ERR_INVALID, "learner.in_dim must be 100 (the UAV observation)");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_train_run before uavrl_env_reset");
+    if (env->cfg.device != l->cfg.device) return fail(UAVRL_ERR_INVALID, "env and learner live on different devices");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    unsigned long long c0[4] = { 0, 0, 0, 0 };
+    double r0 = 0.0;
+    if (stats_host) {
+        UAVRL_CUDA(cudaStreamSynchronize(st));
+        UAVRL_CUDA(cudaMemcpy(c0, env->d.stat_counts, sizeof(c0), cudaMemcpyDeviceToHost));
+        UAVRL_CUDA(cudaMemcpy(&r0, env->d.stat_reward, sizeof(r0), cudaMemcpyDeviceToHost));
+    }
+    int64_t updates = 0;
+    for (int it = 0; it < n_iters; ++it) {
+        float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
+        lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
+        if (!l->frame0_valid) {                          // very first iteration: materialise obs_0
+            if ((rc = launch_env_observe(env->d, obs_t, st))) return rc;
+            l->frame0_valid = true;
+        }
+        // Choose_Action2 -> Trainer.get_action (PathPlan_City.py:338-346)
+        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+        // Move_Agent + replay add (PathPlan_City.py:371-382): reward/done land in the ring slots
+        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        lockstep_commit(l);
+        if (do_update) {
+            for (int u = 0; u < updates_per_iter; ++u) {  // PathPlan_City.update -> Trainer.update (:757-776)
+                l->epoch += 1;
+                if (l->count <= l->cfg.batch_size) continue;
+                BatchSrc src = replay_source(l, nullptr);
+                if ((rc = launch_update(l, src, l->cfg.batch_size, l->cfg.batch_size, l->loss_dev, true, st))) return rc;
+                ++updates;
+            }
+        }
+    }
+    if (stats_host) {
+        UAVRL_CUDA(cudaStreamSynchronize(st));
+        unsigned long long c1[4]; double r1; float loss;
+        UAVRL_CUDA(cudaMemcpy(c1, env->d.stat_counts, sizeof(c1), cudaMemcpyDeviceToHost));
+        UAVRL_CUDA(cudaMemcpy(&r1, env->d.stat_reward, sizeof(r1), cudaMemcpyDeviceToHost));
+        UAVRL_CUDA(cudaMemcpy(&loss, l->loss_dev, sizeof(loss), cudaMemcpyDeviceToHost));
+        stats_host->env_steps = (int64_t)(c1[0] - c0[0]);
+        stats_host->episodes_ended = (int64_t)(c1[1] - c0[1]);
+        stats_host->collisions = (int64_t)(c1[2] - c0[2]);
+        stats_host->sum_reward = r1 - r0;
+        stats_host->updates = updates;
+        stats_host->last_loss = loss;
+    }
+    return 0;
+}

@@ -1,0 +1,225 @@
+/* uavrl.h -- C ABI of the B200-native UAV path-planning hot path (libuavrl_b200.so).
+ *
+ * The reference (young-how/DQN-based-UAV-3D_path_planer, "RLGF") is pure Python with no FFI; its
+ * hot path sits behind a duck-typed plug-in API resolved by name from XML.
+ * This header is the boundary a reference-side plug-in binds with ctypes: plain
+ * pointers and sizes only, no torch types.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative uavrl_status; uavrl_last_error() gives the
+ *     thread-local message.  Nothing falls back to a CPU path: without a CUDA device create() fails.
+ *   - "_dev" pointers are device memory owned by the CALLER (e.g. torch.Tensor.data_ptr());
+ *     "_host" pointers are host memory.  The library owns only its handles and their internal state.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All work is
+ *     enqueued on it; there are no hidden synchronisations except where a _host output is written.
+ *   - one host thread per handle.
+ */
+#ifndef UAVRL_H
+#define UAVRL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVRL_OBS_DIM 100            /* Agents/UAV.py:517 state_map (1,1,1,100) */
+#define UAVRL_MAX_HIDDEN 4
+
+typedef enum {
+    UAVRL_OK = 0,
+    UAVRL_ERR_INVALID = -1,          /* bad argument / configuration */
+    UAVRL_ERR_CUDA = -2,             /* CUDA runtime error (no device, launch failure, ...) */
+    UAVRL_ERR_STATE = -3,            /* call order (e.g. step before reset) */
+    UAVRL_ERR_NOMEM = -4
+} uavrl_status;
+
+typedef enum { UAVRL_INFO_NORMAL = 0, UAVRL_INFO_SUCCESS = 1, UAVRL_INFO_LOSE = 2 } uavrl_info;
+
+/* action encodings accepted by uavrl_env_step */
+typedef enum {
+    UAVRL_ACT_CONT_F32 = 0,          /* steering fraction a0 = action[0] in [-1,1]  (UAV.py:407,414) */
+    UAVRL_ACT_CONT_F64 = 1,          /* same, double (exact replay of reference tapes) */
+    UAVRL_ACT_DISCRETE27 = 2         /* int32 k in 0..26: documented extension, see DESIGN.md */
+} uavrl_action_kind;
+
+typedef enum { UAVRL_ALGO_DQN = 0, UAVRL_ALGO_DDQN = 1, UAVRL_ALGO_DUELING = 2 } uavrl_algo;
+
+/* ------------------------------------------------------------------ environment batch */
+typedef struct uavrl_env uavrl_env;
+
+typedef struct {
+    int32_t n_envs;                  /* UAV instances stepped in lockstep */
+    int32_t max_subgoals;            /* K: capacity of each sub-goal queue (RRT path length bound) */
+    double len, width, h;            /* BaseClass/BaseEnv.py:19-21 (config/PathPlan_City.xml:4-6) */
+    double max_v, min_v;             /* config/UAV.xml:12-13 (Agents/UAV.py:25) */
+    double steering_angle;           /* radians: Steering_angle/180*pi (UAV.py:26) */
+    int32_t max_step;                /* UAV.py:32 */
+    double climb_rate;               /* discrete-27 extension only */
+    int32_t n_buildings;
+    const double *buildings_host;    /* [n][5] = cx, cy, cz, _R, _H (Obstacles/building.py:8-11) */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t auto_reset;              /* 1: an env whose episode ended (UAV.done) restarts from the
+                                        scenario pool inside the same step call */
+} uavrl_env_config;
+
+int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out);
+int uavrl_env_destroy(uavrl_env *env);
+
+/* Scenario pool = pre-generated outcomes of UAV.reset() (UAV.py:335-366): start ~U(10,210)x U(1,10),
+ * goal ~U(330,490)x U(420,490), heading ~U(0,2pi), sub-goal queue from RRT (PathPlan/RRT.py:63-105;
+ * queue[0] is the start point -- the very Loc object of the UAV, `alias0`=1 -- and the last entry
+ * is the goal).  Host arrays: start[P][3], goal[P][3], heading[P], subgoals[P][K][3], n_sub[P],
+ * alias0[P] (NULL = all 1). */
+int uavrl_env_set_pool(uavrl_env *env, int32_t n_scenarios, const double *start_host,
+                       const double *goal_host, const double *heading_host,
+                       const double *subgoals_host, const int32_t *n_sub_host,
+                       const uint8_t *alias0_host);
+
+/* UAV.reset() for every env: env e takes scenario (first_scenario + e) mod P of the pool. */
+int uavrl_env_reset(uavrl_env *env, int32_t first_scenario, void *stream);
+
+/* Host-side scenario generator (reset draws + RRT) for synthetic pools: statistical restatement of
+ * UAV.py:344-360 + RRT.py:26-105 with a counter-based RNG (the reference's Python MT19937 stream is
+ * not reproduced).  Writes the arrays uavrl_env_set_pool takes. */
+int uavrl_make_scenarios(const uavrl_env_config *cfg, uint64_t seed, int32_t n_scenarios,
+                         int32_t rrt_step, double *start_host, double *goal_host,
+                         double *heading_host, double *subgoals_host, int32_t *n_sub_host);
+
+/* UAV.state() -> state_PathPlan (UAV.py:515-567): obs_dev [n_envs][100] float32. */
+int uavrl_env_observe(uavrl_env *env, float *obs_dev, void *stream);
+
+/* BaseEnv.Move_Agent (BaseEnv.py:123-137) = UAV.update_PathPlan (UAV.py:397-513) followed by
+ * UAV.state(), for all envs.  Outputs (any may be NULL): next_obs [n][100] f32, reward [n] f32,
+ * done [n] u8 (the RETURNED flag, True at every sub-goal), info [n] u8 (uavrl_info),
+ * collision [n] u8 (predicate at UAV.py:425), ended [n] u8 (UAV.done after the step, before any
+ * auto-reset). */
+int uavrl_env_step(uavrl_env *env, int32_t action_kind, const void *actions_dev,
+                   float *next_obs_dev, float *reward_dev, uint8_t *done_dev, uint8_t *info_dev,
+                   uint8_t *collision_dev, uint8_t *ended_dev, void *stream);
+
+/* Same call with HOST buffers: copies actions in, runs the step, copies results out, synchronises.
+ * This is the call a reference-side plug-in makes per lockstep iteration. */
+int uavrl_env_step_host(uavrl_env *env, int32_t action_kind, const void *actions_host,
+                        float *next_obs_host, float *reward_host, uint8_t *done_host,
+                        uint8_t *info_host, uint8_t *collision_host, uint8_t *ended_host);
+
+/* fp64 state read-back for parity tests / checkpoints; any pointer may be NULL.  Each [n_envs]. */
+typedef struct {
+    double *px, *py, *pz, *vx, *vy, *V, *score, *total_score, *path_len, *reward64;
+    int32_t *step, *cursor, *scenario;
+    uint8_t *done;
+} uavrl_env_state_host;
+int uavrl_env_get_state(uavrl_env *env, const uavrl_env_state_host *out);
+
+/* PathPlan_City.Threaten_rate (Envs/PathPlan_City.py:215-223) on arbitrary points (device kernel):
+ * pts_host [n][3] -> out_host [n] u8. */
+int uavrl_env_threaten_rate(uavrl_env *env, int32_t n, const double *pts_host, uint8_t *out_host);
+
+/* ------------------------------------------------------------------ learner (Q-net + replay) */
+typedef struct uavrl_learner uavrl_learner;
+
+typedef struct {
+    int32_t in_dim;                       /* w (config/Trainer.xml <w>) */
+    int32_t n_hidden;                     /* trunk layers with ReLU: Qnet2/VAnet2 = 1, QValueNet_SAC/VAnet3 = 2 ... */
+    int32_t hidden[UAVRL_MAX_HIDDEN];     /* e.g. {64}, {64,64}, {128,64} (BaseClass/BaseCNN.py) */
+    int32_t n_actions;                    /* <output> */
+    int32_t dueling;                      /* 1: fc_A + fc_V heads, Q = V + A - mean(A) (BaseCNN.py:131-139) */
+    int32_t algo;                         /* uavrl_algo */
+    float lr;                             /* LEARNING_RATE (BaseTrainer.py:33) */
+    float gamma;                          /* BaseTrainer.py:35 */
+    int32_t batch_size;                   /* Batch_Size (BaseTrainer.py:34) */
+    int32_t update_loop;                  /* hard target update period (DuelingDQN_Trainer.py:30,183) */
+    int64_t replay_capacity;              /* replay_size, in transitions (BaseTrainer.py:32,39) */
+    int32_t lockstep_envs;                /* >0: frame-ring replay fed by uavrl_train_* (N envs per frame);
+                                             0: generic transition store fed by uavrl_replay_push */
+    uint64_t seed;                        /* Philox key for eps-greedy and replay sampling */
+    int32_t device;
+} uavrl_learner_config;
+
+int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out);
+int uavrl_learner_destroy(uavrl_learner *l);
+int64_t uavrl_learner_param_count(const uavrl_learner *l);
+
+/* state_dict()-ordered flat fp32 parameters (fc1.weight [out][in], fc1.bias, ..., for dueling nets
+ * ..., fc_A.weight, fc_A.bias, fc_V.weight, fc_V.bias) -- what torch.save({'model': ...}) holds
+ * (DuelingDQN_Trainer.py:79-84).  which: 0 = q_local, 1 = q_target, 2 = Adam exp_avg,
+ * 3 = Adam exp_avg_sq, 4 = last gradient. */
+int uavrl_learner_set_params(uavrl_learner *l, int32_t which, const float *params_host);
+int uavrl_learner_get_params(uavrl_learner *l, int32_t which, float *params_host);
+int uavrl_learner_set_counters(uavrl_learner *l, int64_t epoch, int64_t adam_step);
+int uavrl_learner_get_counters(uavrl_learner *l, int64_t *epoch, int64_t *adam_step);
+
+/* Trainer.get_action (DuelingDQN_Trainer.py:86-97) for n observations: u > eps (or !is_train)
+ * -> argmax_a q_local(obs), else a uniformly random action.  u_tape_dev / rand_tape_dev inject the
+ * random draws (parity tests); NULL = Philox.  q_out_dev optional [n][A]. */
+int uavrl_learner_act(uavrl_learner *l, const float *obs_dev, int32_t n, float eps, int32_t is_train,
+                      const float *u_tape_dev, const int32_t *rand_tape_dev, int32_t *actions_dev,
+                      float *q_out_dev, void *stream);
+
+/* ReplayMemory.add (BaseClass/replay_buffer.py:41-42), n transitions, FIFO over replay_capacity. */
+int uavrl_replay_push(uavrl_learner *l, int32_t n, const float *obs_dev, const int32_t *actions_dev,
+                      const float *reward_dev, const float *next_obs_dev, const uint8_t *done_dev,
+                      void *stream);
+int64_t uavrl_replay_size(const uavrl_learner *l);
+/* Read back n stored transitions by logical index (0 = oldest) into host arrays (checkpointing the
+ * replay, tests): s/s2 [n][in], a [n], r [n], d [n]. */
+int uavrl_replay_gather(uavrl_learner *l, int32_t n, const int64_t *logical_idx_host, float *s_host,
+                        int32_t *a_host, float *r_host, float *s2_host, uint8_t *d_host);
+
+/* Trainer.update (DuelingDQN_Trainer.py:150-190; DQN_Trainer.py:85-136; DDQN_Trainer.py:72-117):
+ * epoch += 1; sample Batch_Size distinct transitions uniformly (replay_buffer.py:48-51;
+ * idx_tape_dev injects the indices, NULL = Philox), TD target, MSE loss, backward, Adam step, hard
+ * target update every update_loop epochs.  Skipped (epoch still counts) while the replay holds
+ * <= Batch_Size transitions (PathPlan_City.py:383).  loss_dev optional [1]. */
+int uavrl_learner_update(uavrl_learner *l, const int32_t *idx_tape_dev, float *loss_dev, void *stream);
+
+/* The same update on an explicit batch (transition_dict of DuelingDQN_Trainer.update): device arrays
+ * s [B][in], a [B], r [B], s2 [B][in], d [B] (float 0/1). */
+int uavrl_learner_update_batch(uavrl_learner *l, int32_t B, const float *s_dev, const int32_t *a_dev,
+                               const float *r_dev, const float *s2_dev, const float *d_dev,
+                               float *loss_dev, void *stream);
+
+/* Split form for data-parallel training: grads only (sum over the local batch of d(loss)/d(theta),
+ * loss normalised by global_batch), then -- after the caller all-reduced uavrl_learner_grad_ptr()
+ * across ranks -- the optimiser step.  */
+int uavrl_learner_compute_grads(uavrl_learner *l, const int32_t *idx_tape_dev, int32_t global_batch,
+                                float *loss_dev, void *stream);
+float *uavrl_learner_grad_ptr(uavrl_learner *l);          /* device, [param_count] fp32 */
+int uavrl_learner_apply_grads(uavrl_learner *l, void *stream);
+int uavrl_learner_hard_update(uavrl_learner *l, void *stream);   /* DuelingDQN_Trainer.py:199-202 */
+
+/* One-shot NVLink all-reduce fused with Adam: every rank reads all peers' gradient vectors over
+ * peer-mapped memory in rank order (bit-identical replicas) inside the optimiser kernel.
+ * peer_grad_ptrs / peer_flag_ptrs: device pointers valid on THIS device (cudaIpcOpenMemHandle),
+ * one per rank, own rank included. */
+int uavrl_learner_comm_buffers(uavrl_learner *l, void **grad_dev, void **flag_dev, size_t *grad_bytes,
+                               size_t *flag_bytes);
+int uavrl_learner_set_peers(uavrl_learner *l, int32_t rank, int32_t world, void *const *peer_grad_ptrs,
+                            void *const *peer_flag_ptrs);
+
+/* ------------------------------------------------------------------ fused lockstep training loop
+ * PathPlan_City.run_thread_OffPolicy + update (Envs/PathPlan_City.py:364-385,757-776) for all envs:
+ *   obs -> get_action -> Move_Agent -> replay add -> [sample -> Trainer.update]
+ * n_iters lockstep iterations; observations are written once, straight into the replay frame ring.
+ * updates_per_iter optimiser steps follow each env step (reference: 1).  stats_host (optional)
+ * receives {env_steps, updates, episodes_ended, sum_reward, last_loss, collisions}. */
+typedef struct {
+    int64_t env_steps, updates, episodes_ended, collisions;
+    double sum_reward;
+    float last_loss;
+} uavrl_train_stats;
+int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps,
+                    int32_t updates_per_iter, int32_t do_update, uavrl_train_stats *stats_host,
+                    void *stream);
+
+const char *uavrl_last_error(void);
+const char *uavrl_version(void);
+/* number of kernel launches issued by this library in the calling process since load (bench.py) */
+int64_t uavrl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVRL_H */

@@ -1,0 +1,68 @@
+"""CPU-side logic test: csrc/env_core.cuh (the source the CUDA kernel instantiates per env),
+compiled for the host by tests/host_shim, against the golden vectors of the Python reference.
+
+Catches step-logic mistakes without a GPU.  The product library is not involved."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import episode, ROOT
+
+SHIM_DIR = os.path.join(ROOT, "tests", "host_shim")
+SHIM_SO = os.path.join(SHIM_DIR, "_build", "libenv_core_host.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++",
+                           os.path.join(SHIM_DIR, "env_core_host.cpp"), "-o", SHIM_SO])
+    return C.CDLL(SHIM_SO)
+
+
+def shim_step(shim, city, params, b, actions, mode, want_obs=True):
+    n = b.n
+    rew = np.zeros(n); done = np.zeros(n, np.uint8); info = np.zeros(n, np.uint8); coll = np.zeros(n, np.uint8)
+    obs = np.zeros((n, 100), np.float32)
+    st = b._struct()
+    acts = None if actions is None else np.ascontiguousarray(actions, np.float64)
+    shim.shim_step(C.c_double(city.c.width), C.c_double(city.c.h), C.c_int(city.buildings.shape[0]),
+                   O._p(city.buildings, C.c_double), C.c_double(params.max_v), C.c_double(params.min_v),
+                   C.c_double(params.steering), C.c_double(params.climb_rate), C.c_int(params.max_step),
+                   C.c_int(mode), C.byref(st), O._p(acts, C.c_double) if acts is not None else None,
+                   O._p(rew, C.c_double), O._p(done, C.c_uint8), O._p(info, C.c_uint8), O._p(coll, C.c_uint8),
+                   O._p(obs, C.c_float) if want_obs else None)
+    return rew, done, info, coll, obs
+
+
+@pytest.mark.parametrize("which", ["continuous", "discrete27"])
+def test_env_core_matches_reference_goldens(shim, env_golden, env27_golden, which):
+    g = env_golden if which == "continuous" else env27_golden
+    d = env_golden["dims"]
+    city = O.OracleCity(d[0], d[1], d[2], env_golden["buildings"])
+    p = env_golden["uav_params"]
+    params = O.UavParams(p[0], p[1], p[2], float(env27_golden["climb_rate"]), int(p[3]))
+    mode = 0 if which == "continuous" else 1
+    steps = 0
+    for i in range(int(g["epn_episodes"])):
+        ep = episode(g, i)
+        b = O.OracleBatch(city, params, 1, ep["sub"].shape[0])
+        b.reset(ep["start"][None], ep["goal"][None], [ep["heading"]], ep["sub"][None], [ep["n_sub"]], [ep["alias0"]])
+        _, _, _, _, obs = shim_step(shim, city, params, b, None, mode)
+        np.testing.assert_array_equal(obs[0], ep["obs0"].astype(np.float32))
+        for t in range(len(ep["action"])):
+            rew, done, info, coll, obs = shim_step(shim, city, params, b, [ep["action"][t]], mode)
+            assert abs(rew[0] - ep["reward"][t]) <= 1e-12 * max(1.0, abs(ep["reward"][t])), (i, t)
+            assert (done[0], info[0], coll[0]) == (ep["done_ret"][t], ep["info"][t], ep["collision"][t]), (i, t)
+            for k in ("px", "py", "pz", "vx", "vy", "V"):
+                assert abs(getattr(b, k)[0] - ep[k][t]) <= 1e-12 * max(1.0, abs(ep[k][t])), (i, t, k)
+            assert b.step[0] == ep["step"][t] and b.cursor[0] == ep["cursor"][t] and b.done[0] == ep["done"][t]
+            np.testing.assert_allclose(obs[0], ep["obs"][t].astype(np.float32), rtol=0, atol=1e-6)
+            assert np.array_equal(obs[0, 11:86], ep["obs"][t][11:86]) and np.array_equal(obs[0, 90:95], ep["obs"][t][90:95])
+            steps += 1
+    assert steps > 1000

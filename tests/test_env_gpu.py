@@ -1,0 +1,199 @@
+"""CUDA env step / observation (through the C ABI) against the golden vectors of the Python
+reference and against the CPU oracle.  Tolerances (north_star): positions / rewards / real-valued
+observation entries within 1e-5 (we assert 1e-9 relative on the fp64 state), every integer output
+(collision, done, info, step counters, occupancy bits) bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import episode
+from gpu_util import assert_close64, assert_obs, city_and_params
+
+pytestmark = pytest.mark.gpu
+
+
+def run_golden(g, env_golden, env27_golden, kind_name):
+    from uavrl_b200 import engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    ne = int(g["epn_episodes"])
+    eps = [episode(g, i) for i in range(ne)]
+    K = eps[0]["sub"].shape[0]
+    env = engine.EnvBatch(city, params, ne, max_subgoals=K, auto_reset=False)
+    env.set_pool(np.stack([e["start"] for e in eps]), np.stack([e["goal"] for e in eps]),
+                 np.array([e["heading"] for e in eps]), np.stack([e["sub"] for e in eps]),
+                 np.array([e["n_sub"] for e in eps]), np.array([e["alias0"] for e in eps]))
+    env.reset(0)
+    st = env.get_state()
+    for i, e in enumerate(eps):        # initial velocity is the reference's bit pattern
+        assert st["vx"][i] == e["vx0"] and st["vy"][i] == e["vy0"] and st["V"][i] == e["V0"]
+    obs0 = env.observe().cpu().numpy()
+    for i, e in enumerate(eps):
+        assert_obs(obs0[i], e["obs0"], "obs0 ep%d" % i)
+    T = max(len(e["action"]) for e in eps)
+    checked = 0
+    for t in range(T):
+        if kind_name == "continuous":
+            a = np.array([e["action"][t] if t < len(e["action"]) else 0.0 for e in eps], np.float64)
+            act = torch.tensor(a, dtype=torch.float64, device="cuda")
+        else:
+            a = np.array([e["action"][t] if t < len(e["action"]) else 13 for e in eps], np.int32)
+            act = torch.tensor(a, dtype=torch.int32, device="cuda")
+        out = env.step(act)
+        st = env.get_state()
+        o = {k: v.cpu().numpy() for k, v in out.items()}
+        for i, e in enumerate(eps):
+            if t >= len(e["action"]):
+                continue
+            w = "ep%d t%d" % (i, t)
+            assert o["done"][i] == e["done_ret"][t] and o["info"][i] == e["info"][t], w
+            assert o["collision"][i] == e["collision"][t] and o["ended"][i] == e["done"][t], w
+            assert st["step"][i] == e["step"][t] and st["cursor"][i] == e["cursor"][t], w
+            assert_close64(st["reward64"][i], e["reward"][t], 1e-9, w + " reward")
+            assert abs(o["reward"][i] - e["reward"][t]) <= 1e-5 * max(1.0, abs(e["reward"][t])), w
+            for k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len"):
+                assert_close64(st[k][i], e[k][t], 1e-9, w + " " + k)
+            assert_obs(o["obs"][i], e["obs"][t], w)
+            checked += 1
+    env.close()
+    return checked
+
+
+def test_golden_episodes_continuous(env_golden, env27_golden):
+    assert run_golden(env_golden, env_golden, env27_golden, "continuous") > 3000
+
+
+def test_golden_episodes_discrete27(env_golden, env27_golden):
+    assert run_golden(env27_golden, env_golden, env27_golden, "discrete27") > 4000
+
+
+def test_threaten_rate_kat(env_golden, env27_golden):
+    from uavrl_b200 import engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    env = engine.EnvBatch(city, params, 1, max_subgoals=4)
+    got = env.threaten_rate(env_golden["kat_threat_pts"])
+    assert np.array_equal(got, env_golden["kat_threat"])      # incl. points within 1 ulp of R / H / bounds
+
+
+def make_pool(env, P, seed):
+    sc = env.make_scenarios(P, seed=seed)
+    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    return sc
+
+
+@pytest.mark.parametrize("mode", ["continuous_f32", "discrete27"])
+def test_against_oracle_2048_envs(env_golden, env27_golden, mode):
+    """2048 envs x 170 steps on synthetic scenarios vs the C oracle (which is pinned to the reference)."""
+    from uavrl_b200 import engine
+    city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
+    N, T, K = 2048, 170, 64
+    env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=False)
+    sc = make_pool(env, N, seed=11)
+    env.reset(0)
+    ob = O.OracleBatch(ocity, oparams, N, K)
+    ob.reset(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    rng = np.random.default_rng(5)
+    n_coll = n_done = 0
+    for t in range(T):
+        if mode == "continuous_f32":
+            a32 = rng.uniform(-1, 1, N).astype(np.float32)
+            # half of the envs steer toward the sub-goal so that sub-goal / success branches are hit
+            out = env.step(torch.tensor(a32, device="cuda"))
+            rew, done, info, coll, oobs = ob.step_(a32.astype(np.float64), O.ACT_CONTINUOUS)
+        else:
+            a = rng.integers(0, 27, N).astype(np.int32)
+            out = env.step(torch.tensor(a, device="cuda"))
+            rew, done, info, coll, oobs = ob.step_(a.astype(np.float64), O.ACT_DISCRETE27)
+        o = {k: v.cpu().numpy() for k, v in out.items()}
+        assert np.array_equal(o["done"], done) and np.array_equal(o["info"], info), t
+        assert np.array_equal(o["collision"], coll) and np.array_equal(o["ended"], ob.done), t
+        st = env.get_state()
+        assert np.array_equal(st["step"], ob.step) and np.array_equal(st["cursor"], ob.cursor), t
+        assert_close64(st["reward64"], rew, 1e-9, "reward t%d" % t)
+        for k in ("px", "py", "pz", "vx", "vy", "V"):
+            assert_close64(st[k], getattr(ob, k), 1e-9, "%s t%d" % (k, t))
+        np.testing.assert_allclose(o["reward"], rew, rtol=1e-5, atol=1e-5)
+        obs64 = ob.state(want64=True)[1]
+        assert_obs(o["obs"], obs64, "obs t%d" % t)
+        n_coll += int(coll.sum()); n_done += int(done.sum())
+    assert n_coll > 1000 and n_done > N      # both branches exercised
+    env.close()
+
+
+def test_auto_reset_and_host_entry_point(env_golden, env27_golden):
+    """auto_reset=1: an ended env restarts from scenario (scen + N) mod P inside the step; also drives
+    the host-buffer entry point (uavrl_env_step_host) and checks it equals the device-pointer call."""
+    from uavrl_b200 import engine
+    city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
+    N, P, T, K = 256, 1024, 400, 64
+    envA = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    envB = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    sc = make_pool(envA, P, seed=3)
+    envB.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    envA.reset(5); envB.reset(5)
+    scen = (5 + np.arange(N)) % P
+    ob = O.OracleBatch(ocity, oparams, N, K)
+    ob.reset(sc["start"][scen], sc["goal"][scen], sc["heading"][scen], sc["sub"][scen], sc["n_sub"][scen])
+    rng = np.random.default_rng(9)
+    h_obs = np.zeros((N, 100), np.float32); h_rew = np.zeros(N, np.float32)
+    h_done = np.zeros(N, np.uint8); h_info = np.zeros(N, np.uint8); h_coll = np.zeros(N, np.uint8); h_end = np.zeros(N, np.uint8)
+    resets = 0
+    for t in range(T):
+        a = rng.integers(0, 27, N).astype(np.int32)
+        out = envA.step(torch.tensor(a, device="cuda"))
+        envB.step_host(a, engine.ACT_DISCRETE27, h_obs, h_rew, h_done, h_info, h_coll, h_end)
+        o = {k: v.cpu().numpy() for k, v in out.items()}
+        assert np.array_equal(o["obs"], h_obs) and np.array_equal(o["reward"], h_rew)
+        assert np.array_equal(o["done"], h_done) and np.array_equal(o["ended"], h_end)
+        rew, done, info, coll, _ = ob.step_(a.astype(np.float64), O.ACT_DISCRETE27, want_obs=False)
+        assert np.array_equal(o["done"], done) and np.array_equal(o["ended"], ob.done)
+        np.testing.assert_allclose(o["reward"], rew, rtol=1e-5, atol=1e-5)
+        ended = np.nonzero(ob.done)[0]
+        if ended.size:                       # UAV.reset() at the episode boundary, oracle side
+            scen[ended] = (scen[ended] + N) % P
+            sub_all = O.OracleBatch(ocity, oparams, ended.size, K)
+            sub_all.reset(sc["start"][scen[ended]], sc["goal"][scen[ended]], sc["heading"][scen[ended]],
+                          sc["sub"][scen[ended]], sc["n_sub"][scen[ended]])
+            for k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len", "step", "cursor",
+                      "n_sub", "done", "alias0"):
+                getattr(ob, k)[ended] = getattr(sub_all, k)
+            ob.goal[ended] = sub_all.goal; ob.sub[ended] = sub_all.sub
+            resets += ended.size
+        st = envA.get_state()
+        assert np.array_equal(st["scenario"], scen)
+        assert_close64(st["px"], ob.px, 1e-9, "px t%d" % t)
+        assert_obs(o["obs"], ob.state(want64=True)[1], "obs t%d" % t)
+    assert resets > N
+    envA.close(); envB.close()
+
+
+def test_full_size_invariants_65536(env_golden, env27_golden):
+    """BASELINE config size (65536 envs): size-independent properties.  After any step no UAV sits in
+    a threat (collisions revert, UAV.py:425-427), counters stay in range, the centre probes are 0,
+    and the run is deterministic."""
+    from uavrl_b200 import engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    N, P, K = 65536, 4096, 64
+    env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    make_pool(env, P, seed=21)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    digests = []
+    for rep in range(2):
+        env.reset(0)
+        g.manual_seed(1)
+        tot_r = 0.0
+        for t in range(60):
+            a = torch.randint(0, 27, (N,), generator=g, device="cuda", dtype=torch.int32)
+            out = env.step(a)
+            tot_r += float(out["reward"].double().sum())
+        st = env.get_state()
+        pts = np.stack([st["px"], st["py"], st["pz"]], 1)
+        assert env.threaten_rate(pts).sum() == 0
+        assert (st["step"] >= 0).all() and (st["step"] < params.max_step).all()
+        obs = out["obs"]
+        assert float(obs[:, [23, 48, 73]].abs().sum()) == 0.0          # probes at offset (0,0)
+        assert bool(((obs[:, 11:86] == 0) | (obs[:, 11:86] == 1)).all())
+        assert torch.isfinite(obs).all() and np.isfinite(tot_r)
+        digests.append((tot_r, float(obs.double().sum()), st["px"].sum()))
+    assert digests[0] == digests[1]
+    env.close()

@@ -1,0 +1,73 @@
+"""The fused lockstep loop (uavrl_train_run): what it stores in the replay ring must be exactly what
+the reference's run_thread_OffPolicy stores (state, action, reward, next_state, returned done), checked
+by replaying the stored actions through the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from gpu_util import assert_obs, city_and_params
+
+pytestmark = pytest.mark.gpu
+
+
+def test_lockstep_ring_matches_oracle_rollout(env_golden, env27_golden):
+    from uavrl_b200 import engine
+    city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
+    N, T, K = 96, 40, 64                       # N not a multiple of 32: ragged last CTA
+    env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=False)
+    sc = env.make_scenarios(N, seed=4)
+    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    env.reset(0)
+    L = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DDQN, batch_size=64, replay_capacity=N * (T + 5),
+                       lockstep_envs=N, seed=3)
+    L.init_params(0)
+    st = engine.train_run(env, L, T, eps=0.7, do_update=False)
+    assert st.env_steps == N * T and st.updates == 0
+    assert L.replay_size() == N * T
+    s, a, r, s2, d = L.gather(np.arange(N * T))
+    s = s.reshape(T, N, 100); s2 = s2.reshape(T, N, 100)
+    a = a.reshape(T, N); r = r.reshape(T, N); d = d.reshape(T, N)
+    ob = O.OracleBatch(ocity, oparams, N, K)
+    ob.reset(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    obs = ob.state(want64=True)[1]
+    net = O.make_net(100, [64, 64], 27, 0)
+    p = L.get_params(0)
+    n_greedy = 0
+    for t in range(T):
+        assert_obs(s[t], obs, "s t%d" % t)
+        assert a[t].min() >= 0 and a[t].max() < 27
+        n_greedy += int((a[t] == O.net_forward(net, p, s[t]).argmax(1)).sum())
+        rew, done, info, coll, _ = ob.step_(a[t].astype(np.float64), O.ACT_DISCRETE27, want_obs=False)
+        obs = ob.state(want64=True)[1]
+        np.testing.assert_allclose(r[t], rew, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(d[t], done)
+        assert_obs(s2[t], obs, "s2 t%d" % t)
+    frac = n_greedy / (N * T)
+    assert 0.25 < frac < 0.45                  # (1 - eps) + eps/27 = 0.326
+    env.close(); L.close()
+
+
+def test_training_loop_learns_and_counts(env_golden, env27_golden):
+    from uavrl_b200 import engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    N = 512
+    env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
+    sc = env.make_scenarios(1024, seed=8)
+    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    env.reset(0)
+    L = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DDQN, batch_size=N, replay_capacity=N * 64,
+                       lockstep_envs=N, seed=1, update_loop=3)
+    L.init_params(1)
+    p0 = L.get_params(0)
+    st = engine.train_run(env, L, 200, eps=0.1)
+    assert st.env_steps == N * 200
+    assert st.updates == 199                    # the first iteration leaves exactly Batch_Size transitions: not > Batch_Size
+    assert L.counters() == (200, 199)
+    assert np.isfinite(st.last_loss) and np.isfinite(st.sum_reward)
+    assert st.episodes_ended > 0
+    p1 = L.get_params(0)
+    assert np.isfinite(p1).all() and np.abs(p1 - p0).max() > 1e-3
+    # ring wrapped (200 iterations through 65 frames) and stayed consistent
+    assert L.replay_size() == N * 64
+    env.close(); L.close()
