@@ -87,6 +87,7 @@ SIGNATURES = {
     "uavrl_learner_comm_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "uavrl_learner_set_peers": (C.c_int, [VP, C.c_int32, C.c_int32, C.POINTER(VP), C.POINTER(VP)]),
     "uavrl_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),
+    "uavrl_train_profile": (C.c_int, [VP, VP, C.c_int32, C.c_float, VP, VP]),
     "uavrl_last_error": (C.c_char_p, []),
     "uavrl_version": (C.c_char_p, []),
     "uavrl_launch_count": (C.c_int64, []),

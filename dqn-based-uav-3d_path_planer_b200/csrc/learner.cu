@@ -563,8 +563,22 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
     return 0;
 }
 
+static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
+                              cudaStream_t st, cudaEvent_t mid);
+
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
                   cudaStream_t st)
+{
+    return launch_update_impl(l, src, B, global_batch, loss_out, apply, st, nullptr);
+}
+
+int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t mid)
+{
+    return launch_update_impl(l, src, B, B, l->loss_dev, true, st, mid);
+}
+
+static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
+                              cudaStream_t st, cudaEvent_t mid)
 {
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
@@ -574,6 +588,7 @@ int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch
     ua.inv_global_b = 1.0f / (float)global_batch;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net), st>>>(l->net, src, ua);
     UAVRL_LAUNCHED();
+    if (mid) UAVRL_CUDA(cudaEventRecord(mid, st));
     l->last_nparts = grid;
     l->last_global_batch = global_batch;
     AdamArgs a;

@@ -85,6 +85,7 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,
                   bool apply, cudaStream_t st);
+int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t mid);
 int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **act, float **rew, uint8_t **done);
 void lockstep_commit(uavrl_learner *l);
 BatchSrc replay_source(uavrl_learner *l, const int32_t *idx_tape);

@@ -10,6 +10,8 @@
 // a device-side RRT is the "next" row 8f-1.
 #include <math.h>
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -130,7 +132,14 @@ extern "C" int uavrl_make_scenarios(const uavrl_env_config *cfg, uint64_t seed, 
     }
     const int K = cfg->max_subgoals;
     const double step = rrt_step > 0 ? (double)rrt_step : 30.0;       // config/UAV.xml sub_granularity
-    for (int s = 0; s < P; ++s) {
+    // scenarios are independent: spread them over the host cores
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if ((int)nthreads > P) nthreads = (unsigned)P;
+    std::atomic<int> next{0}, failed{0};
+    auto worker = [&]() {
+    for (int s = next.fetch_add(1); s < P; s = next.fetch_add(1)) {
         bool ok = false;
         for (int attempt = 0; attempt < 64 && !ok; ++attempt) {
             Rng rng(seed, ((uint64_t)s << 8) | (uint64_t)attempt);
@@ -148,7 +157,12 @@ extern "C" int uavrl_make_scenarios(const uavrl_env_config *cfg, uint64_t seed, 
             n_sub[s] = (int32_t)path.size();
             ok = true;
         }
-        if (!ok) return fail(UAVRL_ERR_INVALID, "RRT found no path within max_subgoals for a scenario");
+        if (!ok) failed.store(1);
     }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned i = 0; i < nthreads; ++i) pool.emplace_back(worker);
+    for (auto &th : pool) th.join();
+    if (failed.load()) return fail(UAVRL_ERR_INVALID, "RRT found no path within max_subgoals for a scenario");
     return 0;
 }

@@ -8,6 +8,8 @@
 #include "env.cuh"
 #include "learner.cuh"
 
+#include <vector>
+
 using namespace uavrl;
 
 extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, int32_t updates_per_iter,
@@ -65,5 +67,44 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
         stats_host->updates = updates;
         stats_host->last_loss = loss;
     }
+    return 0;
+}
+
+extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, float *ms_out, void *stream)
+{
+    if (!env || !l || n_iters <= 0 || !ms_out) return fail(UAVRL_ERR_INVALID, "bad argument");
+    if (l->mode != kReplayLockstep || l->cfg.lockstep_envs != env->d.n || !env->reset_done || !l->frame0_valid)
+        return fail(UAVRL_ERR_STATE, "uavrl_train_profile needs a warmed-up lockstep env/learner pair");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev((size_t)n_iters * 5);
+    for (auto &e : ev) UAVRL_CUDA(cudaEventCreate(&e));
+    int rc;
+    for (int it = 0; it < n_iters; ++it) {
+        float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
+        lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
+        cudaEvent_t *e = &ev[(size_t)it * 5];
+        UAVRL_CUDA(cudaEventRecord(e[0], st));
+        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+        UAVRL_CUDA(cudaEventRecord(e[1], st));
+        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        UAVRL_CUDA(cudaEventRecord(e[2], st));
+        lockstep_commit(l);
+        l->epoch += 1;
+        if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay not warmed up");
+        BatchSrc src = replay_source(l, nullptr);
+        // launch_update = td kernel + reduce/adam kernel; split the pair with an event in between
+        if ((rc = launch_update_split(l, src, l->cfg.batch_size, st, e[3]))) return rc;
+        UAVRL_CUDA(cudaEventRecord(e[4], st));
+    }
+    UAVRL_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) ms_out[k] = 0.f;
+    for (int it = 0; it < n_iters; ++it)
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            UAVRL_CUDA(cudaEventElapsedTime(&ms, ev[(size_t)it * 5 + k], ev[(size_t)it * 5 + k + 1]));
+            ms_out[k] += ms;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
     return 0;
 }

@@ -290,3 +290,10 @@ def train_run(env, learner, n_iters, eps, updates_per_iter=1, do_update=True, wa
     check(_lib.lib().uavrl_train_run(env.h, learner.h, int(n_iters), float(eps), int(updates_per_iter),
                                      int(bool(do_update)), C.byref(st) if want_stats else None, _stream(env.device)))
     return st
+
+
+def train_profile(env, learner, n_iters, eps):
+    """Per-kernel device time (ms, summed over n_iters) of {act, env_step, td_update, reduce_adam}."""
+    ms = np.zeros(4, np.float32)
+    check(_lib.lib().uavrl_train_profile(env.h, learner.h, int(n_iters), float(eps), _ptr(ms), _stream(env.device)))
+    return ms

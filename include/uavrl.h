@@ -214,6 +214,11 @@ int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps
                     int32_t updates_per_iter, int32_t do_update, uavrl_train_stats *stats_host,
                     void *stream);
 
+/* The same loop with a CUDA event recorded on `stream` before/after every kernel: ms_out[4] receives the
+ * summed device time of {act, env_step, td_update, reduce_adam} over the n_iters iterations (bench.py's
+ * roofline pass; event gaps make the loop slower, never use it for throughput). */
+int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, float *ms_out, void *stream);
+
 const char *uavrl_last_error(void);
 const char *uavrl_version(void);
 /* number of kernel launches issued by this library in the calling process since load (bench.py) */

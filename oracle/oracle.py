@@ -255,3 +255,59 @@ class OracleLearner:
         if self.epoch % self.update_loop == 0:
             self.target[:] = self.local          # hard_update, :199-202
         return float(loss), grads
+
+
+def set_threads(n=0):
+    """Set (n > 0) / query the number of host threads the oracle's batched loops use."""
+    return int(lib().ora_set_threads(C.c_int32(n)))
+
+
+class OracleTrainLoop:
+    """CPU restatement of one lockstep training iteration (PathPlan_City.run_thread_OffPolicy + update,
+    Envs/PathPlan_City.py:364-385,757-776) for N envs sharing one learner -- the workload bench.py times
+    on the GPU, run on the host cores: state -> eps-greedy action -> step -> replay add -> sample ->
+    DQN update.  Used only for bench.py's cpu_baseline / --impl reference legs."""
+
+    def __init__(self, city, params, scen, n_envs, net, algo, flat_params, batch, capacity, seed=0, kmax=64):
+        self.N, self.B = n_envs, batch
+        self.batch = OracleBatch(city, params, n_envs, kmax)
+        self.scen, self.P = scen, len(scen["n_sub"])
+        self.sidx = np.arange(n_envs) % self.P
+        s = self.sidx
+        self.batch.reset(scen["start"][s], scen["goal"][s], scen["heading"][s], scen["sub"][s], scen["n_sub"][s])
+        self.net = net
+        self.learner = OracleLearner(net, algo, flat_params)
+        self.rng = np.random.default_rng(seed)
+        self.cap = capacity
+        self.S = np.zeros((capacity, 100), np.float32); self.S2 = np.zeros((capacity, 100), np.float32)
+        self.A = np.zeros(capacity, np.int32); self.R = np.zeros(capacity, np.float32); self.D = np.zeros(capacity, np.float32)
+        self.head = 0; self.count = 0
+        self.obs = self.batch.state()
+
+    def iteration(self, eps, do_update=True):
+        N = self.N
+        u = self.rng.uniform(size=N).astype(np.float32)
+        ra = self.rng.integers(0, self.net.n_actions, N).astype(np.int32)
+        a, _ = act(self.net, self.learner.local, self.obs, eps, u, ra)
+        rew, done, info, coll, obs2 = self.batch.step_(a.astype(np.float64), ACT_DISCRETE27)
+        idx = (self.head + np.arange(N)) % self.cap
+        self.S[idx] = self.obs; self.S2[idx] = obs2; self.A[idx] = a; self.R[idx] = rew; self.D[idx] = done
+        self.head = (self.head + N) % self.cap; self.count = min(self.count + N, self.cap)
+        ended = np.nonzero(self.batch.done)[0]
+        if ended.size:                                   # UAV.reset() at the episode boundary
+            self.sidx[ended] = (self.sidx[ended] + N) % self.P
+            s = self.sidx[ended]
+            tmp = OracleBatch(self.batch.city, self.batch.p, ended.size, self.batch.kmax)
+            tmp.reset(self.scen["start"][s], self.scen["goal"][s], self.scen["heading"][s], self.scen["sub"][s],
+                      self.scen["n_sub"][s])
+            for k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len", "step", "cursor",
+                      "n_sub", "done", "alias0"):
+                getattr(self.batch, k)[ended] = getattr(tmp, k)
+            self.batch.goal[ended] = tmp.goal; self.batch.sub[ended] = tmp.sub
+            obs2 = self.batch.state()
+        self.obs = obs2
+        loss = None
+        if do_update and self.count > self.B:
+            j = self.rng.choice(self.count, self.B, replace=False)
+            loss, _ = self.learner.update(self.S[j], self.A[j], self.R[j], self.S2[j], self.D[j])
+        return loss

@@ -9,6 +9,9 @@
 #include "uav_oracle.h"
 #include <math.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -263,8 +266,10 @@ void ora_batch_step(const ora_city *c, ora_batch *b, double max_v, double min_v,
                     double climb_rate, int32_t max_step, int32_t act_mode, const double *actions,
                     double *reward, uint8_t *done_ret, uint8_t *info, uint8_t *collision, float *obs)
 {
-    double o[100];
+    /* envs are independent: the multi-core CPU baseline runs them on all host threads */
+    #pragma omp parallel for schedule(static)
     for (int32_t e = 0; e < b->n; ++e) {
+        double o[100];
         ora_uav u; ora_step_out out;
         load(b, e, max_v, min_v, steering, climb_rate, max_step, &u);
         ora_step(c, &u, act_mode, actions[e], &out);
@@ -281,8 +286,9 @@ void ora_batch_step(const ora_city *c, ora_batch *b, double max_v, double min_v,
 void ora_batch_state(const ora_city *c, const ora_batch *b, double max_v, double min_v,
                      double steering, double climb_rate, int32_t max_step, float *obs, double *obs64)
 {
-    double o[100];
+    #pragma omp parallel for schedule(static)
     for (int32_t e = 0; e < b->n; ++e) {
+        double o[100];
         ora_uav u;
         load(b, e, max_v, min_v, steering, climb_rate, max_step, &u);
         ora_state(c, &u, o);
@@ -291,4 +297,16 @@ void ora_batch_state(const ora_city *c, const ora_batch *b, double max_v, double
             if (obs64) obs64[(size_t)e * 100 + k] = o[k];
         }
     }
+}
+
+/* number of host threads the batched drivers / learner oracle use (cpu_baseline reports it) */
+int32_t ora_set_threads(int32_t n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return (int32_t)omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
