@@ -44,7 +44,7 @@ FWD_FLOPS = {"qvalue3": 24448, "qnet2": 2 * (100 * 64 + 64 * 27), "vanet2": 2 * 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1])")
@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -198,7 +198,7 @@ def run_reference_arm(a):
            "dtype": "f64 env / f32 learner", "data": "synthetic", "config": config_dict(a, 1),
            "cpu_baseline": {"value": v, "unit": "env_steps/s", "cores": nthreads, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    print(json.dumps(out, default=float))
 
 
 # ============================================================================ GPU arm
@@ -344,7 +344,7 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out, default=float))
     if world > 1:
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()

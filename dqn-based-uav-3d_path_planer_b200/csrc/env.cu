@@ -38,6 +38,7 @@ __device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs
     s.px = st[0]; s.py = st[1]; s.pz = st[2];
     s.gx = gl[0]; s.gy = gl[1]; s.gz = gl[2];
     s.vx = v0[0]; s.vy = v0[1]; s.V = v0[2];
+    s.theta = angle_xy(s.vx, s.vy);
     s.score = 0.0; s.total = 0.0; s.path_len = 0.0;
     s.step = 0; s.cursor = 0; s.done = 0;
     s.n_sub = d.pool_nsub[scen];
@@ -68,26 +69,26 @@ __device__ __forceinline__ int threat_masked(const EnvConst &k, const Cyl *cyl, 
     return 0;
 }
 
-template <bool DO_STEP>
+template <bool DO_STEP, int EPB>
 __global__ void __launch_bounds__(kEnvThreads)
 env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
            uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
 {
     __shared__ Cyl s_cyl[kMaxCyl];
-    __shared__ __align__(16) float s_obs[kEnvsPerBlock][kObsDim];
-    __shared__ double s_pos[3][kEnvsPerBlock];
-    __shared__ unsigned long long s_mask[kEnvsPerBlock];
+    __shared__ __align__(16) float s_obs[EPB][kObsDim];
+    __shared__ double s_pos[3][EPB];
+    __shared__ unsigned long long s_mask[EPB];
 
     const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * kEnvsPerBlock;
+    const int e0 = blockIdx.x * EPB;
     for (int i = tid; i < d.k.n_cyl * 6; i += kEnvThreads)
         reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
     __syncthreads();
 
     if (tid < 32) {
         const int e = e0 + tid;
-        const bool valid = e < d.n;
+        const bool valid = (tid < EPB) && (e < d.n);
         unsigned long long mask = 0ull;
         double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
         int n_stepped = 0, n_ended = 0, n_coll = 0;
@@ -99,6 +100,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
             s.gx = d.gx[e]; s.gy = d.gy[e]; s.gz = d.gz[e];
             s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
             s.done = d.done[e]; s.alias = d.alias[e];
+            s.theta = d.theta[e];
             int scen = d.scen[e];
             mask = cull_mask(d, s_cyl, s.px, s.py);
             if (DO_STEP) {
@@ -133,7 +135,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
                     d.n_sub[e] = s.n_sub;
                 }
                 d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
-                d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V;
+                d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V; d.theta[e] = s.theta;
                 d.score[e] = s.score; d.total[e] = s.total; d.path_len[e] = s.path_len;
                 d.step[e] = s.step; d.cursor[e] = s.cursor;
                 d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
@@ -145,8 +147,10 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
             }
             px = s.px; py = s.py; pz = s.pz;
         }
-        s_pos[0][tid] = px; s_pos[1][tid] = py; s_pos[2][tid] = pz;
-        s_mask[tid] = mask;
+        if (tid < EPB) {
+            s_pos[0][tid] = px; s_pos[1][tid] = py; s_pos[2][tid] = pz;
+            s_mask[tid] = mask;
+        }
         if (DO_STEP) {
             const unsigned full = 0xffffffffu;
 #pragma unroll
@@ -168,7 +172,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
     __syncthreads();
 
     // phase 2: occupancy probes
-    for (int idx = tid; idx < kEnvsPerBlock * 80; idx += kEnvThreads) {
+    for (int idx = tid; idx < EPB * 80; idx += kEnvThreads) {
         const int le = idx / 80, p = idx - 80 * le;
         if (e0 + le >= d.n) break;
         double x, y, z;
@@ -179,7 +183,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
     __syncthreads();
 
     // phase 3: coalesced 16-byte stores of the contiguous [nvalid][100] tile
-    const int nvalid = min(kEnvsPerBlock, d.n - e0);
+    const int nvalid = min(EPB, d.n - e0);
     const int nvec = nvalid * (kObsDim / 4);
     float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)e0 * kObsDim);
     const float4 *src = reinterpret_cast<const float4 *>(&s_obs[0][0]);
@@ -195,7 +199,7 @@ __global__ void env_reset_kernel(EnvDev d, int first)
     load_scenario(d, scen, s);
     d.scen[e] = scen;
     d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
-    d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V;
+    d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V; d.theta[e] = s.theta;
     d.gx[e] = s.gx; d.gy[e] = s.gy; d.gz[e] = s.gz;
     d.score[e] = 0.0; d.total[e] = 0.0; d.path_len[e] = 0.0; d.rew64[e] = 0.0;
     d.step[e] = 0; d.cursor[e] = 0; d.n_sub[e] = s.n_sub;
@@ -215,16 +219,21 @@ __global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, u
 int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st)
 {
-    const int blocks = (d.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
-    env_kernel<true><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+    if (d.n <= kSmallBatchEnvs) {
+        const int blocks = (d.n + kEnvsPerBlockSmall - 1) / kEnvsPerBlockSmall;
+        env_kernel<true, kEnvsPerBlockSmall><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+    } else {
+        const int blocks = (d.n + kEnvsPerBlockLarge - 1) / kEnvsPerBlockLarge;
+        env_kernel<true, kEnvsPerBlockLarge><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+    }
     UAVRL_LAUNCHED();
     return 0;
 }
 
 int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st)
 {
-    const int blocks = (d.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
-    env_kernel<false><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    const int blocks = (d.n + kEnvsPerBlockLarge - 1) / kEnvsPerBlockLarge;
+    env_kernel<false, kEnvsPerBlockLarge><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -280,7 +289,7 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
 
     const size_t n = (size_t)d.n;
     double **f64[] = { &d.px, &d.py, &d.pz, &d.vx, &d.vy, &d.V, &d.score, &d.total, &d.path_len,
-                       &d.gx, &d.gy, &d.gz, &d.rew64 };
+                       &d.gx, &d.gy, &d.gz, &d.rew64, &d.theta };
     for (auto p : f64) { int rc = dev_alloc(p, n); if (rc) return rc; }
     int32_t **i32[] = { &d.step, &d.cursor, &d.n_sub, &d.scen };
     for (auto p : i32) { int rc = dev_alloc(p, n); if (rc) return rc; }
@@ -307,7 +316,7 @@ int uavrl_env_destroy(uavrl_env *env)
     EnvDev &d = env->d;
     cudaSetDevice(env->cfg.device);
     void *ptrs[] = { (void *)d.cyl, d.px, d.py, d.pz, d.vx, d.vy, d.V, d.score, d.total, d.path_len, d.gx, d.gy,
-                     d.gz, d.rew64, d.step, d.cursor, d.n_sub, d.scen, d.done, d.alias, d.stat_counts,
+                     d.gz, d.rew64, d.theta, d.step, d.cursor, d.n_sub, d.scen, d.done, d.alias, d.stat_counts,
                      d.stat_reward, env->h_act_dev, env->h_obs_dev, env->h_rew_dev, env->h_flags_dev };
     for (void *p : ptrs) cudaFree(p);
     free_pool(d);

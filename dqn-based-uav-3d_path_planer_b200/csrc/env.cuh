@@ -5,8 +5,11 @@
 
 namespace uavrl {
 
-constexpr int kEnvsPerBlock = 32;      // one warp steps 32 envs; 4 warps share their 2560 probes
-constexpr int kEnvThreads = 128;
+constexpr int kEnvThreads = 128;       // warp 0 steps the CTA's envs; all 4 warps share their probes
+// envs per CTA: 32 for big batches; 8 when the batch is small, so that the latency-bound fp64 chains
+// of a 4096-env step spread over 512 CTAs (3-4 per SM) instead of 128
+constexpr int kEnvsPerBlockLarge = 32, kEnvsPerBlockSmall = 8;
+constexpr int kSmallBatchEnvs = 16384;
 constexpr int kMaxCyl = 64;            // candidate sets are 64-bit masks
 
 // Everything a kernel needs, passed by value.
@@ -17,7 +20,7 @@ struct EnvDev {
     double cull_w;                      // half-width of the probe window incl. one step of motion
     const Cyl *cyl;
     // per-env state, structure of arrays
-    double *px, *py, *pz, *vx, *vy, *V, *score, *total, *path_len, *gx, *gy, *gz, *rew64;
+    double *px, *py, *pz, *vx, *vy, *V, *score, *total, *path_len, *gx, *gy, *gz, *rew64, *theta;
     int32_t *step, *cursor, *n_sub, *scen;
     uint8_t *done, *alias;
     // scenario pool (read-only during stepping)

@@ -57,6 +57,7 @@ struct EnvConst {
 
 struct EnvRegs {
     double px, py, pz, vx, vy, V, score, total, path_len, gx, gy, gz;
+    double theta;                       // calculate_angle(0, V_vector) of the current V_vector
     int32_t step, cursor, n_sub;
     int32_t done, alias;
 };
@@ -85,6 +86,10 @@ UAVRL_HD double angle_xy(double dx, double dy)
     t = (t >= 360.0) ? dsub(t, 360.0) : t;
     return dmul(ddiv(t, 180.0), kPi);
 }
+
+// The reference evaluates calculate_angle(0, V_vector) three times per step on the SAME vector
+// (seta_old at :411 is last step's value, tri_V at :423 and state[7] at :526 are this step's):
+// EnvRegs.theta caches it -- identical value, one atan2 instead of three.
 
 // building.py:20-26 -- strict `z > H` and strict `dist < R`
 UAVRL_HD int cyl_hit(const Cyl &c, double x, double y, double z)
@@ -145,7 +150,7 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
 
     s.step += 1;                                                     // :408
     const double ox = s.px, oy = s.py, oz = s.pz;                    // :409
-    const double seta_old = angle_xy(s.vx, s.vy);                    // :411
+    const double seta_old = s.theta;                                 // :411 (cached angle_xy(vx, vy))
     const double dis_old = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);        // :412
     const double dg_old = dist3(s.px, s.py, s.pz, s.gx, s.gy, s.gz);         // :413
     const double seta_new = dadd(seta_old, dmul(a0, k.steering));    // :414
@@ -163,7 +168,8 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
     if (act_mode == 1) s.pz = dadd(s.pz, dz);
     if (alias) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }            // the aliased sub-goal moved too
     const double tri_goal = angle_xy(dsub(sg.x, s.px), dsub(sg.y, s.py));    // :422
-    double tri_V = angle_xy(s.vx, s.vy);                             // :423
+    s.theta = angle_xy(s.vx, s.vy);
+    double tri_V = s.theta;                                          // :423
     if (threat(s.px, s.py, s.pz)) {                                  // :425
         r = dsub(r, 0.3);
         s.px = ox; s.py = oy; s.pz = oz;                             // :427
@@ -200,7 +206,7 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
             s.V = calc_v(k, s.vx, s.vy);
             const P3 ng = sub(s.cursor);
             const double tg = angle_xy(dsub(ng.x, s.px), dsub(ng.y, s.py));   // :488
-            const double tv = angle_xy(s.vx, s.vy);                  // :489
+            const double tv = s.theta;                               // :489 (V_vector unchanged by the local reset)
             r = dadd(r, dmul(0.2, cos(fabs(dsub(tg, tv)))));         // :490
             r = dadd(r, (double)(k.max_step - s.step));              // :491
             s.score = dadd(s.score, r); s.total = dadd(s.total, r);
@@ -221,34 +227,37 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
 
 // UAV.py:515-531,557-560: the 20 real-valued entries of the observation (probes are separate).
 // `o` points at this env's 100 floats (stride 1).
+// Outputs only (rounded to fp32 afterwards): x/10 is computed as x*0.1, within 1 fp64 ulp of the division.
+UAVRL_HD double tenth(double x) { return dmul(x, 0.1); }
+
 template <class SubFn>
 UAVRL_HD void obs_scalars(const EnvRegs &s, SubFn sub, float *o)
 {
     const int nleft = s.n_sub - s.cursor;
-    o[0] = (float)ddiv((double)s.step, 100.0);                       // :518
+    o[0] = (float)dmul((double)s.step, 0.01);                       // :518
     float o1 = 0.f, o2 = 0.f, o3 = 0.f, o8 = 0.f, o9 = 0.f, o10 = 0.f;
     if (nleft >= 1) {                                                // :519-522
         P3 sg = sub(s.cursor);
         if (s.alias && s.cursor == 0) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }
-        o1 = (float)ddiv(dsub(sg.x, s.px), 10.0);
-        o2 = (float)ddiv(dsub(sg.y, s.py), 10.0);
-        o3 = (float)ddiv(dsub(sg.z, s.pz), 10.0);
+        o1 = (float)tenth(dsub(sg.x, s.px));
+        o2 = (float)tenth(dsub(sg.y, s.py));
+        o3 = (float)tenth(dsub(sg.z, s.pz));
     }
     if (nleft >= 2) {                                                // :528-531
         const P3 s1 = sub(s.cursor + 1);
-        o8 = (float)ddiv(dsub(s1.x, s.px), 10.0);
-        o9 = (float)ddiv(dsub(s1.y, s.py), 10.0);
-        o10 = (float)ddiv(dsub(s1.z, s.pz), 10.0);
+        o8 = (float)tenth(dsub(s1.x, s.px));
+        o9 = (float)tenth(dsub(s1.y, s.py));
+        o10 = (float)tenth(dsub(s1.z, s.pz));
     }
     o[1] = o1; o[2] = o2; o[3] = o3;
     o[4] = (float)s.V;                                               // :523
     o[5] = (float)s.vx; o[6] = (float)s.vy;
-    o[7] = (float)angle_xy(s.vx, s.vy);                              // :526
+    o[7] = (float)s.theta;                                           // :526
     o[8] = o8; o[9] = o9; o[10] = o10;
-    o[86] = (float)ddiv(dsub(s.gx, s.px), 10.0);                     // :557-559
-    o[87] = (float)ddiv(dsub(s.gy, s.py), 10.0);
-    o[88] = (float)ddiv(dsub(s.gz, s.pz), 10.0);
-    o[89] = (float)ddiv(s.pz, 10.0);                                 // :560
+    o[86] = (float)tenth(dsub(s.gx, s.px));                     // :557-559
+    o[87] = (float)tenth(dsub(s.gy, s.py));
+    o[88] = (float)tenth(dsub(s.gz, s.pz));
+    o[89] = (float)tenth(s.pz);                                 // :560
     o[95] = 0.f; o[96] = 0.f; o[97] = 0.f; o[98] = 0.f; o[99] = 0.f;
 }
 

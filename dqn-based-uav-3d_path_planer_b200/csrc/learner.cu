@@ -15,6 +15,7 @@
 // a broadcast LDS.128.  Gradients leave the CTA as one coalesced partial vector; the optimiser
 // kernel reduces the partials in a fixed order (deterministic) and applies Adam.
 #include "learner.cuh"
+#include "tma.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -67,24 +68,37 @@ static int build_net(const uavrl_learner_config &c, NetDev &n)
 // ------------------------------------------------------------------ device building blocks
 __device__ __forceinline__ int ldw_of(int out) { return (out & 1) ? out : out + 1; }
 
-// Stage one network's weights into smem, transposed: Wt[k][o] = W[o][k]; pad rows (k >= in) zeroed.
-__device__ void load_weights(const NetDev &net, const float *__restrict__ params, float *sw)
+// flat parameter index -> position in the smem weight image (Wt[k][o] transposed, ld = out|1; biases after)
+static void build_image_map(const NetDev &net, std::vector<int32_t> &map)
 {
+    map.assign((size_t)net.P, 0);
     for (int l = 0; l < net.n_layers; ++l) {
         const LayerDev &L = net.L[l];
-        const int ldw = ldw_of(L.out), in = L.in, in_pad = round_up(in, 4);
+        const int ldw = (L.out & 1) ? L.out : L.out + 1, in = L.in;
         const int out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
-        float *Wt = sw + L.smem_w, *bs = sw + L.smem_b;
-        for (int i = threadIdx.x; i < out_main * in; i += blockDim.x) {
-            const int o = i / in, k = i - o * in;
-            Wt[k * ldw + o] = params[L.w_off + i];
+        for (int o = 0; o < out_main; ++o) {
+            for (int k = 0; k < in; ++k) map[(size_t)L.w_off + (size_t)o * in + k] = L.smem_w + k * ldw + o;
+            map[(size_t)L.b_off + o] = L.smem_b + o;
         }
-        if (L.w2_off >= 0)
-            for (int k = threadIdx.x; k < in; k += blockDim.x) Wt[k * ldw + out_main] = params[L.w2_off + k];
-        for (int i = threadIdx.x; i < (in_pad - in) * ldw; i += blockDim.x) Wt[in * ldw + i] = 0.f;
-        for (int o = threadIdx.x; o < out_main; o += blockDim.x) bs[o] = params[L.b_off + o];
-        if (L.w2_off >= 0 && threadIdx.x == 0) bs[out_main] = params[L.b2_off];
+        if (L.w2_off >= 0) {
+            for (int k = 0; k < in; ++k) map[(size_t)L.w2_off + k] = L.smem_w + k * ldw + out_main;
+            map[(size_t)L.b2_off] = L.smem_b + out_main;
+        }
     }
+}
+
+__global__ void pack_image_kernel(int P, const float *__restrict__ flat, const int32_t *__restrict__ map, float *__restrict__ img)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) img[map[i]] = flat[i];
+}
+
+// Stage a whole network image (weights transposed + biases, pads zero) into smem with the TMA engine.
+// Called by one thread; everybody then waits on the mbarrier.
+__device__ __forceinline__ void stage_weights(const NetDev &net, const float *__restrict__ img, float *sw, uint64_t *bar)
+{
+    fence_proxy_async();
+    bulk_g2s_chunked(sw, img, (uint32_t)net.smem_w_floats * 4u, bar);
 }
 
 // Y[b][o] = act(sum_k X[b][k] * Wt[k][o] + bias[o]), b < 32.  lane -> o, warp -> 4 samples.
@@ -295,13 +309,18 @@ act_kernel(NetDev net, const float *__restrict__ params, const float *__restrict
     float *sB = sA + kTile * kMaxDim;
     float *head = sB + kTile * kMaxDim;
     __shared__ const float *rows[kTile];
-    load_weights(net, params, sw);
+    __shared__ uint64_t wbar;
+    if (threadIdx.x == 0) { mbar_init(&wbar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) stage_weights(net, params, sw, &wbar);      // params = the network's smem image
+    bool weights_ready = false;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int e0 = t * kTile;
         if (threadIdx.x < kTile) rows[threadIdx.x] = (e0 + threadIdx.x < n) ? obs + (size_t)(e0 + threadIdx.x) * net.in_dim : nullptr;
         __syncthreads();
         if (net.in_dim % 4 == 0) load_rows(rows, smem + net.act_off[0], net.act_ld[0], net.in_dim);
         else load_rows_scalar(rows, smem + net.act_off[0], net.act_ld[0], net.in_dim);
+        if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
         __syncthreads();
         net_forward(net, sw, smem + net.act_off[0], net.act_ld[0], smem, false, sA, sB, head);
         if (threadIdx.x < kTile && e0 + threadIdx.x < n) {
@@ -358,20 +377,24 @@ __device__ uint64_t perm_index(uint64_t i, uint64_t M, const uint32_t key[4])
 
 // ------------------------------------------------------------------ TD update kernel
 struct UpdateArgs {
-    const float *local, *target;
+    const float *img_local, *img_target;
     float *partials, *loss_partials;
-    int B, n_tiles, algo;
+    int B, n_tiles, algo, dual;
     float gamma, inv_global_b;
 };
 
+// smem: [W primary (local)] [W secondary (target), only if dual] [planes X0,H1..] [X2] [sA] [sB] [Q] [Qt] [Ql2]
 __global__ void __launch_bounds__(kNetThreads)
 update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
 {
     extern __shared__ __align__(16) float smem[];
-    float *sw = smem;
-    float *X0 = smem + net.act_off[0];
+    const int wf = net.smem_w_floats;
+    float *swL = smem;                                   // local image (single-buffer mode: whichever net is live)
+    float *swT = ua.dual ? smem + wf : smem;
+    float *pl = smem + (ua.dual ? wf : 0);               // base the NetDev plane offsets are relative to
+    float *X0 = pl + net.act_off[0];
     const int ld0 = net.act_ld[0];
-    float *X2 = smem + net.smem_total_floats;            // next-state plane
+    float *X2 = pl + net.smem_total_floats;              // next-state plane
     float *sA = X2 + kTile * ld0;                        // scratch / gradient ping
     float *sB = sA + kTile * kMaxDim;                    // scratch / gradient pong
     float *Q = sB + kTile * kMaxDim;                     // [32][32] Q_local(s)
@@ -381,12 +404,21 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
     __shared__ const float *rows_s2[kTile];
     __shared__ int s_act[kTile];
     __shared__ float s_rew[kTile], s_done[kTile], s_loss[kTile];
+    __shared__ uint64_t barL, barT;
 
     float *gpart = ua.partials + (size_t)blockIdx.x * net.P;
     float loss_acc = 0.f;
     int iter = 0;
     uint32_t pkey[4];
     Philox::gen(src.key, src.epoch, 0x5A17ull, pkey);
+    uint32_t phL = 0, phT = 0;
+
+    if (threadIdx.x == 0) { mbar_init(&barL, 1); mbar_init(&barT, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stage_weights(net, ua.img_target, swT, &barT);                  // target first: it is needed first
+        if (ua.dual) stage_weights(net, ua.img_local, swL, &barL);
+    }
 
     for (int t = blockIdx.x; t < ua.n_tiles; t += gridDim.x, ++iter) {
         // ---- resolve the tile's transitions
@@ -423,17 +455,23 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
         if (net.in_dim % 4 == 0) { load_rows(rows_s, X0, ld0, net.in_dim); load_rows(rows_s2, X2, ld0, net.in_dim); }
         else { load_rows_scalar(rows_s, X0, ld0, net.in_dim); load_rows_scalar(rows_s2, X2, ld0, net.in_dim); }
         // ---- target network on s'
-        load_weights(net, ua.target, sw);
+        if (!ua.dual && iter > 0) {                       // single buffer: bring the target image back
+            __syncthreads();
+            if (threadIdx.x == 0) stage_weights(net, ua.img_target, swT, &barT);
+        }
+        if (!ua.dual || iter == 0) { mbar_wait(&barT, phT); phT ^= 1; }
         __syncthreads();
-        net_forward(net, sw, X2, ld0, smem, false, sA, sB, Qt);
+        net_forward(net, swT, X2, ld0, pl, false, sA, sB, Qt);
         // ---- local network on s' (double-DQN action selection) and on s (kept for backward)
-        load_weights(net, ua.local, sw);
+        if (!ua.dual) {
+            if (threadIdx.x == 0) stage_weights(net, ua.img_local, swL, &barL);
+            mbar_wait(&barL, phL); phL ^= 1;
+        } else if (iter == 0) { mbar_wait(&barL, phL); phL ^= 1; }
         __syncthreads();
-        if (ua.algo != UAVRL_ALGO_DQN) net_forward(net, sw, X2, ld0, smem, false, sA, sB, Ql2);
-        net_forward(net, sw, X0, ld0, smem, true, sA, sB, Q);
+        if (ua.algo != UAVRL_ALGO_DQN) net_forward(net, swL, X2, ld0, pl, false, sA, sB, Ql2);
+        net_forward(net, swL, X0, ld0, pl, true, sA, sB, Q);
         // ---- TD target, loss, dLoss/dHead  (head gradient plane = sA, [32][kMaxDim], zero padded)
         const int nA = net.n_actions;
-        const LayerDev &H = net.L[net.n_layers - 1];
         if (threadIdx.x < kTile) {
             const int b = threadIdx.x;
             float *g = sA + b * kMaxDim;
@@ -465,11 +503,11 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
         float *dY = sA, *dXb = sB;
         for (int l = net.n_layers - 1; l >= 0; --l) {
             const LayerDev &L = net.L[l];
-            const float *Xin = smem + net.act_off[l];
+            const float *Xin = pl + net.act_off[l];
             const int ldx = net.act_ld[l];
             layer_backward_dw(dY, kMaxDim, Xin, ldx, gpart, L, iter > 0);
             if (l > 0) {
-                layer_backward_dx(dY, kMaxDim, sw + L.smem_w, Xin, ldx, dXb, kMaxDim, L.in, L.out);
+                layer_backward_dx(dY, kMaxDim, swL + L.smem_w, Xin, ldx, dXb, kMaxDim, L.in, L.out);
                 // zero the pad columns [in, round_up(in,32)) the next dW pass will read
                 const int pad0 = L.in, pad1 = round_up(L.in, 32);
                 for (int i = threadIdx.x; i < kTile * (pad1 - pad0); i += blockDim.x)
@@ -478,7 +516,6 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
             __syncthreads();
             float *tmp = dY; dY = dXb; dXb = tmp;
         }
-        (void)H;
     }
     if (threadIdx.x == 0) ua.loss_partials[blockIdx.x] = loss_acc;
 }
@@ -489,16 +526,35 @@ struct AdamArgs {
     float step_size, beta1_c, beta2, beta2_c, eps, bc2_sqrt, inv_b;
 };
 
-__global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
-                                   float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m,
-                                   float *__restrict__ v, float *__restrict__ target, float *__restrict__ loss_out)
+// 64 parameters per CTA x 4 partial-groups: the cross-CTA gradient reduction runs 4-wide with
+// independent loads in flight, then Adam; fixed summation order -> run-to-run deterministic.
+__global__ void __launch_bounds__(256)
+reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
+                   float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
+                   float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
+                   const int32_t *__restrict__ img_map, float *__restrict__ loss_out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.P) {
-        float g;
+    __shared__ float red[4][64];
+    const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + ix;
+    float g = 0.f;
+    if (i < a.P && a.nparts > 0) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        int c = cg;
+        for (; c + 12 < a.nparts; c += 16) {
+            g0 += partials[(size_t)c * a.P + i];
+            g1 += partials[(size_t)(c + 4) * a.P + i];
+            g2 += partials[(size_t)(c + 8) * a.P + i];
+            g3 += partials[(size_t)(c + 12) * a.P + i];
+        }
+        for (; c < a.nparts; c += 4) g0 += partials[(size_t)c * a.P + i];
+        g = (g0 + g1) + (g2 + g3);
+    }
+    red[cg][ix] = g;
+    __syncthreads();
+    if (cg == 0 && i < a.P) {
         if (a.nparts > 0) {
-            g = 0.f;
-            for (int c = 0; c < a.nparts; ++c) g += partials[(size_t)c * a.P + i];
+            g = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
             grad[i] = g;
         } else {
             g = grad[i];                                  // already reduced (and all-reduced) by the caller
@@ -511,13 +567,18 @@ __global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partial
             const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
             p = p - a.step_size * (mi / denom);
             m[i] = mi; v[i] = vi; local[i] = p;
-            if (a.hard) target[i] = p;                    // hard_update (DuelingDQN_Trainer.py:199-202)
+            const int im = img_map[i];
+            img_local[im] = p;
+            if (a.hard) { target[i] = p; img_target[im] = p; }   // hard_update (DuelingDQN_Trainer.py:199-202)
         }
     }
-    if (i == 0 && loss_out && a.nparts > 0) {
+    if (blockIdx.x == 0 && threadIdx.x >= 224 && loss_out && a.nparts > 0) {     // last warp: loss = sum / B
+        const int lane = threadIdx.x & 31;
         float s = 0.f;
-        for (int c = 0; c < a.nparts; ++c) s += loss_partials[c];
-        *loss_out = s * a.inv_b;
+        for (int c = lane; c < a.nparts; c += 32) s += loss_partials[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) *loss_out = s * a.inv_b;
     }
 }
 
@@ -546,17 +607,19 @@ __global__ void push_kernel(int n, int in, int64_t head, int64_t cap, const floa
 
 // ------------------------------------------------------------------ host launchers
 static size_t act_smem_bytes(const NetDev &n) { return (size_t)(n.smem_total_floats + 2 * kTile * kMaxDim + kTile * 32) * 4; }
-static size_t upd_smem_bytes(const NetDev &n)
+static size_t upd_smem_bytes(const NetDev &n, int dual)
 {
-    return (size_t)(n.smem_total_floats + kTile * n.act_ld[0] + 2 * kTile * kMaxDim + 3 * kTile * 32) * 4;
+    return (size_t)((dual ? n.smem_w_floats : 0) + n.smem_total_floats + kTile * n.act_ld[0] + 2 * kTile * kMaxDim +
+                    3 * kTile * 32) * 4;
 }
+static const size_t kMaxDynSmem = 227 * 1024;
 
 int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st)
 {
     const int n_tiles = (n + kTile - 1) / kTile;
     const int grid = n_tiles < 4 * 148 ? n_tiles : 4 * 148;
-    act_kernel<<<grid, kNetThreads, act_smem_bytes(l->net), st>>>(l->net, l->local, obs, n, eps, is_train, u_tape,
+    act_kernel<<<grid, kNetThreads, act_smem_bytes(l->net), st>>>(l->net, l->img_local, obs, n, eps, is_train, u_tape,
                                                                 rand_tape, l->cfg.seed ^ 0xAC7ull, l->act_calls++,
                                                                 actions, nullptr, q_out, n_tiles);
     UAVRL_LAUNCHED();
@@ -583,10 +646,10 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
     UpdateArgs ua;
-    ua.local = l->local; ua.target = l->target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
-    ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma;
+    ua.img_local = l->img_local; ua.img_target = l->img_target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
+    ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma; ua.dual = l->dual_weights;
     ua.inv_global_b = 1.0f / (float)global_batch;
-    update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net), st>>>(l->net, src, ua);
+    update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
     UAVRL_LAUNCHED();
     if (mid) UAVRL_CUDA(cudaEventRecord(mid, st));
     l->last_nparts = grid;
@@ -604,9 +667,19 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
         a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
         a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
     }
-    const int threads = 256, blocks = (a.P + threads - 1) / threads;
-    reduce_adam_kernel<<<blocks, threads, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
-                                                  l->target, loss_out ? loss_out : l->loss_dev);
+    reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
+                                                       l->target, l->img_local, l->img_target, l->img_map,
+                                                       loss_out ? loss_out : l->loss_dev);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+static int repack_images(uavrl_learner *l, cudaStream_t st)
+{
+    const int threads = 256, blocks = (l->net.P + threads - 1) / threads;
+    pack_image_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->local, l->img_map, l->img_local);
+    UAVRL_LAUNCHED();
+    pack_image_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->img_map, l->img_target);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -674,6 +747,16 @@ int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
         (rc = dev_alloc(&l->partials, P * (size_t)l->max_ctas)) || (rc = dev_alloc(&l->loss_partials, (size_t)l->max_ctas)) ||
         (rc = dev_alloc(&l->loss_dev, 1)) || (rc = dev_alloc(&l->flags, 64)))
         return rc;
+    {
+        const size_t wf = (size_t)l->net.smem_w_floats;
+        if ((rc = dev_alloc(&l->img_local, wf)) || (rc = dev_alloc(&l->img_target, wf)) || (rc = dev_alloc(&l->img_map, P))) return rc;
+        std::vector<int32_t> map;
+        build_image_map(l->net, map);
+        UAVRL_CUDA(cudaMemcpy(l->img_map, map.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
+        l->dual_weights = upd_smem_bytes(l->net, 1) <= kMaxDynSmem ? 1 : 0;
+        if (upd_smem_bytes(l->net, l->dual_weights) > kMaxDynSmem || act_smem_bytes(l->net) > kMaxDynSmem)
+            return fail(UAVRL_ERR_INVALID, "network too large for the shared-memory resident kernels");
+    }
     const size_t in = (size_t)cfg->in_dim;
     if (cfg->lockstep_envs > 0) {
         const int64_t N = cfg->lockstep_envs;
@@ -692,7 +775,7 @@ int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
         (rc = dev_alloc(&l->r_done, (size_t)l->slots)))
         return rc;
     UAVRL_CUDA(cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem_bytes(l->net)));
-    UAVRL_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(l->net)));
+    UAVRL_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(l->net, l->dual_weights)));
     *out = l;
     return 0;
 }
@@ -702,7 +785,8 @@ int uavrl_learner_destroy(uavrl_learner *l)
     if (!l) return 0;
     cudaSetDevice(l->cfg.device);
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
-                     l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev };
+                     l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev, l->img_local, l->img_target,
+                     l->img_map };
     for (void *p : ptrs) cudaFree(p);
     delete l;
     return 0;
@@ -724,6 +808,7 @@ int uavrl_learner_set_params(uavrl_learner *l, int32_t which, const float *h)
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
     UAVRL_CUDA(cudaDeviceSynchronize());
     UAVRL_CUDA(cudaMemcpy(which_buf(l, which), h, (size_t)l->net.P * 4, cudaMemcpyHostToDevice));
+    if (which <= 1) { int rc = repack_images(l, 0); if (rc) return rc; UAVRL_CUDA(cudaDeviceSynchronize()); }
     return 0;
 }
 
@@ -860,9 +945,9 @@ int uavrl_learner_apply_grads(uavrl_learner *l, void *stream)
     a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
     a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
     a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
-    const int threads = 256, blocks = (a.P + threads - 1) / threads;
-    reduce_adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a, l->partials, l->loss_partials, l->grad, l->local,
-                                                                    l->m, l->v, l->target, nullptr);
+    reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, (cudaStream_t)stream>>>(a, l->partials, l->loss_partials, l->grad, l->local,
+                                                                         l->m, l->v, l->target, l->img_local, l->img_target,
+                                                                         l->img_map, nullptr);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -873,6 +958,9 @@ int uavrl_learner_hard_update(uavrl_learner *l, void *stream)
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
     const int threads = 256, blocks = (l->net.P + threads - 1) / threads;
     copy_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(l->net.P, l->local, l->target);
+    UAVRL_LAUNCHED();
+    const int wf = l->net.smem_w_floats;
+    copy_kernel<<<(wf + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(wf, l->img_local, l->img_target);
     UAVRL_LAUNCHED();
     return 0;
 }

@@ -53,6 +53,11 @@ struct uavrl_learner {
     uavrl::NetDev net;
     // parameters and optimiser state (flat, state_dict order)
     float *local = nullptr, *target = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
+    // kernel-layout copies of the two networks (exactly the smem weight image: transposed, padded),
+    // kept in sync by the optimiser kernel so a CTA stages a whole network with one TMA bulk copy
+    float *img_local = nullptr, *img_target = nullptr;
+    int32_t *img_map = nullptr;       // flat parameter index -> image index
+    int32_t dual_weights = 0;         // update kernel keeps local+target images resident at once
     float *partials = nullptr;        // [max_ctas][P] per-CTA gradient partials
     float *loss_partials = nullptr;   // [max_ctas]
     float *loss_dev = nullptr;        // [1]

@@ -50,6 +50,7 @@ void shim_step(double width, double h, int n_cyl, const double *buildings, doubl
         s.gx = b->goal[3 * e]; s.gy = b->goal[3 * e + 1]; s.gz = b->goal[3 * e + 2];
         s.step = b->step[e]; s.cursor = b->cursor[e]; s.n_sub = b->n_sub[e];
         s.done = b->done[e]; s.alias = b->alias0[e];
+        s.theta = angle_xy(s.vx, s.vy);        // the kernel carries this in its state (same value)
         const double *q = b->sub + (size_t)e * b->kmax * 3;
         auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
         if (actions) {

@@ -82,11 +82,11 @@ def make_pool(env, P, seed):
 
 
 @pytest.mark.parametrize("mode", ["continuous_f32", "discrete27"])
-def test_against_oracle_2048_envs(env_golden, env27_golden, mode):
+def test_against_oracle_1024_envs(env_golden, env27_golden, mode):
     """2048 envs x 170 steps on synthetic scenarios vs the C oracle (which is pinned to the reference)."""
     from uavrl_b200 import engine
     city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
-    N, T, K = 2048, 170, 64
+    N, T, K = 1024, 160, 64
     env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=False)
     sc = make_pool(env, N, seed=11)
     env.reset(0)
@@ -116,7 +116,7 @@ def test_against_oracle_2048_envs(env_golden, env27_golden, mode):
         obs64 = ob.state(want64=True)[1]
         assert_obs(o["obs"], obs64, "obs t%d" % t)
         n_coll += int(coll.sum()); n_done += int(done.sum())
-    assert n_coll > 1000 and n_done > N      # both branches exercised
+    assert n_coll > 500 and n_done > N      # both branches exercised
     env.close()
 
 
