@@ -49,7 +49,8 @@ class LearnerConfig(C.Structure):
 
 class TrainStats(C.Structure):
     _fields_ = [("env_steps", C.c_int64), ("updates", C.c_int64), ("episodes_ended", C.c_int64),
-                ("collisions", C.c_int64), ("sum_reward", C.c_double), ("last_loss", C.c_float)]
+                ("collisions", C.c_int64), ("n_success", C.c_int64), ("n_lose", C.c_int64),
+                ("sum_reward", C.c_double), ("last_loss", C.c_float)]
 
 
 _lib = None
@@ -84,6 +85,7 @@ SIGNATURES = {
     "uavrl_learner_grad_ptr": (VP, [VP]),
     "uavrl_learner_apply_grads": (C.c_int, [VP, VP]),
     "uavrl_learner_hard_update": (C.c_int, [VP, VP]),
+    "uavrl_learner_lockstep_restart": (C.c_int, [VP]),
     "uavrl_learner_comm_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "uavrl_learner_set_peers": (C.c_int, [VP, C.c_int32, C.c_int32, C.POINTER(VP), C.POINTER(VP)]),
     "uavrl_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),

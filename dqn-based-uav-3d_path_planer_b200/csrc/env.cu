@@ -91,7 +91,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
         const bool valid = (tid < EPB) && (e < d.n);
         unsigned long long mask = 0ull;
         double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
-        int n_stepped = 0, n_ended = 0, n_coll = 0;
+        int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
         if (valid) {
             EnvRegs s;
             s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
@@ -120,6 +120,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
                 step_core(d.k, s, mode, act, sub, threat, o);
                 rew = o.reward;
                 n_stepped = 1; n_coll = o.coll; n_ended = s.done;
+                n_succ = (o.info == 1); n_lose = (o.info == 2);
                 if (reward) reward[e] = (float)o.reward;
                 d.rew64[e] = o.reward;
                 if (done_out) done_out[e] = (uint8_t)o.done_ret;
@@ -158,12 +159,16 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
                 n_stepped += __shfl_xor_sync(full, n_stepped, off);
                 n_ended += __shfl_xor_sync(full, n_ended, off);
                 n_coll += __shfl_xor_sync(full, n_coll, off);
+                n_succ += __shfl_xor_sync(full, n_succ, off);
+                n_lose += __shfl_xor_sync(full, n_lose, off);
                 rew += __shfl_xor_sync(full, rew, off);
             }
             if (tid == 0 && n_stepped) {
                 atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
                 if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
                 if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);
+                if (n_succ) atomicAdd(&d.stat_counts[3], (unsigned long long)n_succ);
+                if (n_lose) atomicAdd(&d.stat_counts[4], (unsigned long long)n_lose);
                 atomicAdd(d.stat_reward, rew);
             }
         }
@@ -295,7 +300,7 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
     for (auto p : i32) { int rc = dev_alloc(p, n); if (rc) return rc; }
     { int rc = dev_alloc(&d.done, n); if (rc) return rc; }
     { int rc = dev_alloc(&d.alias, n); if (rc) return rc; }
-    { int rc = dev_alloc(&d.stat_counts, 4); if (rc) return rc; }
+    { int rc = dev_alloc(&d.stat_counts, 8); if (rc) return rc; }
     { int rc = dev_alloc(&d.stat_reward, 1); if (rc) return rc; }
     UAVRL_CUDA(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
     *out = env;

@@ -965,6 +965,15 @@ int uavrl_learner_hard_update(uavrl_learner *l, void *stream)
     return 0;
 }
 
+int uavrl_learner_lockstep_restart(uavrl_learner *l)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    if (l->mode != kReplayLockstep) return 0;
+    l->count = 0;
+    l->frame0_valid = false;
+    return 0;
+}
+
 int uavrl_learner_comm_buffers(uavrl_learner *l, void **grad_dev, void **flag_dev, size_t *grad_bytes, size_t *flag_bytes)
 {
     if (!l) return fail(UAVRL_ERR_INVALID, "null learner");

@@ -24,7 +24,7 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    unsigned long long c0[4] = { 0, 0, 0, 0 };
+    unsigned long long c0[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     double r0 = 0.0;
     if (stats_host) {
         UAVRL_CUDA(cudaStreamSynchronize(st));
@@ -56,13 +56,15 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
     }
     if (stats_host) {
         UAVRL_CUDA(cudaStreamSynchronize(st));
-        unsigned long long c1[4]; double r1; float loss;
+        unsigned long long c1[8]; double r1; float loss;
         UAVRL_CUDA(cudaMemcpy(c1, env->d.stat_counts, sizeof(c1), cudaMemcpyDeviceToHost));
         UAVRL_CUDA(cudaMemcpy(&r1, env->d.stat_reward, sizeof(r1), cudaMemcpyDeviceToHost));
         UAVRL_CUDA(cudaMemcpy(&loss, l->loss_dev, sizeof(loss), cudaMemcpyDeviceToHost));
         stats_host->env_steps = (int64_t)(c1[0] - c0[0]);
         stats_host->episodes_ended = (int64_t)(c1[1] - c0[1]);
         stats_host->collisions = (int64_t)(c1[2] - c0[2]);
+        stats_host->n_success = (int64_t)(c1[3] - c0[3]);
+        stats_host->n_lose = (int64_t)(c1[4] - c0[4]);
         stats_host->sum_reward = r1 - r0;
         stats_host->updates = updates;
         stats_host->last_loss = loss;

@@ -272,6 +272,9 @@ class Learner:
     def hard_update(self):
         check(_lib.lib().uavrl_learner_hard_update(self.h, _stream(self.device)))
 
+    def lockstep_restart(self):
+        check(_lib.lib().uavrl_learner_lockstep_restart(self.h))
+
 
 class _DevView:
     """Expose a raw device pointer as a torch tensor through __cuda_array_interface__."""

@@ -1,0 +1,9 @@
+"""Trainer plug-in: vanilla DQN (Trainer/DQN_Trainer.py) on the B200 library."""
+import uavrl_b200  # noqa: F401  (repository root must be on sys.path)
+from uavrl_b200 import engine
+from uavrl_b200.plugins._trainer_base import TrainerB200
+
+
+class DQN_Trainer_B200(TrainerB200):
+    ALGO = engine.ALGO_DQN
+    TAG = ""                       # DQN_Trainer.py:55-56: q_target_<name>.pth / q_local_<name>.pth

@@ -1,0 +1,191 @@
+"""Env plug-in: the reference's PathPlan_City (Envs/PathPlan_City.py) with `num_UAV` UAV instances
+stepped in lockstep on a B200 and ONE shared Q-network trainer (the north-star design; the
+reference keeps one trainer per UAV -- with num_UAV = 1 both coincide).
+
+Constructor takes the same parsed-XML dict the reference's EnvFactory passes
+(config/PathPlan_City.xml <env> ... </env>): len/width/h, num_UAV, Agent.xml_path_agent,
+Agent.Trainer.Trainer_path, Obstacles.buildings.  simulator.py drives it unchanged:
+env.run_eposide(eps) -> result dict; env.Agents[i].Train_time / Testing_time; env.Trainer.hard_update().
+"""
+import importlib
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+import uavrl_b200  # noqa: F401  (repository root must be on sys.path)
+from uavrl_b200 import engine
+from uavrl_b200.plugins.xmlconfig import None2Value, XML2Dict
+
+
+class UAVBatchView:
+    """What simulator.py / PathPlan_City read from an Agent, aggregated over the batch."""
+
+    def __init__(self, env, name="UAV_batch"):
+        self.env, self.name = env, name
+        self.Train_time = 0.0        # UAV.py:124-125, accumulated by run_eposide
+        self.Testing_time = 0.0
+        self.Trainer = env.Trainer
+        self.score = 0.0
+        self.Step = 0
+        self.done = False
+        self.UEs = []
+        self.energy_cost_total = 0
+        self.task_collect = 0
+        self.transition_dict = {'states': [], 'actions': [], 'next_states': [], 'rewards': [], 'dones': []}
+
+    @property
+    def path(self):
+        st = self.env.batch.get_state()
+        return np.stack([st["px"], st["py"], st["pz"]], 1).tolist()
+
+    def state(self):
+        return self.env.states()
+
+    def record_list(self):
+        pass
+
+    def reset(self):
+        self.env.Scene_Random_Reset()
+
+
+def uav_params_from_dict(uav: dict):
+    """Agents/UAV.py:25-32: Max_V int(), Steering_angle degrees -> rad, Max_Step int()."""
+    return engine.UavParams(max_v=int(uav.get("Max_V")), min_v=float(None2Value(uav.get("Min_V"), 0.6)),
+                            steering=float(uav.get("Steering_angle")) / 180 * math.pi,
+                            climb_rate=float(None2Value(uav.get("climb_rate"), 1.0)), max_step=int(uav.get("Max_Step")))
+
+
+def buildings_from_dict(bdict: dict):
+    """Obstacles/building.py:8-11 for every <Threaten> of config/buildings.xml."""
+    th = bdict["Threaten"]
+    if isinstance(th, dict):
+        th = [th]
+    return np.array([[float(t["position"]["x"]), float(t["position"]["y"]), float(t["position"]["z"]),
+                      float(None2Value(t.get("_R"), 10)), float(None2Value(t.get("_H"), 20))] for t in th], np.float64)
+
+
+class PathPlan_City_B200:
+    def __init__(self, param: dict) -> None:
+        # BaseEnv.__init__ (BaseClass/BaseEnv.py:19-21,34)
+        self.len = int(None2Value(param.get("len"), 100))
+        self.width = int(None2Value(param.get("width"), 100))
+        self.h = int(None2Value(param.get("h"), 20))
+        self.Is_AC = int(None2Value(param.get("Is_AC"), 0))
+        self.eps = float(None2Value(param.get('eps'), 0.1))
+        self.Is_On_Policy = int(None2Value(param.get('Is_On_Policy'), 0))
+        if self.Is_On_Policy:
+            raise ValueError("PathPlan_City_B200 implements the off-policy (DQN-family) loop only")
+        self.param = param
+        self.device_index = int(None2Value(param.get("device"), 0))
+        # buildings (PathPlan_City.py:43-51)
+        bpath = os.path.normpath(param['Obstacles']['buildings'])
+        self.buildings_param = XML2Dict(bpath).get('buildings')
+        self.buildings_table = buildings_from_dict(self.buildings_param)
+        self.city = engine.City(self.len, self.width, self.h, self.buildings_table)
+        # agents (PathPlan_City.py:54-69)
+        self.num_UAV = int(param.get('num_UAV'))
+        agents_params = param.get('Agent')
+        self.uav_dict = XML2Dict(os.path.normpath(agents_params['xml_path_agent'])).get('Agent')
+        self.uav_params = uav_params_from_dict(self.uav_dict)
+        self.sub_granularity = int(None2Value(self.uav_dict.get("sub_granularity"), 30))
+        fn = self.uav_dict.get("update_function_name")
+        self.discrete = (fn != "update_PathPlan")            # update_PathPlan27: the discrete-27 extension
+        self.batch = engine.EnvBatch(self.city, self.uav_params, self.num_UAV, max_subgoals=64,
+                                     device=self.device_index, auto_reset=True)
+        self.pool_size = int(None2Value(param.get("scenario_pool"), max(1024, 2 * self.num_UAV)))
+        sc = self.batch.make_scenarios(self.pool_size, seed=int(None2Value(param.get("seed"), 42)),
+                                       rrt_step=self.sub_granularity)
+        self.batch.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+        self._next_first = 0
+        # trainer (one, shared)
+        tpath = os.path.normpath(agents_params['Trainer']['Trainer_path'])
+        tdict = XML2Dict(tpath).get('Trainer')
+        tdict['name'] = 'UAV_0'
+        tdict['lockstep_envs'] = str(self.num_UAV)
+        tdict['device'] = str(self.device_index)
+        ttype = tdict.get('Trainer_Type')
+        try:
+            mod = importlib.import_module("uavrl_b200.plugins." + ttype)
+        except ImportError:
+            mod = importlib.import_module(ttype)
+        self.Trainer = getattr(mod, ttype)(tdict)
+        self.Agents = [UAVBatchView(self)]
+        self.result = {}
+        self.epoch = 0
+        self.print_loop = int(None2Value(param.get('print_loop'), 2))
+        self.Is_FL = 0
+        self.executed_time = 0
+        self.Scene_Random_Reset()
+
+    # ---- geometry the planners use
+    def Threaten_rate(self, p):
+        return int(self.batch.threaten_rate([[p.x, p.y, p.z]])[0])
+
+    # ---- reset / observation / step for all UAVs
+    def Scene_Random_Reset(self):
+        """UAV.reset() for the whole batch (a new block of the scenario pool).  Individual UAVs whose
+        episode ends restart by themselves inside the step kernel."""
+        self.batch.reset(self._next_first)
+        self._next_first = (self._next_first + self.num_UAV) % self.pool_size
+        self.Trainer._learner_reset_lockstep()
+
+    def states(self):
+        return self.batch.observe().cpu().numpy()
+
+    def Move_Agents(self, actions):
+        """BaseEnv.Move_Agent for every UAV: actions [N] (int32 indices or float32 steering) ->
+        (next_states [N,100], rewards [N], dones [N], infos [N])."""
+        a = np.asarray(actions)
+        if self.discrete:
+            t = torch.from_numpy(a.astype(np.int32)).cuda(self.device_index)
+        else:
+            t = torch.from_numpy(a.astype(np.float32)).cuda(self.device_index)
+        out = self.batch.step(t)
+        infos = [engine.INFO_NAMES[i] for i in out["info"].cpu().numpy()]
+        return out["obs"].cpu().numpy(), out["reward"].cpu().numpy(), out["done"].cpu().numpy().astype(bool), infos
+
+    def Check_uav_Done(self):
+        return bool(self.batch.get_state()["done"].all())
+
+    def Reset_Result(self, eps_rate):
+        self.result = {'success': 0, 'lose': 0, 'meet_threaten': 0, 'normal': 0, 'loss': 0, 'sum_epoch': 0,
+                       'eps': eps_rate, 'score': 0, 'average_score': 0, 'step': 0}
+
+    # ---- the episode loop (PathPlan_City.run_eposide :410-478, off-policy branch)
+    def run_eposide(self, eps_rate=0.1):
+        """One 'episode' of the batch: lockstep iterations (act -> step -> replay add -> update) until as
+        many episodes ended as there are UAVs (every UAV finished one episode on average; finished UAVs
+        restart from the scenario pool, which is the reference's per-episode UAV.reset())."""
+        self.Reset_Result(eps_rate)
+        if not self.discrete:
+            raise ValueError("DQN-family trainers need update_function_name = update_PathPlan27")
+        learner = self.Trainer._learner
+        t0 = time.time()
+        ended = steps = updates = coll = n_s = n_l = 0
+        reward_sum, loss, chunk, iters = 0.0, 0.0, 16, 0
+        max_iters = 64 * self.uav_params.max_step
+        while ended < self.num_UAV and iters < max_iters:
+            st = engine.train_run(self.batch, learner, chunk, eps_rate, 1, bool(self.Trainer.Is_Train))
+            ended += st.episodes_ended; steps += st.env_steps; updates += st.updates; coll += st.collisions
+            n_s += st.n_success; n_l += st.n_lose; reward_sum += st.sum_reward; loss = st.last_loss
+            iters += chunk
+        dt = time.time() - t0
+        ag = self.Agents[0]
+        ag.Train_time += dt
+        ag.score = reward_sum / max(1, ended)
+        ag.Step = iters
+        self.result.update(success=n_s, lose=n_l, normal=steps - n_s - n_l, loss=float(loss),
+                           sum_epoch=self.Trainer.epoch, score=reward_sum, average_score=reward_sum / self.num_UAV,
+                           step=iters, env_steps=steps, updates=updates, collisions=coll, episodes=ended)
+        self.epoch += 1
+        self.executed_time += dt
+        return self.result
+
+    def run_XML_scene(self):
+        pass
+
+    def update(self):
+        return [self.Trainer.learn_off_policy()]

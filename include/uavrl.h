@@ -189,6 +189,10 @@ int uavrl_learner_compute_grads(uavrl_learner *l, const int32_t *idx_tape_dev, i
 float *uavrl_learner_grad_ptr(uavrl_learner *l);          /* device, [param_count] fp32 */
 int uavrl_learner_apply_grads(uavrl_learner *l, void *stream);
 int uavrl_learner_hard_update(uavrl_learner *l, void *stream);   /* DuelingDQN_Trainer.py:199-202 */
+/* After an explicit uavrl_env_reset the lockstep ring's current frame no longer matches the env
+ * state: call this; the next uavrl_train_run re-observes into a fresh frame and the lockstep replay
+ * restarts empty (envs that end episodes restart by themselves with auto_reset and need no call). */
+int uavrl_learner_lockstep_restart(uavrl_learner *l);
 
 /* One-shot NVLink all-reduce fused with Adam: every rank reads all peers' gradient vectors over
  * peer-mapped memory in rank order (bit-identical replicas) inside the optimiser kernel.
@@ -204,9 +208,10 @@ int uavrl_learner_set_peers(uavrl_learner *l, int32_t rank, int32_t world, void 
  *   obs -> get_action -> Move_Agent -> replay add -> [sample -> Trainer.update]
  * n_iters lockstep iterations; observations are written once, straight into the replay frame ring.
  * updates_per_iter optimiser steps follow each env step (reference: 1).  stats_host (optional)
- * receives {env_steps, updates, episodes_ended, sum_reward, last_loss, collisions}. */
+ * receives the counters below. */
 typedef struct {
     int64_t env_steps, updates, episodes_ended, collisions;
+    int64_t n_success, n_lose;       /* steps whose info was 'success' / 'lose' (PathPlan_City.Run_statistics) */
     double sum_reward;
     float last_loss;
 } uavrl_train_stats;

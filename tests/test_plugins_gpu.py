@@ -1,0 +1,120 @@
+"""Reference-facing plug-ins on the GPU: the trainer classes reproduce the reference trainers'
+results through the reference's own method names (get_action / update(transition_dict) / save /
+Load_Mod / hard_update), and the env plug-in runs an episode from the XML configs exactly the way
+simulator.py drives the reference (env.run_eposide(eps))."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BASE = {"w": "100", "hiden_dim": "64", "output": "27", "name": "t0", "LEARNING_RATE": "0.0005", "Batch_Size": "64",
+        "gamma": "0.99", "save_loop": "1000000000", "replay_size": "1000", "Update_loop": "3", "Is_Train": "1"}
+CASES = [("dueling_vanet2", "DuelingDQN_Trainer_B200", "VAnet2"), ("ddqn_qvalue3", "DDQN_Trainer_B200", "QValueNet_SAC"),
+         ("dqn_qnet2", "DQN_Trainer_B200", "Qnet2")]
+
+
+def make(ttype, net, tmp, **kw):
+    import importlib
+    mod = importlib.import_module("uavrl_b200.plugins." + ttype)
+    p = dict(BASE, Trainer_Type=ttype, NetWork=net, model_path=str(tmp), **kw)
+    return getattr(mod, ttype)(p)
+
+
+@pytest.mark.parametrize("name,ttype,net", CASES)
+def test_trainer_plugin_matches_reference_trainer(dqn_golden, tmp_path, name, ttype, net):
+    g = dqn_golden
+    tr = make(ttype, net, tmp_path)
+    tr._learner.set_params(g[name + "_local0"], 0)
+    tr._learner.set_params(g[name + "_target0"], 1)
+    snap = list(g[name + "_snap"])
+    for step in range(10):
+        td = {"states": g["batch_s"][step].tolist(), "actions": g["batch_a"][step].tolist(),
+              "next_states": g["batch_s2"][step].tolist(), "rewards": g["batch_r"][step].tolist(),
+              "dones": g["batch_d"][step].tolist()}
+        res = tr.update(td)                                     # the reference's call (PathPlan_City.py:757-776)
+        assert res["sum_epoch"] == step + 1 == tr.epoch
+        assert np.isclose(float(res["loss"]), g[name + "_loss"][step], rtol=2e-5)
+        if step in snap:
+            k = snap.index(step)
+            flat = np.concatenate([v.numpy().ravel() for v in tr.state_dict(0).values()])
+            np.testing.assert_allclose(flat, g[name + "_local"][k], atol=2e-5)
+            flat_t = np.concatenate([v.numpy().ravel() for v in tr.state_dict(1).values()])
+            np.testing.assert_allclose(flat_t, g[name + "_target"][k], atol=2e-5)
+    # get_action: greedy with eps = 0, single state -> python int, batch -> array
+    q_ref = g[name + "_q_final"]
+    a = tr.get_action(g["batch_s"][0], 0.0)
+    assert np.array_equal(a, q_ref.argmax(1))
+    assert tr.get_action(g["batch_s"][0][3], 0.0) == int(q_ref[3].argmax())
+    assert tr.update({"states": [], "actions": [], "next_states": [], "rewards": [], "dones": []})["sum_epoch"] == 11
+    # checkpoint round trip in the reference's .pth format, loadable by torch modules of the reference's shape
+    tr.save()
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and all(f.endswith("_t0.pth") for f in files)
+    ck = torch.load(os.path.join(tmp_path, [f for f in files if f.startswith("q_local")][0]), weights_only=False)
+    assert set(ck) == {"model", "optimizer", "epoch"} and ck["epoch"] == 11
+    keys = list(ck["model"])
+    assert keys[0] == "fc1.weight" and ck["model"]["fc1.weight"].shape == (64, 100)
+    assert ck["optimizer"]["param_groups"][0]["betas"] == (0.9, 0.999)
+    tr2 = make(ttype, net, tmp_path)                            # Load_Mod() in the constructor resumes
+    assert tr2.epoch == 11
+    assert np.array_equal(tr2._learner.get_params(0), tr._learner.get_params(0))
+    assert np.array_equal(tr2._learner.get_params(1), tr._learner.get_params(1))
+    assert np.array_equal(tr2._learner.get_params(2), tr._learner.get_params(2))
+    assert tr2._learner.counters() == tr._learner.counters()
+    tr2.hard_update()
+    assert np.array_equal(tr2._learner.get_params(1), tr2._learner.get_params(0))
+
+
+def test_replay_facade_matches_reference_flow(dqn_golden, tmp_path):
+    """replay_memory.add / len(buffer) / sample2 / Push_Replay as PathPlan_City.run_thread_OffPolicy uses them."""
+    g = dqn_golden
+    tr = make("DDQN_Trainer_B200", "QValueNet_SAC", tmp_path)
+    s, a, r, s2, d = (g["batch_" + k][0] for k in ("s", "a", "r", "s2", "d"))
+    for i in range(70):
+        tr.replay_memory.add(s[i % 64], int(a[i % 64]), float(r[i % 64]), s2[i % 64], bool(d[i % 64]))
+    assert len(tr.replay_memory.buffer) == 70
+    tr.Push_Replay((torch.tensor(s[:1]), torch.tensor([[int(a[0])]]), torch.tensor([[r[0]]]), torch.tensor(s2[:1]),
+                    torch.tensor([[d[0]]])))
+    assert len(tr.replay_memory.buffer) == 71 > tr.Batch_Size
+    b_s, b_a, b_r, b_ns, b_d, idx, w = tr.replay_memory.sample2(tr.Batch_Size)
+    assert b_s.shape == (64, 100) and len(b_a) == 64 and idx is None and w is None
+    res = tr.update({'states': b_s, 'actions': b_a, 'next_states': b_ns, 'rewards': b_r, 'dones': b_d})
+    assert np.isfinite(float(res["loss"]))
+    assert tr.learn_off_policy()["sum_epoch"] == 2
+
+
+def test_env_plugin_runs_an_episode_from_xml(tmp_path):
+    """EnvFactory-style construction from the XML files + simulator-style driving."""
+    import importlib
+    from uavrl_b200.plugins import xmlconfig
+    cwd = os.getcwd()
+    os.chdir(ROOT)                                   # the reference resolves ./config/... relative to CWD
+    try:
+        cfg = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "PathPlan_City_B200.xml"))["simulator"]
+        env_dict = cfg["env"]
+        env_dict["num_UAV"] = "256"
+        env_dict["scenario_pool"] = "512"
+        mod = importlib.import_module("uavrl_b200.plugins." + env_dict["Env_Type"])
+        env = getattr(mod, env_dict["Env_Type"])(env_dict)           # FactoryClass/EnvFactory.py:17-20
+    finally:
+        os.chdir(cwd)
+    env.Trainer.save_loop = 10 ** 9
+    env.Trainer.Batch_Size = 4096
+    assert (env.len, env.width, env.h) == (500, 500, 100) and len(env.buildings_table) == 26
+    assert env.Threaten_rate(type("L", (), {"x": -1.0, "y": 5.0, "z": 0.0})()) == 1
+    eps = xmlconfig.epsilon_annealing(1, float(cfg["min_eps"]), int(cfg["max_eps_episode"]))
+    info = env.run_eposide(eps)
+    for k in ("average_score", "loss", "score", "success", "lose", "meet_threaten", "normal", "sum_epoch", "eps", "step"):
+        assert k in info                                              # the keys simulator.py / record() read
+    assert info["episodes"] >= 256 and info["env_steps"] == 256 * info["step"]
+    assert info["success"] + info["lose"] + info["normal"] == info["env_steps"]
+    assert np.isfinite(info["loss"]) and "%.3f" % info["average_score"]
+    assert env.Agents[0].Train_time > 0 and env.Agents[0].Testing_time == 0
+    s = env.states()
+    ns, r, d, infos = env.Move_Agents(np.full(256, 13, np.int32))
+    assert s.shape == ns.shape == (256, 100) and set(infos) <= {"normal", "success", "lose"}
