@@ -15,7 +15,9 @@
 // a broadcast LDS.128.  Gradients leave the CTA as one coalesced partial vector; the optimiser
 // kernel reduces the partials in a fixed order (deterministic) and applies Adam.
 #include "learner.cuh"
+#include "tc_forward.cuh"
 #include "tma.cuh"
+#include "umma.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -91,6 +93,16 @@ __global__ void pack_image_kernel(int P, const float *__restrict__ flat, const i
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) img[map[i]] = flat[i];
+}
+
+__global__ void pack_tc_kernel(int P, const float *__restrict__ flat, const int32_t *__restrict__ hi_map,
+                               const int32_t *__restrict__ lo_map, float *__restrict__ img)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float p = flat[i];
+    if (lo_map[i] >= 0) { float hi, lo; tf32_split(p, hi, lo); img[hi_map[i]] = hi; img[lo_map[i]] = lo; }
+    else img[hi_map[i]] = p;                              // biases stay fp32
 }
 
 // Stage a whole network image (weights transposed + biases, pads zero) into smem with the TMA engine.
@@ -344,43 +356,13 @@ act_kernel(NetDev net, const float *__restrict__ params, const float *__restrict
     }
 }
 
-// ------------------------------------------------------------------ replay index sampling
-__device__ __forceinline__ uint32_t mix32(uint32_t x)
-{
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
-
-// i-th element of a keyed pseudo-random permutation of [0, M): 4-round Feistel on 2*h bits with
-// cycle walking.  perm(0..B-1) = B distinct uniform indices = random.sample(range(M), B)
-// (BaseClass/replay_buffer.py:49).
-__device__ uint64_t perm_index(uint64_t i, uint64_t M, const uint32_t key[4])
-{
-    int bits = 1;
-    while ((1ull << bits) < M) ++bits;
-    const int h = (bits + 1) / 2;
-    const uint32_t mask = (h >= 32) ? 0xffffffffu : ((1u << h) - 1u);
-    uint64_t x = i;
-    do {
-        uint32_t Lh = (uint32_t)(x >> h) & mask, Rh = (uint32_t)x & mask;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t f = mix32(Rh ^ key[r]) & mask;
-            const uint32_t nl = Rh;
-            Rh = Lh ^ f;
-            Lh = nl;
-        }
-        x = ((uint64_t)Lh << h) | Rh;
-    } while (x >= M);
-    return x;
-}
-
 // ------------------------------------------------------------------ TD update kernel
 struct UpdateArgs {
     const float *img_local, *img_target;
     float *partials, *loss_partials;
     int B, n_tiles, algo, dual;
     float gamma, inv_global_b;
+    const float *y_in;                 // non-null: TD targets already computed (tensor-core pass); skip the target net
 };
 
 // smem: [W primary (local)] [W secondary (target), only if dual] [planes X0,H1..] [X2] [sA] [sB] [Q] [Qt] [Ql2]
@@ -415,60 +397,48 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
 
     if (threadIdx.x == 0) { mbar_init(&barL, 1); mbar_init(&barT, 1); fence_barrier_init(); }
     __syncthreads();
+    const bool have_y = ua.y_in != nullptr;
     if (threadIdx.x == 0) {
-        stage_weights(net, ua.img_target, swT, &barT);                  // target first: it is needed first
-        if (ua.dual) stage_weights(net, ua.img_local, swL, &barL);
+        if (have_y) stage_weights(net, ua.img_local, swL, &barL);       // only the local network is evaluated here
+        else {
+            stage_weights(net, ua.img_target, swT, &barT);              // target first: it is needed first
+            if (ua.dual) stage_weights(net, ua.img_local, swL, &barL);
+        }
     }
 
     for (int t = blockIdx.x; t < ua.n_tiles; t += gridDim.x, ++iter) {
         // ---- resolve the tile's transitions
         if (threadIdx.x < kTile) {
             const int gb = t * kTile + threadIdx.x;
-            const float *ps = nullptr, *ps2 = nullptr;
-            int a = 0; float r = 0.f, d = 0.f;
-            if (gb < ua.B) {
-                if (src.mode == kBatchExplicit) {
-                    ps = src.frames + (size_t)gb * net.in_dim;
-                    ps2 = src.s2_rows + (size_t)gb * net.in_dim;
-                    a = src.act[gb]; r = src.rew[gb]; d = src.done_f32[gb];
-                } else {
-                    const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb]
-                                                    : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
-                    int64_t slot, row, row2;
-                    if (src.mode == kReplayLockstep) {
-                        const int64_t f = (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
-                        const int64_t e = (int64_t)(j % src.n_envs);
-                        slot = f * src.n_envs + e; row = slot;
-                        row2 = ((f + 1) % src.cap) * src.n_envs + e;
-                    } else {
-                        slot = (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
-                    }
-                    ps = src.frames + (size_t)row * net.in_dim;
-                    ps2 = src.frames + (size_t)row2 * net.in_dim;
-                    a = src.act[slot]; r = src.rew[slot]; d = src.done_u8[slot] ? 1.f : 0.f;
-                }
-            }
-            rows_s[threadIdx.x] = ps; rows_s2[threadIdx.x] = ps2;
-            s_act[threadIdx.x] = a; s_rew[threadIdx.x] = r; s_done[threadIdx.x] = d;
+            Transition tr; tr.s = nullptr; tr.s2 = nullptr; tr.a = 0; tr.r = 0.f; tr.d = 0.f;
+            if (gb < ua.B) tr = resolve_transition(src, gb, net.in_dim, pkey);
+            rows_s[threadIdx.x] = tr.s; rows_s2[threadIdx.x] = ua.y_in ? nullptr : tr.s2;
+            s_act[threadIdx.x] = tr.a; s_rew[threadIdx.x] = tr.r; s_done[threadIdx.x] = tr.d;
         }
         __syncthreads();
-        if (net.in_dim % 4 == 0) { load_rows(rows_s, X0, ld0, net.in_dim); load_rows(rows_s2, X2, ld0, net.in_dim); }
-        else { load_rows_scalar(rows_s, X0, ld0, net.in_dim); load_rows_scalar(rows_s2, X2, ld0, net.in_dim); }
-        // ---- target network on s'
-        if (!ua.dual && iter > 0) {                       // single buffer: bring the target image back
+        if (net.in_dim % 4 == 0) { load_rows(rows_s, X0, ld0, net.in_dim); if (!have_y) load_rows(rows_s2, X2, ld0, net.in_dim); }
+        else { load_rows_scalar(rows_s, X0, ld0, net.in_dim); if (!have_y) load_rows_scalar(rows_s2, X2, ld0, net.in_dim); }
+        if (have_y) {
+            if (iter == 0) { mbar_wait(&barL, phL); phL ^= 1; }
             __syncthreads();
-            if (threadIdx.x == 0) stage_weights(net, ua.img_target, swT, &barT);
+        } else {
+            // ---- target network on s'
+            if (!ua.dual && iter > 0) {                   // single buffer: bring the target image back
+                __syncthreads();
+                if (threadIdx.x == 0) stage_weights(net, ua.img_target, swT, &barT);
+            }
+            if (!ua.dual || iter == 0) { mbar_wait(&barT, phT); phT ^= 1; }
+            __syncthreads();
+            net_forward(net, swT, X2, ld0, pl, false, sA, sB, Qt);
+            // ---- local network on s' (double-DQN action selection)
+            if (!ua.dual) {
+                if (threadIdx.x == 0) stage_weights(net, ua.img_local, swL, &barL);
+                mbar_wait(&barL, phL); phL ^= 1;
+            } else if (iter == 0) { mbar_wait(&barL, phL); phL ^= 1; }
+            __syncthreads();
+            if (ua.algo != UAVRL_ALGO_DQN) net_forward(net, swL, X2, ld0, pl, false, sA, sB, Ql2);
         }
-        if (!ua.dual || iter == 0) { mbar_wait(&barT, phT); phT ^= 1; }
-        __syncthreads();
-        net_forward(net, swT, X2, ld0, pl, false, sA, sB, Qt);
-        // ---- local network on s' (double-DQN action selection) and on s (kept for backward)
-        if (!ua.dual) {
-            if (threadIdx.x == 0) stage_weights(net, ua.img_local, swL, &barL);
-            mbar_wait(&barL, phL); phL ^= 1;
-        } else if (iter == 0) { mbar_wait(&barL, phL); phL ^= 1; }
-        __syncthreads();
-        if (ua.algo != UAVRL_ALGO_DQN) net_forward(net, swL, X2, ld0, pl, false, sA, sB, Ql2);
+        // ---- local network on s (activations kept for backward)
         net_forward(net, swL, X0, ld0, pl, true, sA, sB, Q);
         // ---- TD target, loss, dLoss/dHead  (head gradient plane = sA, [32][kMaxDim], zero padded)
         const int nA = net.n_actions;
@@ -478,11 +448,15 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
             for (int o = 0; o < 32; ++o) g[o] = 0.f;
             float lossb = 0.f;
             if (t * kTile + b < ua.B) {
-                const float *qt = Qt + b * 32;
-                float nq;
-                if (ua.algo == UAVRL_ALGO_DQN) nq = qt[argmax_row(qt, nA)];           // DQN_Trainer.py:109
-                else nq = qt[argmax_row(Ql2 + b * 32, nA)];                          // DDQN_Trainer.py:94-95
-                const float y = s_rew[b] + (ua.gamma * nq * (1.f - s_done[b]));      // :99 / :114 / :171
+                float y;
+                if (have_y) y = ua.y_in[t * kTile + b];
+                else {
+                    const float *qt = Qt + b * 32;
+                    float nq;
+                    if (ua.algo == UAVRL_ALGO_DQN) nq = qt[argmax_row(qt, nA)];       // DQN_Trainer.py:109
+                    else nq = qt[argmax_row(Ql2 + b * 32, nA)];                      // DDQN_Trainer.py:94-95
+                    y = s_rew[b] + (ua.gamma * nq * (1.f - s_done[b]));              // :99 / :114 / :171
+                }
                 const int a = s_act[b];
                 const float diff = Q[b * 32 + a] - y;
                 lossb = diff * diff;
@@ -532,7 +506,8 @@ __global__ void __launch_bounds__(256)
 reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
                    float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
                    float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
-                   const int32_t *__restrict__ img_map, float *__restrict__ loss_out)
+                   const int32_t *__restrict__ img_map, float *__restrict__ tc_local, float *__restrict__ tc_target,
+                   const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, float *__restrict__ loss_out)
 {
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
@@ -570,6 +545,14 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
             const int im = img_map[i];
             img_local[im] = p;
             if (a.hard) { target[i] = p; img_target[im] = p; }   // hard_update (DuelingDQN_Trainer.py:199-202)
+            if (tc_local) {                                      // tensor-core images: TF32 hi/lo split of the new value
+                const int ih = tc_hi[i], il = tc_lo[i];
+                float hi = p, lo = 0.f;
+                if (il >= 0) tf32_split(p, hi, lo);
+                tc_local[ih] = hi;
+                if (il >= 0) tc_local[il] = lo;
+                if (a.hard) { tc_target[ih] = hi; if (il >= 0) tc_target[il] = lo; }
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x >= 224 && loss_out && a.nparts > 0) {     // last warp: loss = sum / B
@@ -617,6 +600,14 @@ static const size_t kMaxDynSmem = 227 * 1024;
 int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st)
 {
+    if (l->tc_ok && l->use_tc) {                         // tensor-core forward chain (tc_forward.cu)
+        TcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.img = l->tc_img_local; a.obs = obs; a.n = n; a.n_tiles = (n + kTcTile - 1) / kTcTile; a.mode = kTcAct;
+        a.eps = eps; a.is_train = is_train; a.u_tape = u_tape; a.rand_tape = rand_tape;
+        a.key = l->cfg.seed ^ 0xAC7ull; a.call = l->act_calls++; a.actions = actions; a.q_out = q_out;
+        return launch_tc_forward(l, a, st);
+    }
     const int n_tiles = (n + kTile - 1) / kTile;
     const int grid = n_tiles < 4 * 148 ? n_tiles : 4 * 148;
     act_kernel<<<grid, kNetThreads, act_smem_bytes(l->net), st>>>(l->net, l->img_local, obs, n, eps, is_train, u_tape,
@@ -645,10 +636,38 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
 {
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
+    const float *y_in = nullptr;
+    if (l->tc_ok && l->use_tc) {
+        // TD targets on the tensor cores: y = r + gamma * next_q * (1 - d) for the whole batch, then the
+        // update kernel only evaluates the local network (forward on s, backward)
+        if (B > l->y_cap) {
+            UAVRL_CUDA(cudaStreamSynchronize(st));
+            cudaFree(l->y_buf); cudaFree(l->astar_buf);
+            UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)B * 4));
+            UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)B * 4));
+            l->y_cap = B;
+        }
+        TcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.src = src; a.n = B; a.n_tiles = (B + kTcTile - 1) / kTcTile; a.use_next = 1; a.gamma = l->cfg.gamma;
+        a.actions = l->astar_buf; a.y_out = l->y_buf;
+        int rc;
+        if (l->cfg.algo != UAVRL_ALGO_DQN) {             // double DQN: a* = argmax_a q_local(s')
+            a.img = l->tc_img_local; a.mode = kTcArgmax;
+            if ((rc = launch_tc_forward(l, a, st))) return rc;
+            a.mode = kTcTdGather;
+        } else {
+            a.mode = kTcTdMax;
+        }
+        a.img = l->tc_img_target;
+        if ((rc = launch_tc_forward(l, a, st))) return rc;
+        y_in = l->y_buf;
+    }
     UpdateArgs ua;
     ua.img_local = l->img_local; ua.img_target = l->img_target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
     ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma; ua.dual = l->dual_weights;
     ua.inv_global_b = 1.0f / (float)global_batch;
+    ua.y_in = y_in;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
     UAVRL_LAUNCHED();
     if (mid) UAVRL_CUDA(cudaEventRecord(mid, st));
@@ -669,6 +688,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     }
     reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
                                                        l->target, l->img_local, l->img_target, l->img_map,
+                                                       (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map,
                                                        loss_out ? loss_out : l->loss_dev);
     UAVRL_LAUNCHED();
     return 0;
@@ -681,6 +701,12 @@ static int repack_images(uavrl_learner *l, cudaStream_t st)
     UAVRL_LAUNCHED();
     pack_image_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->img_map, l->img_target);
     UAVRL_LAUNCHED();
+    if (l->tc_ok) {
+        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->local, l->tc_hi_map, l->tc_lo_map, (float *)l->tc_img_local);
+        UAVRL_LAUNCHED();
+        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->tc_hi_map, l->tc_lo_map, (float *)l->tc_img_target);
+        UAVRL_LAUNCHED();
+    }
     return 0;
 }
 
@@ -757,6 +783,7 @@ int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
         if (upd_smem_bytes(l->net, l->dual_weights) > kMaxDynSmem || act_smem_bytes(l->net) > kMaxDynSmem)
             return fail(UAVRL_ERR_INVALID, "network too large for the shared-memory resident kernels");
     }
+    if ((rc = tc_init(l))) return rc;
     const size_t in = (size_t)cfg->in_dim;
     if (cfg->lockstep_envs > 0) {
         const int64_t N = cfg->lockstep_envs;
@@ -786,7 +813,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
     cudaSetDevice(l->cfg.device);
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
                      l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev, l->img_local, l->img_target,
-                     l->img_map };
+                     l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf };
     for (void *p : ptrs) cudaFree(p);
     delete l;
     return 0;
@@ -947,7 +974,8 @@ int uavrl_learner_apply_grads(uavrl_learner *l, void *stream)
     a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
     reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, (cudaStream_t)stream>>>(a, l->partials, l->loss_partials, l->grad, l->local,
                                                                          l->m, l->v, l->target, l->img_local, l->img_target,
-                                                                         l->img_map, nullptr);
+                                                                         l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target,
+                                                                         l->tc_hi_map, l->tc_lo_map, nullptr);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -962,7 +990,20 @@ int uavrl_learner_hard_update(uavrl_learner *l, void *stream)
     const int wf = l->net.smem_w_floats;
     copy_kernel<<<(wf + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(wf, l->img_local, l->img_target);
     UAVRL_LAUNCHED();
+    if (l->tc_ok) {
+        const int nf = l->tc.img_bytes / 4;
+        copy_kernel<<<(nf + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(nf, (const float *)l->tc_img_local,
+                                                                                       (float *)l->tc_img_target);
+        UAVRL_LAUNCHED();
+    }
     return 0;
+}
+
+int uavrl_learner_set_tensor_cores(uavrl_learner *l, int32_t enable)
+{
+    if (!l) return 0;
+    l->use_tc = enable != 0;
+    return (l->tc_ok && l->use_tc) ? 1 : 0;
 }
 
 int uavrl_learner_lockstep_restart(uavrl_learner *l)

@@ -46,6 +46,22 @@ struct BatchSrc {
     uint64_t key, epoch;              // Philox key / counter for sampling
 };
 
+// ---- tensor-core (tcgen05) forward path: one dense layer as a B operand [N_pad][K_pad], K-major canonical
+// layout (umma.cuh), hi and lo images of the 3xTF32 split
+struct TcLayer {
+    int32_t K_pad, N_pad, K_real, N_real;
+    int32_t hi_off, lo_off;            // byte offsets inside the TC weight image
+    int32_t bias_off;                  // float index of the zero-padded bias vector inside the image's bias area
+};
+
+struct TcNet {
+    int32_t n_layers, in_dim, n_actions, dueling;
+    int32_t img_bytes;                 // whole image: all layers hi|lo, then biases
+    int32_t bias_base;                 // byte offset of the bias area
+    int32_t a_bytes;                   // bytes of ONE A-operand buffer (hi or lo): 128 rows x max K_pad
+    TcLayer L[kMaxLayers];
+};
+
 }  // namespace uavrl
 
 struct uavrl_learner {
@@ -58,6 +74,15 @@ struct uavrl_learner {
     float *img_local = nullptr, *img_target = nullptr;
     int32_t *img_map = nullptr;       // flat parameter index -> image index
     int32_t dual_weights = 0;         // update kernel keeps local+target images resident at once
+    // tensor-core forward path (act + TD target); tc_ok = the network fits the SMEM-resident tcgen05 kernel
+    uavrl::TcNet tc;
+    bool tc_ok = false;
+    bool use_tc = true;               // runtime switch (uavrl_learner_set_tensor_cores): false = fp32 CUDA-core path
+    unsigned char *tc_img_local = nullptr, *tc_img_target = nullptr;
+    int32_t *tc_hi_map = nullptr, *tc_lo_map = nullptr;   // flat param index -> float index in the TC image (-1: none)
+    float *y_buf = nullptr;           // [batch_size] TD targets produced by the tensor-core pass
+    int32_t *astar_buf = nullptr;     // [batch_size] double-DQN argmax actions
+    int32_t y_cap = 0;
     float *partials = nullptr;        // [max_ctas][P] per-CTA gradient partials
     float *loss_partials = nullptr;   // [max_ctas]
     float *loss_dev = nullptr;        // [1]
@@ -86,6 +111,66 @@ struct uavrl_learner {
 };
 
 namespace uavrl {
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// i-th element of a keyed pseudo-random permutation of [0, M): 4-round Feistel on 2*h bits with
+// cycle walking.  perm(0..B-1) = B distinct uniform indices = random.sample(range(M), B)
+// (BaseClass/replay_buffer.py:49).
+__device__ __forceinline__ uint64_t perm_index(uint64_t i, uint64_t M, const uint32_t key[4])
+{
+    int bits = 1;
+    while ((1ull << bits) < M) ++bits;
+    const int h = (bits + 1) / 2;
+    const uint32_t mask = (h >= 32) ? 0xffffffffu : ((1u << h) - 1u);
+    uint64_t x = i;
+    do {
+        uint32_t Lh = (uint32_t)(x >> h) & mask, Rh = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t f = mix32(Rh ^ key[r]) & mask;
+            const uint32_t nl = Rh;
+            Rh = Lh ^ f;
+            Lh = nl;
+        }
+        x = ((uint64_t)Lh << h) | Rh;
+    } while (x >= M);
+    return x;
+}
+
+// batch position gb -> the transition's state row, next-state row and metadata
+struct Transition { const float *s, *s2; int a; float r, d; };
+__device__ __forceinline__ Transition resolve_transition(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4])
+{
+    Transition t;
+    if (src.mode == kBatchExplicit) {
+        t.s = src.frames + (size_t)gb * in_dim;
+        t.s2 = src.s2_rows + (size_t)gb * in_dim;
+        t.a = src.act[gb]; t.r = src.rew[gb]; t.d = src.done_f32[gb];
+        return t;
+    }
+    const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb] : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
+    int64_t slot, row, row2;
+    if (src.mode == kReplayLockstep) {
+        const int64_t f = (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
+        const int64_t e = (int64_t)(j % src.n_envs);
+        slot = f * src.n_envs + e; row = slot;
+        row2 = ((f + 1) % src.cap) * src.n_envs + e;
+    } else {
+        slot = (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+    }
+    t.s = src.frames + (size_t)row * in_dim;
+    t.s2 = src.frames + (size_t)row2 * in_dim;
+    t.a = src.act[slot]; t.r = src.rew[slot]; t.d = src.done_u8[slot] ? 1.f : 0.f;
+    return t;
+}
+#endif
+
 int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,

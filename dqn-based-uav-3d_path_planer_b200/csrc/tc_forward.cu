@@ -1,0 +1,280 @@
+// tc_forward.cu -- the Q-network forward chain on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Used for Trainer.get_action (Trainer/DuelingDQN_Trainer.py:86-97) and for the TD-target part of
+// Trainer.update (target-network forward, :164-171; DQN_Trainer.py:109; DDQN_Trainer.py:94-95).
+//
+// One CTA = one tile of 128 samples (UMMA M = 128).  The whole network lives in SMEM as B operands in the
+// canonical K-major layout, pre-split into TF32 hi/lo images that the optimiser kernel keeps current
+// (one TMA bulk copy stages it).  Per layer:   D[128 x N] (TMEM, fp32) = A[128 x K] * W[N x K]^T
+// issued by ONE thread as 3 x K/8 `tcgen05.mma.kind::tf32` (hi*hi + hi*lo + lo*hi: the 3xTF32 split,
+// measured 1.4e-6 relative -- fp32 grade, so results stay inside the parity tolerance of the fp32 path).
+// The epilogue reads the accumulator with `tcgen05.ld`, adds the bias, applies ReLU, re-splits and writes
+// the next layer's A operand straight back into SMEM -- activations never touch HBM.  The head's epilogue
+// forms Q (dueling combine), then eps-greedy / argmax / max / gather depending on the mode.
+#include "tc_forward.cuh"
+
+#include <string.h>
+
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace uavrl {
+
+static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+
+int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::vector<int32_t> &hi_map, std::vector<int32_t> &lo_map)
+{
+    memset(&tc, 0, sizeof(tc));
+    tc.n_layers = net.n_layers; tc.in_dim = net.in_dim; tc.n_actions = net.n_actions; tc.dueling = net.dueling;
+    if (net.in_dim % 4 != 0) return -1;
+    int off = 0, maxK = 0, k_pad = rup(net.in_dim, 8);
+    for (int l = 0; l < net.n_layers; ++l) {
+        const LayerDev &L = net.L[l];
+        TcLayer &T = tc.L[l];
+        const bool head = (l == net.n_layers - 1);
+        T.K_real = L.in; T.K_pad = k_pad; T.N_real = L.out;
+        T.N_pad = head ? 32 : rup(L.out, 16);
+        if (T.N_pad > 128 || T.K_pad > 128 || (head && L.out > 32)) return -1;
+        const int bytes = T.N_pad * T.K_pad * 4;
+        T.hi_off = off; off += bytes;
+        T.lo_off = off; off += bytes;
+        if (T.K_pad > maxK) maxK = T.K_pad;
+        k_pad = T.N_pad;
+    }
+    tc.bias_base = off;
+    int boff = 0;
+    for (int l = 0; l < net.n_layers; ++l) { tc.L[l].bias_off = boff; boff += tc.L[l].N_pad; }
+    tc.img_bytes = rup(off + boff * 4, 16);
+    tc.a_bytes = (int)umma_tile_bytes(kTcTile, maxK);
+    // parameter -> image maps (float indices)
+    hi_map.assign((size_t)net.P, -1); lo_map.assign((size_t)net.P, -1);
+    auto elem = [](const TcLayer &T, int base, int n, int k) {     // float index of element (row n, col k)
+        const int sbo = (T.K_pad / 4) * 128;
+        return (base + (n >> 3) * sbo + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4) / 4;
+    };
+    for (int l = 0; l < net.n_layers; ++l) {
+        const LayerDev &L = net.L[l];
+        const TcLayer &T = tc.L[l];
+        const int out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
+        for (int o = 0; o < out_main; ++o) {
+            for (int k = 0; k < L.in; ++k) {
+                hi_map[(size_t)L.w_off + (size_t)o * L.in + k] = elem(T, T.hi_off, o, k);
+                lo_map[(size_t)L.w_off + (size_t)o * L.in + k] = elem(T, T.lo_off, o, k);
+            }
+            hi_map[(size_t)L.b_off + o] = tc.bias_base / 4 + T.bias_off + o;
+        }
+        if (L.w2_off >= 0) {
+            for (int k = 0; k < L.in; ++k) {
+                hi_map[(size_t)L.w2_off + k] = elem(T, T.hi_off, out_main, k);
+                lo_map[(size_t)L.w2_off + k] = elem(T, T.lo_off, out_main, k);
+            }
+            hi_map[(size_t)L.b2_off] = tc.bias_base / 4 + T.bias_off + out_main;
+        }
+    }
+    (void)c;
+    return 0;
+}
+
+size_t tc_smem_bytes(const TcNet &tc) { return (size_t)2 * tc.a_bytes + (size_t)tc.img_bytes; }
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *Ahi = smem, *Alo = smem + tc.a_bytes, *W = smem + 2 * tc.a_bytes;
+    __shared__ uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ const float *rows[kTcTile];
+    __shared__ float s_rew[kTcTile], s_done[kTcTile];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
+
+    uint32_t pkey[4];
+    Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+    uint32_t mphase = 0;
+    bool wready = false;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int base = tile * kTcTile;
+        if (tid < kTcTile) {
+            const int b = base + tid;
+            const float *p = nullptr;
+            float r = 0.f, d = 0.f;
+            if (b < a.n) {
+                if (a.mode == kTcAct) p = a.obs + (size_t)b * tc.in_dim;
+                else {
+                    const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
+                    p = a.use_next ? t.s2 : t.s; r = t.r; d = t.d;
+                }
+            }
+            rows[tid] = p; s_rew[tid] = r; s_done[tid] = d;
+        }
+        __syncthreads();
+        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout
+        {
+            const int K0 = tc.L[0].K_pad, chunks = K0 / 4;
+            const uint32_t sbo = umma_sbo(K0);
+            for (int i = tid; i < kTcTile * chunks; i += kTcThreads) {
+                const int r = i / chunks, j = i - r * chunks;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rows[r] && 4 * j < tc.in_dim) v = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
+                float4 h, l;
+                tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+                const uint32_t off = umma_off(r, 4 * j, sbo);
+                *reinterpret_cast<float4 *>(Ahi + off) = h;
+                *reinterpret_cast<float4 *>(Alo + off) = l;
+            }
+        }
+        if (!wready) { mbar_wait(&wbar, 0); wready = true; }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+
+        for (int l = 0; l < tc.n_layers; ++l) {
+            const TcLayer T = tc.L[l];
+            const uint32_t sbo = umma_sbo(T.K_pad);
+            const uint32_t dcol = (uint32_t)(l & 1) * 128u;
+            if (tid == 0) {
+                const uint32_t idesc = umma_idesc_tf32(kTcTile, T.N_pad);
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t aa = smem_u32((pass == 2) ? Alo : Ahi);
+                    const uint32_t bb = smem_u32(W + ((pass == 1) ? T.lo_off : T.hi_off));
+                    for (int k = 0; k < T.K_pad / 8; ++k) {
+                        umma_tf32(tmem + dcol, umma_desc(aa + k * 2 * kUmmaLBO, sbo), umma_desc(bb + k * 2 * kUmmaLBO, sbo), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(&mbar);
+            }
+            mbar_wait(&mbar, mphase);
+            mphase ^= 1;
+            tc_fence_after();
+            const float *bias = bias_all + T.bias_off;
+            const int row = quad * 32 + lane;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            if (l + 1 < tc.n_layers) {
+                // hidden layer epilogue: bias + ReLU, re-split, write the next A operand (K_next = N_pad)
+                const uint32_t sbon = umma_sbo(T.N_pad);
+                for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 h, lo4;
+                        float x0 = fmaxf(v[4 * j + 0] + bias[c0 + 4 * j + 0], 0.f), x1 = fmaxf(v[4 * j + 1] + bias[c0 + 4 * j + 1], 0.f);
+                        float x2 = fmaxf(v[4 * j + 2] + bias[c0 + 4 * j + 2], 0.f), x3 = fmaxf(v[4 * j + 3] + bias[c0 + 4 * j + 3], 0.f);
+                        tf32_split(x0, h.x, lo4.x); tf32_split(x1, h.y, lo4.y); tf32_split(x2, h.z, lo4.z); tf32_split(x3, h.w, lo4.w);
+                        const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
+                        *reinterpret_cast<float4 *>(Ahi + off) = h;
+                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+            } else {
+                // head epilogue: Q row of this sample, then the mode's output
+                if (half == 0) {
+                    float q[32];
+                    tmem_ld32(taddr, q);
+                    const int nA = tc.n_actions;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] += bias[j];
+                    if (tc.dueling) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nA) s += q[j];
+                        const float mean = s / (float)nA;
+                        float V = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j == nA) V = q[j];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = V + q[j] - mean;
+                    }
+                    int best = 0; float bv = q[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) if (j < nA && q[j] > bv) { bv = q[j]; best = j; }
+                    const int b = base + row;
+                    if (b < a.n) {
+                        if (a.q_out) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j < nA) a.q_out[(size_t)b * nA + j] = q[j];
+                        }
+                        if (a.mode == kTcAct) {
+                            float u; int ra;
+                            if (a.u_tape) { u = a.u_tape[b]; ra = a.rand_tape ? a.rand_tape[b] : 0; }
+                            else {
+                                uint32_t rr[4];
+                                Philox::gen(a.key, a.call, (uint64_t)b, rr);
+                                u = Philox::u01(rr[0]);
+                                ra = (int)(((uint64_t)rr[1] * (uint64_t)nA) >> 32);
+                            }
+                            a.actions[b] = (u > a.eps || !a.is_train) ? best : ra;      // DuelingDQN_Trainer.py:89-97
+                        } else if (a.mode == kTcArgmax) {
+                            a.actions[b] = best;                                        // DDQN_Trainer.py:94
+                        } else {
+                            float nq = bv;                                              // DQN_Trainer.py:109
+                            if (a.mode == kTcTdGather) {                                // DDQN_Trainer.py:95
+                                const int as = a.actions[b];
+                                nq = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j == as) nq = q[j];
+                            }
+                            a.y_out[b] = s_rew[row] + (a.gamma * nq * (1.f - s_done[row]));   // :99 / :114 / :171
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st)
+{
+    const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+    tc_forward_kernel<<<grid, kTcThreads, tc_smem_bytes(l->tc), st>>>(l->tc, a);
+    UAVRL_LAUNCHED();
+    return 0;
+}
+
+int tc_init(uavrl_learner *l)
+{
+    std::vector<int32_t> hi, lo;
+    l->tc_ok = false;
+    if (tc_build(l->cfg, l->net, l->tc, hi, lo) != 0) return 0;
+    if (tc_smem_bytes(l->tc) > 227 * 1024) return 0;
+    const size_t P = (size_t)l->net.P;
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_local, (size_t)l->tc.img_bytes));
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_target, (size_t)l->tc.img_bytes));
+    UAVRL_CUDA(cudaMemset(l->tc_img_local, 0, (size_t)l->tc.img_bytes));
+    UAVRL_CUDA(cudaMemset(l->tc_img_target, 0, (size_t)l->tc.img_bytes));
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_hi_map, P * 4));
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_lo_map, P * 4));
+    UAVRL_CUDA(cudaMemcpy(l->tc_hi_map, hi.data(), P * 4, cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(l->tc_lo_map, lo.data(), P * 4, cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)l->cfg.batch_size * 4));
+    UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)l->cfg.batch_size * 4));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    l->y_cap = l->cfg.batch_size;
+    l->tc_ok = true;
+    return 0;
+}
+
+}  // namespace uavrl

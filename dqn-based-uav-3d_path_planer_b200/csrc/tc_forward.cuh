@@ -1,0 +1,33 @@
+// tc_forward.cuh -- tensor-core (tcgen05 / TMEM) forward chain of the Q-network, 3xTF32 split precision.
+#pragma once
+#include <vector>
+
+#include "learner.cuh"
+
+namespace uavrl {
+
+constexpr int kTcThreads = 256;        // 8 warps: warp w owns TMEM lanes 32*(w%4).. ; two warps share a quadrant
+constexpr int kTcTile = 128;           // samples per CTA tile (= UMMA M)
+
+enum TcMode { kTcAct = 0, kTcArgmax = 1, kTcTdMax = 2, kTcTdGather = 3 };
+
+struct TcArgs {
+    const unsigned char *img;          // TC weight image of the network to evaluate
+    BatchSrc src;                      // row source for the TD modes (next-state rows); unused for kTcAct
+    const float *obs;                  // kTcAct: [n][in_dim]
+    int32_t n, n_tiles, mode, use_next;
+    float eps; int32_t is_train;
+    const float *u_tape; const int32_t *rand_tape;
+    uint64_t key, call;
+    int32_t *actions;                  // kTcAct out / kTcArgmax out (astar) / kTcTdGather in (astar)
+    float *q_out;                      // optional [n][A]
+    float *y_out;                      // TD modes: y[b] = r + gamma * next_q * (1 - d)
+    float gamma;
+};
+
+int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::vector<int32_t> &hi_map, std::vector<int32_t> &lo_map);
+size_t tc_smem_bytes(const TcNet &tc);
+int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st);
+int tc_init(uavrl_learner *l);        // builds the TC images/maps; leaves l->tc_ok = false when the net does not fit
+
+}  // namespace uavrl

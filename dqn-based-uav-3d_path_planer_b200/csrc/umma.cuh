@@ -1,0 +1,97 @@
+// umma.cuh -- tcgen05 (5th-gen tensor core) helpers for sm_100a, inline PTX: TMEM allocation, shared-memory
+// matrix descriptors (K-major, no swizzle), kind::tf32 MMA issue, commit -> mbarrier, TMEM -> register loads.
+//
+// Operand layout used throughout (canonical K-major "interleave" layout, cute::UMMA::LayoutType::SWIZZLE_NONE):
+//   core matrix = 8 rows x 16 bytes (4 fp32/tf32 values), stored as 128 contiguous bytes (row stride 16 B);
+//   core matrices adjacent in K are LBO bytes apart, adjacent in M/N (next 8 rows) SBO bytes apart.
+//   element (r, c) of a [rows][K] operand lives at   (r/8)*SBO + (c/4)*LBO + (r%8)*16 + (c%4)*4.
+//   One kind::tf32 instruction consumes K = 8 (two 16-byte chunks); the next K step starts 2*LBO further.
+#pragma once
+#include <stdint.h>
+
+namespace uavrl {
+
+constexpr uint32_t kUmmaLBO = 128;                 // K-adjacent core matrices are contiguous
+
+__host__ __device__ constexpr uint32_t umma_sbo(int k_pad) { return (uint32_t)(k_pad / 4) * 128u; }
+__host__ __device__ constexpr uint32_t umma_tile_bytes(int rows, int k_pad) { return (uint32_t)(rows / 8) * umma_sbo(k_pad); }
+
+// byte offset of element (r, c) inside an operand tile
+__device__ __forceinline__ uint32_t umma_off(int r, int c, uint32_t sbo)
+{
+    return (uint32_t)(r >> 3) * sbo + (uint32_t)(c >> 2) * kUmmaLBO + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 3) * 4u;
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 (no swizzle) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((kUmmaLBO >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4) /* c = F32 */ | (2u << 7) /* a = TF32 */ | (2u << 10) /* b = TF32 */ |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)   // whole warp, ncols power of 2 >= 32
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)     // same warp that allocated
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T   (single thread issues)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes (rows), 32 consecutive fp32 columns starting at taddr
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 3xTF32 split: hi = x rounded to TF32 (10-bit mantissa), lo = x - hi (exact).  hi*hi + hi*lo + lo*hi
+// reproduces the fp32 product to ~2^-21.
+__device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
+{
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+}  // namespace uavrl

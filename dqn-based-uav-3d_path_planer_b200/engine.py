@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_CONT_F32, ACT_CONT_F64, ACT_DISCRETE27, ALGO_DDQN, ALGO_DQN, ALGO_DUELING,  # noqa: F401
-                   OBS_DIM, UavrlError, check)
+                   INFO_NAMES, OBS_DIM, UavrlError, check)
 
 
 def _ptr(t):
@@ -271,6 +271,10 @@ class Learner:
 
     def hard_update(self):
         check(_lib.lib().uavrl_learner_hard_update(self.h, _stream(self.device)))
+
+    def set_tensor_cores(self, enable):
+        """True = tcgen05 3xTF32 forward passes (default when the net fits), False = fp32 CUDA cores."""
+        return bool(_lib.lib().uavrl_learner_set_tensor_cores(self.h, int(bool(enable))))
 
     def lockstep_restart(self):
         check(_lib.lib().uavrl_learner_lockstep_restart(self.h))

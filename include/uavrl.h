@@ -188,6 +188,9 @@ int uavrl_learner_compute_grads(uavrl_learner *l, const int32_t *idx_tape_dev, i
                                 float *loss_dev, void *stream);
 float *uavrl_learner_grad_ptr(uavrl_learner *l);          /* device, [param_count] fp32 */
 int uavrl_learner_apply_grads(uavrl_learner *l, void *stream);
+/* Select the arithmetic path of the Q-network forward passes (get_action, TD target): 1 = tcgen05 tensor
+ * cores with the 3xTF32 split (default when the network fits), 0 = fp32 CUDA cores.  Returns the path in use. */
+int uavrl_learner_set_tensor_cores(uavrl_learner *l, int32_t enable);
 int uavrl_learner_hard_update(uavrl_learner *l, void *stream);   /* DuelingDQN_Trainer.py:199-202 */
 /* After an explicit uavrl_env_reset the lockstep ring's current frame no longer matches the env
  * state: call this; the next uavrl_train_run re-observes into a fresh frame and the lockstep replay

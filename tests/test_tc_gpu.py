@@ -1,0 +1,80 @@
+"""Tensor-core (tcgen05, 3xTF32) forward path vs the fp32 CUDA-core path and the oracle: same actions,
+Q within 2e-5, and the full update (TD targets from the tensor-core pass) inside the reference-trainer
+tolerances for every algorithm; also large ragged batches and the explicit switch."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x, dt=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t if dt is None else t.to(dt)
+
+
+@pytest.mark.parametrize("hidden,dueling", [([64, 64], 0), ([64], 1), ([64], 0), ([128, 64], 1)])
+def test_tc_act_matches_fp32_path_and_oracle(dqn_golden, hidden, dueling):
+    from uavrl_b200 import engine
+    g = dqn_golden
+    rng = np.random.default_rng(3)
+    net = O.make_net(100, hidden, 27, dueling)
+    P = O.net_param_count(net)
+    params = rng.normal(0, 0.15, P).astype(np.float32)
+    n = 5000                                              # ragged: 39 full tiles of 128 + 8
+    x = np.tile(np.concatenate([g["batch_s"].reshape(-1, 100), g["batch_s2"].reshape(-1, 100)]), (4, 1))[:n]
+    x = x + rng.normal(0, 0.01, x.shape).astype(np.float32)
+    L = engine.Learner(100, hidden, 27, dueling, 1)
+    L.set_params(params, 0)
+    on = L.set_tensor_cores(True)
+    if hidden == [128, 64]:
+        assert not on                                     # does not fit the SMEM-resident kernel: fp32 path serves it
+        L.close()
+        return
+    assert on
+    u = rng.uniform(size=n).astype(np.float32); ra = rng.integers(0, 27, n).astype(np.int32)
+    a_tc, q_tc = L.act(dev(x), 0.2, u_tape=dev(u), rand_tape=dev(ra), want_q=True)
+    assert not L.set_tensor_cores(False)
+    a_32, q_32 = L.act(dev(x), 0.2, u_tape=dev(u), rand_tape=dev(ra), want_q=True)
+    a_or, q_or = O.act(net, params, x, 0.2, u, ra)
+    q_tc, q_32 = q_tc.cpu().numpy(), q_32.cpu().numpy()
+    np.testing.assert_allclose(q_tc, q_or, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(q_32, q_or, rtol=2e-5, atol=2e-5)
+    # actions: identical except where the top-2 Q gap is inside the arithmetic noise (none expected at this scale)
+    top2 = np.sort(q_or, 1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4
+    assert clear.mean() > 0.99
+    assert np.array_equal(a_tc.cpu().numpy()[clear], a_or[clear])
+    assert np.array_equal(a_32.cpu().numpy()[clear], a_or[clear])
+    L.close()
+
+
+CASES = {"dueling_vanet2": ([64], 1, 2), "ddqn_qvalue3": ([64, 64], 0, 1), "dqn_qvalue3": ([64, 64], 0, 0), "dqn_qnet2": ([64], 0, 0)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tc_td_targets_keep_update_parity(dqn_golden, name):
+    """The learner tests run with the tensor-core path on by default; this one pins it explicitly and
+    compares TC-on vs TC-off trajectories of 10 updates."""
+    from uavrl_b200 import engine
+    g = dqn_golden
+    hidden, dueling, algo = CASES[name]
+    out = {}
+    for tc in (True, False):
+        L = engine.Learner(100, hidden, 27, dueling, algo, batch_size=64, update_loop=3, replay_capacity=1000)
+        assert L.set_tensor_cores(tc) == tc
+        L.set_params(g[name + "_local0"], 0); L.set_params(g[name + "_target0"], 1)
+        loss = torch.zeros(1, device="cuda"); losses = []
+        for step in range(10):
+            L.update_batch(dev(g["batch_s"][step]), dev(g["batch_a"][step], torch.int32), dev(g["batch_r"][step]),
+                           dev(g["batch_s2"][step]), dev(g["batch_d"][step]), loss)
+            losses.append(float(loss))
+        out[tc] = (np.array(losses), L.get_params(0), L.get_params(1))
+        L.close()
+    np.testing.assert_allclose(out[True][0], g[name + "_loss"], rtol=2e-5)
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-5)
+    np.testing.assert_allclose(out[True][1], g[name + "_local"][-1], atol=2e-5)
+    np.testing.assert_allclose(out[True][1], out[False][1], atol=5e-6)
+    np.testing.assert_allclose(out[True][2], out[False][2], atol=5e-6)
