@@ -514,16 +514,17 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     const int i = blockIdx.x * 64 + ix;
     float g = 0.f;
     if (i < a.P && a.nparts > 0) {
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        // 4 groups x 8 independent loads in flight per thread: the partials are L2 resident, latency bound
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
         int c = cg;
-        for (; c + 12 < a.nparts; c += 16) {
-            g0 += partials[(size_t)c * a.P + i];
-            g1 += partials[(size_t)(c + 4) * a.P + i];
-            g2 += partials[(size_t)(c + 8) * a.P + i];
-            g3 += partials[(size_t)(c + 12) * a.P + i];
+        for (; c + 28 < a.nparts; c += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(c + 4 * u) * a.P + i];
         }
-        for (; c < a.nparts; c += 4) g0 += partials[(size_t)c * a.P + i];
-        g = (g0 + g1) + (g2 + g3);
+        for (; c < a.nparts; c += 4) acc[0] += partials[(size_t)c * a.P + i];
+        g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     }
     red[cg][ix] = g;
     __syncthreads();

@@ -101,9 +101,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     uint32_t mphase = 0;
     bool wready = false;
 
+    // R = real rows per tile (32 / 64 / 128).  The MMA is always M = 128; accumulator rows >= R hold garbage
+    // computed from whatever SMEM follows the R-row operand (still inside this CTA's allocation) and are
+    // never read.  Small batches use R = 32 so that 4096 samples spread over 128 CTAs instead of 32.
+    const int R = a.rows_per_tile;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int base = tile * kTcTile;
-        if (tid < kTcTile) {
+        const int base = tile * R;
+        if (tid < R) {
             const int b = base + tid;
             const float *p = nullptr;
             float r = 0.f, d = 0.f;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
         {
             const int K0 = tc.L[0].K_pad, chunks = K0 / 4;
             const uint32_t sbo = umma_sbo(K0);
-            for (int i = tid; i < kTcTile * chunks; i += kTcThreads) {
+            for (int i = tid; i < R * chunks; i += kTcThreads) {
                 const int r = i / chunks, j = i - r * chunks;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (rows[r] && 4 * j < tc.in_dim) v = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
@@ -143,17 +147,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             const uint32_t sbo = umma_sbo(T.K_pad);
             const uint32_t dcol = (uint32_t)(l & 1) * 128u;
             if (tid == 0) {
+                // one thread issues 3 x K/8 MMAs.  Descriptors differ only in the 14-bit start-address field:
+                // the next K step (two 16-byte chunks = 2*LBO bytes) is +16 in units of 16 B.
                 const uint32_t idesc = umma_idesc_tf32(kTcTile, T.N_pad);
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t aa = smem_u32((pass == 2) ? Alo : Ahi);
-                    const uint32_t bb = smem_u32(W + ((pass == 1) ? T.lo_off : T.hi_off));
-                    for (int k = 0; k < T.K_pad / 8; ++k) {
-                        umma_tf32(tmem + dcol, umma_desc(aa + k * 2 * kUmmaLBO, sbo), umma_desc(bb + k * 2 * kUmmaLBO, sbo), idesc, acc);
-                        acc = 1;
-                    }
-                }
+                const uint64_t a_hi = umma_desc(smem_u32(Ahi), sbo), a_lo = umma_desc(smem_u32(Alo), sbo);
+                const uint64_t b_hi = umma_desc(smem_u32(W + T.hi_off), sbo), b_lo = umma_desc(smem_u32(W + T.lo_off), sbo);
+                const uint32_t d = tmem + dcol;
+                const int ksteps = T.K_pad / 8;
+                constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
+                uint64_t da = a_hi, db = b_hi;
+                umma_tf32(d, da, db, idesc, 0u);                                   // hi * hi (first MMA overwrites D)
+                for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
+                da = a_hi; db = b_lo;
+                for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }   // hi * lo
+                da = a_lo; db = b_hi;
+                for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }   // lo * hi
                 umma_commit(&mbar);
             }
             mbar_wait(&mbar, mphase);
@@ -162,10 +170,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             const float *bias = bias_all + T.bias_off;
             const int row = quad * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            const bool live = quad * 32 < R;                       // this warp's TMEM quadrant holds real rows
             if (l + 1 < tc.n_layers) {
                 // hidden layer epilogue: bias + ReLU, re-split, write the next A operand (K_next = N_pad)
                 const uint32_t sbon = umma_sbo(T.N_pad);
-                for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
+                for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 tc_fence_after();
             } else {
                 // head epilogue: Q row of this sample, then the mode's output
-                if (half == 0) {
+                if (half == 0 && live) {
                     float q[32];
                     tmem_ld32(taddr, q);
                     const int nA = tc.n_actions;
@@ -246,8 +255,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st)
+int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
 {
+    TcArgs a = a_in;
+    a.rows_per_tile = (a.n >= 128 * 148) ? 128 : (a.n >= 64 * 148) ? 64 : 32;
+    a.n_tiles = (a.n + a.rows_per_tile - 1) / a.rows_per_tile;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     tc_forward_kernel<<<grid, kTcThreads, tc_smem_bytes(l->tc), st>>>(l->tc, a);
     UAVRL_LAUNCHED();

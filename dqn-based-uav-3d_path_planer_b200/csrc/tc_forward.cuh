@@ -15,7 +15,7 @@ struct TcArgs {
     const unsigned char *img;          // TC weight image of the network to evaluate
     BatchSrc src;                      // row source for the TD modes (next-state rows); unused for kTcAct
     const float *obs;                  // kTcAct: [n][in_dim]
-    int32_t n, n_tiles, mode, use_next;
+    int32_t n, n_tiles, mode, use_next, rows_per_tile;
     float eps; int32_t is_train;
     const float *u_tape; const int32_t *rand_tape;
     uint64_t key, call;
