@@ -96,13 +96,17 @@ __global__ void pack_image_kernel(int P, const float *__restrict__ flat, const i
 }
 
 __global__ void pack_tc_kernel(int P, const float *__restrict__ flat, const int32_t *__restrict__ hi_map,
-                               const int32_t *__restrict__ lo_map, float *__restrict__ img)
+                               const int32_t *__restrict__ lo_map, const int32_t *__restrict__ hi2_map,
+                               const int32_t *__restrict__ lo2_map, float *__restrict__ img)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const float p = flat[i];
-    if (lo_map[i] >= 0) { float hi, lo; tf32_split(p, hi, lo); img[hi_map[i]] = hi; img[lo_map[i]] = lo; }
-    else img[hi_map[i]] = p;                              // biases stay fp32
+    if (lo_map[i] >= 0) {
+        float hi, lo; tf32_split(p, hi, lo);
+        img[hi_map[i]] = hi; img[lo_map[i]] = lo;
+        if (hi2_map[i] >= 0) { img[hi2_map[i]] = hi; img[lo2_map[i]] = lo; }   // transposed block (dX chain)
+    } else img[hi_map[i]] = p;                            // biases stay fp32
 }
 
 // Stage a whole network image (weights transposed + biases, pads zero) into smem with the TMA engine.
@@ -496,7 +500,7 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
 
 // ------------------------------------------------------------------ reduce partials + Adam + target copy
 struct AdamArgs {
-    int P, nparts, apply, hard, world;
+    int P, nparts, apply, hard, world, n_loss_parts;
     float step_size, beta1_c, beta2, beta2_c, eps, bc2_sqrt, inv_b;
 };
 
@@ -507,7 +511,8 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
                    float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
                    float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
                    const int32_t *__restrict__ img_map, float *__restrict__ tc_local, float *__restrict__ tc_target,
-                   const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, float *__restrict__ loss_out)
+                   const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, const int32_t *__restrict__ tc_hi2,
+                   const int32_t *__restrict__ tc_lo2, float *__restrict__ loss_out)
 {
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
@@ -552,14 +557,20 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
                 if (il >= 0) tf32_split(p, hi, lo);
                 tc_local[ih] = hi;
                 if (il >= 0) tc_local[il] = lo;
-                if (a.hard) { tc_target[ih] = hi; if (il >= 0) tc_target[il] = lo; }
+                const int ih2 = tc_hi2[i], il2 = tc_lo2[i];
+                if (ih2 >= 0) { tc_local[ih2] = hi; tc_local[il2] = lo; }
+                if (a.hard) {
+                    tc_target[ih] = hi;
+                    if (il >= 0) tc_target[il] = lo;
+                    if (ih2 >= 0) { tc_target[ih2] = hi; tc_target[il2] = lo; }
+                }
             }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x >= 224 && loss_out && a.nparts > 0) {     // last warp: loss = sum / B
         const int lane = threadIdx.x & 31;
         float s = 0.f;
-        for (int c = lane; c < a.nparts; c += 32) s += loss_partials[c];
+        for (int c = lane; c < a.n_loss_parts; c += 32) s += loss_partials[c];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) *loss_out = s * a.inv_b;
@@ -664,6 +675,20 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
         if ((rc = launch_tc_forward(l, a, st))) return rc;
         y_in = l->y_buf;
     }
+    int nparts = grid, n_loss_parts = grid;
+    if (y_in && l->tc_train_ok) {
+        // the whole update on the tensor cores: forward + dX chain, then split-K weight gradients (tc_train.cu)
+        if (B > l->train_cap) {
+            UAVRL_CUDA(cudaStreamSynchronize(st));
+            cudaFree(l->act_buf); cudaFree(l->dz_buf);
+            UAVRL_CUDA(cudaMalloc((void **)&l->act_buf, (size_t)B * (size_t)(l->tc.act_stride > 0 ? l->tc.act_stride : 4) * 4));
+            UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, (size_t)B * (size_t)l->tc.dz_stride * 4));
+            l->train_cap = B;
+        }
+        if ((B + 127) / 128 > l->max_ctas) return fail(UAVRL_ERR_INVALID, "batch too large for the gradient partial buffer");
+        int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st);
+        if (rc) return rc;
+    } else {
     UpdateArgs ua;
     ua.img_local = l->img_local; ua.img_target = l->img_target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
     ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma; ua.dual = l->dual_weights;
@@ -671,12 +696,13 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     ua.y_in = y_in;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
     UAVRL_LAUNCHED();
+    }
     if (mid) UAVRL_CUDA(cudaEventRecord(mid, st));
-    l->last_nparts = grid;
+    l->last_nparts = nparts;
     l->last_global_batch = global_batch;
     AdamArgs a;
     memset(&a, 0, sizeof(a));
-    a.P = l->net.P; a.nparts = grid; a.apply = apply ? 1 : 0; a.world = l->world;
+    a.P = l->net.P; a.nparts = nparts; a.n_loss_parts = n_loss_parts; a.apply = apply ? 1 : 0; a.world = l->world;
     a.inv_b = 1.0f / (float)global_batch;
     if (apply) {
         l->adam_t += 1;
@@ -690,7 +716,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
                                                        l->target, l->img_local, l->img_target, l->img_map,
                                                        (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map,
-                                                       loss_out ? loss_out : l->loss_dev);
+                                                       l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -703,9 +729,11 @@ static int repack_images(uavrl_learner *l, cudaStream_t st)
     pack_image_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->img_map, l->img_target);
     UAVRL_LAUNCHED();
     if (l->tc_ok) {
-        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->local, l->tc_hi_map, l->tc_lo_map, (float *)l->tc_img_local);
+        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->local, l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map,
+                                                   (float *)l->tc_img_local);
         UAVRL_LAUNCHED();
-        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->tc_hi_map, l->tc_lo_map, (float *)l->tc_img_target);
+        pack_tc_kernel<<<blocks, threads, 0, st>>>(l->net.P, l->target, l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map,
+                                                   (float *)l->tc_img_target);
         UAVRL_LAUNCHED();
     }
     return 0;
@@ -814,7 +842,8 @@ int uavrl_learner_destroy(uavrl_learner *l)
     cudaSetDevice(l->cfg.device);
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
                      l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev, l->img_local, l->img_target,
-                     l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf };
+                     l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf, l->tc_hi2_map,
+                     l->tc_lo2_map, l->act_buf, l->dz_buf };
     for (void *p : ptrs) cudaFree(p);
     delete l;
     return 0;
@@ -976,7 +1005,7 @@ int uavrl_learner_apply_grads(uavrl_learner *l, void *stream)
     reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, (cudaStream_t)stream>>>(a, l->partials, l->loss_partials, l->grad, l->local,
                                                                          l->m, l->v, l->target, l->img_local, l->img_target,
                                                                          l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target,
-                                                                         l->tc_hi_map, l->tc_lo_map, nullptr);
+                                                                         l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map, nullptr);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -992,7 +1021,7 @@ int uavrl_learner_hard_update(uavrl_learner *l, void *stream)
     copy_kernel<<<(wf + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(wf, l->img_local, l->img_target);
     UAVRL_LAUNCHED();
     if (l->tc_ok) {
-        const int nf = l->tc.img_bytes / 4;
+        const int nf = l->tc.train_img_bytes / 4;
         copy_kernel<<<(nf + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(nf, (const float *)l->tc_img_local,
                                                                                        (float *)l->tc_img_target);
         UAVRL_LAUNCHED();

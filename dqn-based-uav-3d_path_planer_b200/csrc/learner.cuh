@@ -52,13 +52,22 @@ struct TcLayer {
     int32_t K_pad, N_pad, K_real, N_real;
     int32_t hi_off, lo_off;            // byte offsets inside the TC weight image
     int32_t bias_off;                  // float index of the zero-padded bias vector inside the image's bias area
+    // transposed copy W^T as a B operand [K_pad rows][N_pad cols] for the dX chain (layers >= 1 only; -1 otherwise)
+    int32_t t_hi_off, t_lo_off;
+    // where this layer's pieces live in the flat parameter / gradient vector (state_dict order)
+    int32_t w_off, b_off, w2_off, b2_off, out_main;
+    int32_t act_off, dz_off;           // float offsets of this layer's input activations / output derivatives in the
+                                       // per-sample scratch rows (act: layer input, valid for l >= 1; dz: dLoss/d(pre-activation))
 };
 
 struct TcNet {
     int32_t n_layers, in_dim, n_actions, dueling;
-    int32_t img_bytes;                 // whole image: all layers hi|lo, then biases
+    int32_t img_bytes;                 // forward image: all layers hi|lo, then biases
     int32_t bias_base;                 // byte offset of the bias area
+    int32_t train_img_bytes;           // forward image + transposed blocks (training chain)
     int32_t a_bytes;                   // bytes of ONE A-operand buffer (hi or lo): 128 rows x max K_pad
+    int32_t max_k;                     // max K_pad over layers
+    int32_t act_stride, dz_stride;     // floats per sample in the activation / derivative scratch
     TcLayer L[kMaxLayers];
 };
 
@@ -83,6 +92,11 @@ struct uavrl_learner {
     float *y_buf = nullptr;           // [batch_size] TD targets produced by the tensor-core pass
     int32_t *astar_buf = nullptr;     // [batch_size] double-DQN argmax actions
     int32_t y_cap = 0;
+    // tensor-core training path scratch (per sampled transition): hidden activations and dLoss/d(pre-activation)
+    int32_t *tc_hi2_map = nullptr, *tc_lo2_map = nullptr;  // flat param index -> transposed-block positions (-1: none)
+    float *act_buf = nullptr, *dz_buf = nullptr;
+    bool tc_train_ok = false;
+    int32_t train_cap = 0;
     float *partials = nullptr;        // [max_ctas][P] per-CTA gradient partials
     float *loss_partials = nullptr;   // [max_ctas]
     float *loss_dev = nullptr;        // [1]

@@ -22,7 +22,8 @@ namespace uavrl {
 
 static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
-int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::vector<int32_t> &hi_map, std::vector<int32_t> &lo_map)
+int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::vector<int32_t> &hi_map, std::vector<int32_t> &lo_map,
+             std::vector<int32_t> &hi2_map, std::vector<int32_t> &lo2_map)
 {
     memset(&tc, 0, sizeof(tc));
     tc.n_layers = net.n_layers; tc.in_dim = net.in_dim; tc.n_actions = net.n_actions; tc.dueling = net.dueling;
@@ -39,36 +40,58 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
         T.hi_off = off; off += bytes;
         T.lo_off = off; off += bytes;
         if (T.K_pad > maxK) maxK = T.K_pad;
+        T.w_off = L.w_off; T.b_off = L.b_off; T.w2_off = L.w2_off; T.b2_off = L.b2_off;
+        T.out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
         k_pad = T.N_pad;
     }
     tc.bias_base = off;
     int boff = 0;
     for (int l = 0; l < net.n_layers; ++l) { tc.L[l].bias_off = boff; boff += tc.L[l].N_pad; }
     tc.img_bytes = rup(off + boff * 4, 16);
+    // transposed blocks for the dX chain (layers >= 1): B' = W^T, rows = input units (K_pad), reduction = outputs (N_pad)
+    int toff = tc.img_bytes;
+    for (int l = 0; l < net.n_layers; ++l) {
+        TcLayer &T = tc.L[l];
+        T.t_hi_off = T.t_lo_off = -1;
+        if (l == 0) continue;
+        const int bytes = T.K_pad * T.N_pad * 4;
+        T.t_hi_off = toff; toff += bytes;
+        T.t_lo_off = toff; toff += bytes;
+    }
+    tc.train_img_bytes = rup(toff, 16);
     tc.a_bytes = (int)umma_tile_bytes(kTcTile, maxK);
+    tc.max_k = maxK;
+    // per-sample scratch: act = inputs of layers 1.. (K_pad each), dz = output derivatives of every layer (N_pad each)
+    int ao = 0, dzo = 0;
+    for (int l = 0; l < net.n_layers; ++l) {
+        tc.L[l].act_off = (l == 0) ? -1 : ao;
+        if (l > 0) ao += tc.L[l].K_pad;
+        tc.L[l].dz_off = dzo; dzo += tc.L[l].N_pad;
+    }
+    tc.act_stride = ao; tc.dz_stride = dzo;
     // parameter -> image maps (float indices)
     hi_map.assign((size_t)net.P, -1); lo_map.assign((size_t)net.P, -1);
-    auto elem = [](const TcLayer &T, int base, int n, int k) {     // float index of element (row n, col k)
-        const int sbo = (T.K_pad / 4) * 128;
+    hi2_map.assign((size_t)net.P, -1); lo2_map.assign((size_t)net.P, -1);
+    auto elem = [](int k_pad_cols, int base, int n, int k) {     // float index of element (row n, col k), K-major canonical
+        const int sbo = (k_pad_cols / 4) * 128;
         return (base + (n >> 3) * sbo + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4) / 4;
     };
     for (int l = 0; l < net.n_layers; ++l) {
         const LayerDev &L = net.L[l];
         const TcLayer &T = tc.L[l];
-        const int out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
-        for (int o = 0; o < out_main; ++o) {
+        const int out_main = T.out_main;
+        for (int o = 0; o < L.out; ++o) {
+            const bool vrow = (o >= out_main);                   // dueling value row
             for (int k = 0; k < L.in; ++k) {
-                hi_map[(size_t)L.w_off + (size_t)o * L.in + k] = elem(T, T.hi_off, o, k);
-                lo_map[(size_t)L.w_off + (size_t)o * L.in + k] = elem(T, T.lo_off, o, k);
+                const size_t pi = vrow ? (size_t)L.w2_off + k : (size_t)L.w_off + (size_t)o * L.in + k;
+                hi_map[pi] = elem(T.K_pad, T.hi_off, o, k);
+                lo_map[pi] = elem(T.K_pad, T.lo_off, o, k);
+                if (l > 0) {                                      // W^T: row k, column o
+                    hi2_map[pi] = elem(T.N_pad, T.t_hi_off, k, o);
+                    lo2_map[pi] = elem(T.N_pad, T.t_lo_off, k, o);
+                }
             }
-            hi_map[(size_t)L.b_off + o] = tc.bias_base / 4 + T.bias_off + o;
-        }
-        if (L.w2_off >= 0) {
-            for (int k = 0; k < L.in; ++k) {
-                hi_map[(size_t)L.w2_off + k] = elem(T, T.hi_off, out_main, k);
-                lo_map[(size_t)L.w2_off + k] = elem(T, T.lo_off, out_main, k);
-            }
-            hi_map[(size_t)L.b2_off] = tc.bias_base / 4 + T.bias_off + out_main;
+            hi_map[vrow ? (size_t)L.b2_off : (size_t)L.b_off + o] = tc.bias_base / 4 + T.bias_off + o;
         }
     }
     (void)c;
@@ -268,25 +291,28 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
 
 int tc_init(uavrl_learner *l)
 {
-    std::vector<int32_t> hi, lo;
-    l->tc_ok = false;
-    if (tc_build(l->cfg, l->net, l->tc, hi, lo) != 0) return 0;
+    std::vector<int32_t> hi, lo, hi2, lo2;
+    l->tc_ok = false; l->tc_train_ok = false;
+    if (tc_build(l->cfg, l->net, l->tc, hi, lo, hi2, lo2) != 0) return 0;
     if (tc_smem_bytes(l->tc) > 227 * 1024) return 0;
     const size_t P = (size_t)l->net.P;
-    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_local, (size_t)l->tc.img_bytes));
-    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_target, (size_t)l->tc.img_bytes));
-    UAVRL_CUDA(cudaMemset(l->tc_img_local, 0, (size_t)l->tc.img_bytes));
-    UAVRL_CUDA(cudaMemset(l->tc_img_target, 0, (size_t)l->tc.img_bytes));
-    UAVRL_CUDA(cudaMalloc((void **)&l->tc_hi_map, P * 4));
-    UAVRL_CUDA(cudaMalloc((void **)&l->tc_lo_map, P * 4));
-    UAVRL_CUDA(cudaMemcpy(l->tc_hi_map, hi.data(), P * 4, cudaMemcpyHostToDevice));
-    UAVRL_CUDA(cudaMemcpy(l->tc_lo_map, lo.data(), P * 4, cudaMemcpyHostToDevice));
+    const size_t img = (size_t)l->tc.train_img_bytes;
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_local, img));
+    UAVRL_CUDA(cudaMalloc((void **)&l->tc_img_target, img));
+    UAVRL_CUDA(cudaMemset(l->tc_img_local, 0, img));
+    UAVRL_CUDA(cudaMemset(l->tc_img_target, 0, img));
+    int32_t **maps[] = { &l->tc_hi_map, &l->tc_lo_map, &l->tc_hi2_map, &l->tc_lo2_map };
+    std::vector<int32_t> *src[] = { &hi, &lo, &hi2, &lo2 };
+    for (int i = 0; i < 4; ++i) {
+        UAVRL_CUDA(cudaMalloc((void **)maps[i], P * 4));
+        UAVRL_CUDA(cudaMemcpy(*maps[i], src[i]->data(), P * 4, cudaMemcpyHostToDevice));
+    }
     UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
     l->y_cap = l->cfg.batch_size;
     l->tc_ok = true;
-    return 0;
+    return tc_train_init(l);
 }
 
 }  // namespace uavrl

@@ -1,0 +1,429 @@
+// tc_train.cu -- the TD update's forward + backward on the tensor cores (tcgen05 / TMEM, 3xTF32), sm_100a.
+//
+// Replaces the arithmetic of Trainer.update (Trainer/DuelingDQN_Trainer.py:164-180, DDQN_Trainer.py:93-107,
+// DQN_Trainer.py:107-126): Q(s).gather(a), MSE against the TD target, loss.backward().
+//
+//   tc_train_kernel  one CTA = R (32/64) sampled transitions.  Forward chain exactly like tc_forward.cu, then the
+//                    loss / dLoss/dQ in the head epilogue, then the dX chain with the TRANSPOSED weight blocks of the
+//                    training image:  dH_l = dZ_{l+1} * W_{l+1}  (A = dZ rows, B = W^T K-major), ReLU mask applied
+//                    in the epilogue.  Hidden activations and every dZ are written once to a per-sample scratch
+//                    (L2 resident: 4096 x ~0.9 KB) for the weight-gradient pass.
+//   tc_dw_kernel     split-K weight gradients: CTA (layer l, chunk of 128 samples) computes
+//                    dW_l^T [in+1 x out] = [act_l ; 1]^T (in+1 x 128) * dZ_l (128 x out)  -- the extra all-ones
+//                    row yields the bias gradient for free -- and stores its slice of partial `chunk`.
+//                    reduce_adam_kernel then sums B/128 partials (instead of B/32) in a fixed order.
+// All products use the hi*hi + hi*lo + lo*hi TF32 split (fp32-grade, see tc_forward.cu).
+#include <string.h>
+
+#include "tc_forward.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace uavrl {
+
+constexpr int kDwChunk = 128;          // samples reduced by one dW CTA (the MMA's K extent)
+
+struct TcTrainArgs {
+    const unsigned char *img;          // local network, training image (forward blocks + biases + transposed blocks)
+    BatchSrc src;
+    int32_t B, R, n_tiles;
+    const float *y;                    // [B] TD targets
+    float inv_global_b;
+    float *act_buf, *dz_buf;           // per-sample scratch rows
+    float *loss_partials;              // [grid]
+};
+
+struct TcDwArgs {
+    BatchSrc src;
+    int32_t B, n_chunks, P;
+    const float *act_buf, *dz_buf;
+    float *partials;                   // [n_chunks][P]
+};
+
+static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+
+// issue hi*hi + hi*lo + lo*hi over `ksteps` K-steps (single thread)
+__device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, int ksteps)
+{
+    constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
+    uint64_t da = a_hi, db = b_hi;
+    umma_tf32(d, da, db, idesc, 0u);
+    for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
+    da = a_hi; db = b_lo;
+    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
+    da = a_lo; db = b_hi;
+    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int R = a.R;
+    const uint32_t a_bytes = (uint32_t)(R / 8) * umma_sbo(tc.max_k);
+    unsigned char *Ahi = smem, *Alo = smem + a_bytes, *W = smem + 2 * a_bytes;
+    __shared__ uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ const float *rows[kTcTile];
+    __shared__ int s_act[kTcTile];
+    __shared__ float s_y[kTcTile];
+    __shared__ float s_loss;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); s_loss = 0.f; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar); }
+    const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
+
+    uint32_t pkey[4];
+    Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+    uint32_t mphase = 0;
+    bool wready = false;
+    const int nl = tc.n_layers;
+    const int row = quad * 32 + lane;
+    const bool live = quad * 32 < R;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int base = tile * R;
+        if (tid < R) {
+            const int b = base + tid;
+            const float *p = nullptr; int act = 0; float y = 0.f;
+            if (b < a.B) {
+                const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
+                p = t.s; act = t.a; y = a.y[b];
+            }
+            rows[tid] = p; s_act[tid] = act; s_y[tid] = y;
+        }
+        __syncthreads();
+        {   // A operand of layer 0
+            const int K0 = tc.L[0].K_pad, chunks = K0 / 4;
+            const uint32_t sbo = umma_sbo(K0);
+            for (int i = tid; i < R * chunks; i += kTcThreads) {
+                const int r = i / chunks, j = i - r * chunks;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rows[r] && 4 * j < tc.in_dim) v = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
+                float4 h, l;
+                tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+                const uint32_t off = umma_off(r, 4 * j, sbo);
+                *reinterpret_cast<float4 *>(Ahi + off) = h;
+                *reinterpret_cast<float4 *>(Alo + off) = l;
+            }
+        }
+        if (!wready) { mbar_wait(&wbar, 0); wready = true; }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const int gb = base + row;                          // this thread's sample (valid when live && gb < B)
+        const bool mine = live && gb < a.B;
+
+        // ---------------- forward chain
+        for (int l = 0; l < nl; ++l) {
+            const TcLayer T = tc.L[l];
+            const uint32_t sbo = umma_sbo(T.K_pad);
+            const uint32_t dcol = (uint32_t)(l & 1) * 128u;
+            if (tid == 0) {
+                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo),
+                             umma_idesc_tf32(kTcTile, T.N_pad), T.K_pad / 8);
+                umma_commit(&mbar);
+            }
+            mbar_wait(&mbar, mphase);
+            mphase ^= 1;
+            tc_fence_after();
+            const float *bias = bias_all + T.bias_off;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            if (l + 1 < nl) {
+                const uint32_t sbon = umma_sbo(T.N_pad);
+                float *act_row = a.act_buf + (size_t)gb * tc.act_stride + tc.L[l + 1].act_off;
+                for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 x, h, lo4;
+                        x.x = fmaxf(v[4 * j + 0] + bias[c0 + 4 * j + 0], 0.f); x.y = fmaxf(v[4 * j + 1] + bias[c0 + 4 * j + 1], 0.f);
+                        x.z = fmaxf(v[4 * j + 2] + bias[c0 + 4 * j + 2], 0.f); x.w = fmaxf(v[4 * j + 3] + bias[c0 + 4 * j + 3], 0.f);
+                        tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
+                        const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
+                        *reinterpret_cast<float4 *>(Ahi + off) = h;
+                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (mine) *reinterpret_cast<float4 *>(act_row + c0 + 4 * j) = x;      // kept for ReLU' and dW
+                    }
+                }
+            } else {
+                // head: Q(s, .), loss, dLoss/dHead -> next A operand (K = 32) and the dz scratch
+                const uint32_t sbon = umma_sbo(T.N_pad);
+                if (half == 0 && live) {
+                    float q[32];
+                    tmem_ld32(taddr, q);
+                    const int nA = tc.n_actions;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] += bias[j];
+                    if (tc.dueling) {
+                        float s = 0.f, V = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < nA) s += q[j]; if (j == nA) V = q[j]; }
+                        const float mean = s / (float)nA;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = V + q[j] - mean;
+                    }
+                    const int act = s_act[row];
+                    float qa = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j == act) qa = q[j];
+                    float gq = 0.f;
+                    if (mine) {
+                        const float diff = qa - s_y[row];
+                        atomicAdd(&s_loss, diff * diff);
+                        gq = 2.f * diff * a.inv_global_b;
+                    }
+                    float g[32];
+                    const float inv = 1.f / (float)nA;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float gj;
+                        if (tc.dueling) gj = (j < nA) ? gq * ((j == act ? 1.f : 0.f) - inv) : (j == nA ? gq : 0.f);
+                        else gj = (j == act) ? gq : 0.f;
+                        g[j] = gj;
+                    }
+                    float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + T.dz_off;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 x = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]), h, lo4;
+                        tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
+                        const uint32_t off = umma_off(row, 4 * j, sbon);
+                        *reinterpret_cast<float4 *>(Ahi + off) = h;
+                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (mine) *reinterpret_cast<float4 *>(dz_row + 4 * j) = x;
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+        }
+
+        // ---------------- dX chain: dZ_{l-1} = (dZ_l * W_l) .* (H_l > 0), l = nl-1 .. 1
+        for (int l = nl - 1; l >= 1; --l) {
+            const TcLayer T = tc.L[l];
+            const uint32_t sbo = umma_sbo(T.N_pad);             // reduction runs over this layer's outputs
+            const uint32_t dcol = (uint32_t)((l + 1) & 1) * 128u;       // the head used (nl-1)&1: alternate from there
+            if (tid == 0) {
+                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                             umma_desc(smem_u32(W + T.t_hi_off), sbo), umma_desc(smem_u32(W + T.t_lo_off), sbo),
+                             umma_idesc_tf32(kTcTile, T.K_pad), T.N_pad / 8);
+                umma_commit(&mbar);
+            }
+            mbar_wait(&mbar, mphase);
+            mphase ^= 1;
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            const uint32_t sbon = umma_sbo(T.K_pad);
+            const float *act_row = a.act_buf + (size_t)gb * tc.act_stride + T.act_off;           // H_l (this layer's input)
+            float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + tc.L[l - 1].dz_off;
+            for (int c0 = half * 32; live && c0 < T.K_pad; c0 += 64) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 hh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mine) hh = *reinterpret_cast<const float4 *>(act_row + c0 + 4 * j);
+                    float4 x, h, lo4;
+                    x.x = hh.x > 0.f ? v[4 * j + 0] : 0.f; x.y = hh.y > 0.f ? v[4 * j + 1] : 0.f;
+                    x.z = hh.z > 0.f ? v[4 * j + 2] : 0.f; x.w = hh.w > 0.f ? v[4 * j + 3] : 0.f;
+                    if (mine) *reinterpret_cast<float4 *>(dz_row + c0 + 4 * j) = x;
+                    if (l > 1) {
+                        tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
+                        const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
+                        *reinterpret_cast<float4 *>(Ahi + off) = h;
+                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+        }
+    }
+    if (tid == 0) a.loss_partials[blockIdx.x] = s_loss;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------ split-K weight gradients
+__global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int l = blockIdx.x % tc.n_layers, chunk = blockIdx.x / tc.n_layers;
+    const TcLayer T = tc.L[l];
+    const int rowsA = T.K_real + 1;                           // input features + the all-ones row (bias gradient)
+    const int gA = (rowsA + 7) / 8, gB = T.N_pad / 8;
+    constexpr uint32_t SBO = umma_sbo(kDwChunk);               // K extent = 128 samples -> 4096 B per 8 rows
+    unsigned char *Ahi = smem, *Alo = Ahi + gA * SBO, *Bhi = Alo + gA * SBO, *Blo = Bhi + gB * SBO;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ const float *rows[kDwChunk];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
+    const int b0 = chunk * kDwChunk;
+    if (tid < kDwChunk) {
+        const int b = b0 + tid;
+        const float *p = nullptr;
+        if (b < a.B) {
+            if (l == 0) {
+                uint32_t pkey[4];
+                Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+                p = resolve_transition(a.src, b, tc.in_dim, pkey).s;
+            } else {
+                p = a.act_buf + (size_t)b * tc.act_stride + T.act_off;
+            }
+        }
+        rows[tid] = p;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row
+    const int fch = (T.K_real + 3) / 4;
+    for (int i = tid; i < kDwChunk * fch; i += kTcThreads) {
+        const int bl = i % kDwChunk, jc = i / kDwChunk;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rows[bl]) v = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc);
+        const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int f = 4 * jc + e;
+            if (f < T.K_real) {
+                float hi, lo; tf32_split(vv[e], hi, lo);
+                const uint32_t off = umma_off(f, bl, SBO);
+                *reinterpret_cast<float *>(Ahi + off) = hi;
+                *reinterpret_cast<float *>(Alo + off) = lo;
+            }
+        }
+    }
+    for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
+        const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
+        const uint32_t off = umma_off(f, bl, SBO);
+        *reinterpret_cast<float *>(Ahi + off) = (f == T.K_real && rows[bl]) ? 1.f : 0.f;
+        *reinterpret_cast<float *>(Alo + off) = 0.f;
+    }
+    // B = dZ^T : element (row o, col b)
+    const int och = T.N_pad / 4;
+    for (int i = tid; i < kDwChunk * och; i += kTcThreads) {
+        const int bl = i % kDwChunk, jc = i / kDwChunk;
+        const int b = b0 + bl;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < a.B) v = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+        const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float hi, lo; tf32_split(vv[e], hi, lo);
+            const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+            *reinterpret_cast<float *>(Bhi + off) = hi;
+            *reinterpret_cast<float *>(Blo + off) = lo;
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO), umma_desc(smem_u32(Alo), SBO), umma_desc(smem_u32(Bhi), SBO),
+                     umma_desc(smem_u32(Blo), SBO), umma_idesc_tf32(kTcTile, T.N_pad), kDwChunk / 8);
+        umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    // epilogue: accumulator row f = input feature (or the ones row), column o = output unit
+    float *part = a.partials + (size_t)chunk * a.P;
+    const int f = quad * 32 + lane;
+    for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
+        if (quad * 32 >= rowsA) break;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        if (f < rowsA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int o = c0 + j;
+                if (o < T.N_real) {
+                    const bool vrow = o >= T.out_main;                                   // dueling value head row
+                    if (f < T.K_real) part[vrow ? T.w2_off + f : T.w_off + o * T.K_real + f] = v[j];
+                    else part[vrow ? T.b2_off : T.b_off + o] = v[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }
+static size_t dw_smem_bytes(const TcNet &tc)
+{
+    size_t mx = 0;
+    for (int l = 0; l < tc.n_layers; ++l) {
+        const size_t b = (size_t)2 * ((tc.L[l].K_real + 1 + 7) / 8 + tc.L[l].N_pad / 8) * umma_sbo(kDwChunk);
+        if (b > mx) mx = b;
+    }
+    return mx;
+}
+
+int tc_train_init(uavrl_learner *l)
+{
+    l->tc_train_ok = false;
+    const TcNet &tc = l->tc;
+    for (int i = 0; i < tc.n_layers; ++i)
+        if (tc.L[i].K_real + 1 > 128) return 0;                  // no room for the ones row
+    // the M=128 MMA reads 16 row groups from each A buffer: with fewer real rows it runs into the next buffers,
+    // which must still be inside the CTA's allocation
+    if (train_smem_bytes(tc, 32) > 227 * 1024 || dw_smem_bytes(tc) > 227 * 1024) return 0;
+    if (train_smem_bytes(tc, 32) < (size_t)(32 / 8) * umma_sbo(tc.max_k) + (size_t)16 * umma_sbo(tc.max_k)) return 0;
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
+    const size_t cap = (size_t)l->cfg.batch_size;
+    UAVRL_CUDA(cudaMalloc((void **)&l->act_buf, cap * (size_t)(tc.act_stride > 0 ? tc.act_stride : 4) * 4));
+    UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, cap * (size_t)tc.dz_stride * 4));
+    l->train_cap = (int32_t)cap;
+    l->tc_train_ok = true;
+    return 0;
+}
+
+int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
+                    int *n_loss_parts, cudaStream_t st)
+{
+    const TcNet &tc = l->tc;
+    TcTrainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.img = l->tc_img_local; a.src = src; a.B = B; a.y = y; a.inv_global_b = 1.0f / (float)global_batch;
+    a.act_buf = l->act_buf; a.dz_buf = l->dz_buf; a.loss_partials = l->loss_partials;
+    a.R = (B >= 64 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
+    a.n_tiles = (B + a.R - 1) / a.R;
+    const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+    tc_train_kernel<<<grid, kTcThreads, train_smem_bytes(tc, a.R), st>>>(tc, a);
+    UAVRL_LAUNCHED();
+    TcDwArgs d;
+    memset(&d, 0, sizeof(d));
+    d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
+    d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
+    tc_dw_kernel<<<d.n_chunks * tc.n_layers, kTcThreads, dw_smem_bytes(tc), st>>>(tc, d);
+    UAVRL_LAUNCHED();
+    *n_grad_parts = d.n_chunks;
+    *n_loss_parts = grid;
+    return 0;
+}
+
+}  // namespace uavrl
