@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--replay", type=int, default=1 << 20, help="replay capacity per GPU (transitions)")
     ap.add_argument("--pool", type=int, default=2048, help="scenario pool size (host RRT)")
     ap.add_argument("--eps", type=float, default=0.1)
+    ap.add_argument("--tc", type=int, default=1, help="1 = tcgen05 3xTF32 tensor-core path for the Q-network (default), 0 = fp32 CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -230,6 +231,7 @@ def run_ours(a):
     L = engine.Learner(OBS, hidden, 27, dueling, ALGOS[a.algo], lr=5e-4, gamma=0.99, batch_size=B, update_loop=3,
                        replay_capacity=a.replay, lockstep_envs=N, seed=1234 + rank, device=local)
     L.init_params(0)                       # same seed on every rank: replicas start identical
+    tc_on = L.set_tensor_cores(bool(a.tc))
     stream = torch.cuda.current_stream(dev)
 
     def iterate(k):
@@ -285,7 +287,8 @@ def run_ours(a):
                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64 env state / f32 obs+learner", "data": "synthetic",
-               "config": config_dict(a, world), "clocks": clocks, "gpu_launches": int(launches),
+               "config": dict(config_dict(a, world), qnet_path=("tcgen05 3xTF32 (fp32-grade)" if tc_on else "fp32 CUDA cores")),
+               "clocks": clocks, "gpu_launches": int(launches),
                "host_wall_ms_per_step": 1e3 * t_wall / a.steps}
 
     # ---- roofline pass: per-kernel CUDA-event time (rank 0's GPU; same workload, events between kernels)

@@ -13,6 +13,7 @@
 // forms Q (dueling combine), then eps-greedy / argmax / max / gather depending on the mode.
 #include "tc_forward.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "tma.cuh"
@@ -100,8 +101,11 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
 
 size_t tc_smem_bytes(const TcNet &tc) { return (size_t)2 * tc.a_bytes + (size_t)tc.img_bytes; }
 
+#define TC_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcArgs a)
 {
+    TC_TRACE(0);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *Ahi = smem, *Alo = smem + tc.a_bytes, *W = smem + 2 * tc.a_bytes;
     __shared__ uint64_t wbar, mbar;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    TC_TRACE(1);
     if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
@@ -144,26 +149,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             rows[tid] = p; s_rew[tid] = r; s_done[tid] = d;
         }
         __syncthreads();
-        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout
+        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout (4 loads in flight per thread)
         {
-            const int K0 = tc.L[0].K_pad, chunks = K0 / 4;
+            const int K0 = tc.L[0].K_pad, chunks = K0 / 4, total = R * chunks;
             const uint32_t sbo = umma_sbo(K0);
-            for (int i = tid; i < R * chunks; i += kTcThreads) {
-                const int r = i / chunks, j = i - r * chunks;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rows[r] && 4 * j < tc.in_dim) v = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
-                float4 h, l;
-                tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
-                const uint32_t off = umma_off(r, 4 * j, sbo);
-                *reinterpret_cast<float4 *>(Ahi + off) = h;
-                *reinterpret_cast<float4 *>(Alo + off) = l;
+            for (int i0 = tid; i0 < total; i0 += 4 * kTcThreads) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTcThreads;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < total) {
+                        const int r = i / chunks, j = i - r * chunks;
+                        if (rows[r] && 4 * j < tc.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTcThreads;
+                    if (i < total) {
+                        const int r = i / chunks, j = i - r * chunks;
+                        float4 h, l;
+                        tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+                        const uint32_t off = umma_off(r, 4 * j, sbo);
+                        *reinterpret_cast<float4 *>(Ahi + off) = h;
+                        *reinterpret_cast<float4 *>(Alo + off) = l;
+                    }
+                }
             }
         }
+        TC_TRACE(2);
         if (!wready) { mbar_wait(&wbar, 0); wready = true; }
+        TC_TRACE(3);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        TC_TRACE(4);
 
         for (int l = 0; l < tc.n_layers; ++l) {
             const TcLayer T = tc.L[l];
@@ -187,9 +209,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }   // lo * hi
                 umma_commit(&mbar);
             }
+            TC_TRACE(5 + 3 * l);
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
+            TC_TRACE(6 + 3 * l);
             const float *bias = bias_all + T.bias_off;
             const int row = quad * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
@@ -215,6 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 tc_fence_before();
                 __syncthreads();
                 tc_fence_after();
+                TC_TRACE(7 + 3 * l);
             } else {
                 // head epilogue: Q row of this sample, then the mode's output
                 if (half == 0 && live) {
@@ -273,9 +298,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             }
         }
     }
+    TC_TRACE(20);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
+    TC_TRACE(21);
 }
 
 int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
@@ -284,8 +311,20 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
     a.rows_per_tile = (a.n >= 128 * 148) ? 128 : (a.n >= 64 * 148) ? 64 : 32;
     a.n_tiles = (a.n + a.rows_per_tile - 1) / a.rows_per_tile;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+    static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
+    long long *tr = nullptr;
+    if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 32 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 32 * sizeof(long long))); a.trace = tr; }
     tc_forward_kernel<<<grid, kTcThreads, tc_smem_bytes(l->tc), st>>>(l->tc, a);
     UAVRL_LAUNCHED();
+    if (trace_on) {
+        long long h[32];
+        UAVRL_CUDA(cudaStreamSynchronize(st));
+        UAVRL_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(tr);
+        fprintf(stderr, "[tc_trace] mode=%d n=%d R=%d grid=%d cycles since start:", a.mode, a.n, a.rows_per_tile, grid);
+        for (int i = 1; i < 22; ++i) if (h[i]) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 

@@ -23,6 +23,7 @@ struct TcArgs {
     float *q_out;                      // optional [n][A]
     float *y_out;                      // TD modes: y[b] = r + gamma * next_q * (1 - d)
     float gamma;
+    long long *trace;                  // debug: CTA 0 / thread 0 writes clock64() at stage boundaries (UAVRL_TC_TRACE=1)
 };
 
 int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::vector<int32_t> &hi_map, std::vector<int32_t> &lo_map,

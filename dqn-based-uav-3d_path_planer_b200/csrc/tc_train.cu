@@ -56,6 +56,38 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t
     for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
 }
 
+// Gather R rows (pointers in rows[]) into the layer-0 A operand.  All of a thread's loads are issued before any
+// is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.
+__device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo)
+{
+    const int chunks = K0 / 4, total = R * chunks;
+    const uint32_t sbo = umma_sbo(K0);
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kTcThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < total) {
+                const int r = i / chunks, j = i - r * chunks;
+                if (rows[r] && 4 * j < in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i < total) {
+                const int r = i / chunks, j = i - r * chunks;
+                float4 h, l;
+                tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+                const uint32_t off = umma_off(r, 4 * j, sbo);
+                *reinterpret_cast<float4 *>(Ahi + off) = h;
+                *reinterpret_cast<float4 *>(Alo + off) = l;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -99,20 +131,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             rows[tid] = p; s_act[tid] = act; s_y[tid] = y;
         }
         __syncthreads();
-        {   // A operand of layer 0
-            const int K0 = tc.L[0].K_pad, chunks = K0 / 4;
-            const uint32_t sbo = umma_sbo(K0);
-            for (int i = tid; i < R * chunks; i += kTcThreads) {
-                const int r = i / chunks, j = i - r * chunks;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rows[r] && 4 * j < tc.in_dim) v = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
-                float4 h, l;
-                tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
-                const uint32_t off = umma_off(r, 4 * j, sbo);
-                *reinterpret_cast<float4 *>(Ahi + off) = h;
-                *reinterpret_cast<float4 *>(Alo + off) = l;
-            }
-        }
+        build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
         if (!wready) { mbar_wait(&wbar, 0); wready = true; }
         fence_proxy_async();
         tc_fence_before();
@@ -220,20 +239,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                              umma_idesc_tf32(kTcTile, T.K_pad), T.N_pad / 8);
                 umma_commit(&mbar);
             }
+            // H_l (this layer's input, written by the forward epilogue of the same thread) is needed for ReLU':
+            // fetch it while the MMA runs.  K_pad <= 128 -> at most two 32-column chunks per thread.
+            const float *act_row = a.act_buf + (size_t)gb * tc.act_stride + T.act_off;
+            float4 hpre[2][8];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = half * 32 + cc * 64;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hpre[cc][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mine && c0 < T.K_pad) hpre[cc][j] = *reinterpret_cast<const float4 *>(act_row + c0 + 4 * j);
+                }
+            }
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             const uint32_t sbon = umma_sbo(T.K_pad);
-            const float *act_row = a.act_buf + (size_t)gb * tc.act_stride + T.act_off;           // H_l (this layer's input)
             float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + tc.L[l - 1].dz_off;
-            for (int c0 = half * 32; live && c0 < T.K_pad; c0 += 64) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = half * 32 + cc * 64;
+                if (!(live && c0 < T.K_pad)) continue;
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float4 hh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (mine) hh = *reinterpret_cast<const float4 *>(act_row + c0 + 4 * j);
+                    const float4 hh = hpre[cc][j];
                     float4 x, h, lo4;
                     x.x = hh.x > 0.f ? v[4 * j + 0] : 0.f; x.y = hh.y > 0.f ? v[4 * j + 1] : 0.f;
                     x.z = hh.z > 0.f ? v[4 * j + 2] : 0.f; x.w = hh.w > 0.f ? v[4 * j + 3] : 0.f;
@@ -295,21 +328,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row
+    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row;
+    // 4 loads are in flight per thread before any is split / stored
     const int fch = (T.K_real + 3) / 4;
-    for (int i = tid; i < kDwChunk * fch; i += kTcThreads) {
-        const int bl = i % kDwChunk, jc = i / kDwChunk;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rows[bl]) v = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc);
-        const float vv[4] = { v.x, v.y, v.z, v.w };
+    for (int i0 = tid; i0 < kDwChunk * fch; i0 += 4 * kTcThreads) {
+        float4 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int f = 4 * jc + e;
-            if (f < T.K_real) {
-                float hi, lo; tf32_split(vv[e], hi, lo);
-                const uint32_t off = umma_off(f, bl, SBO);
-                *reinterpret_cast<float *>(Ahi + off) = hi;
-                *reinterpret_cast<float *>(Alo + off) = lo;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i >= kDwChunk * fch) continue;
+            const int bl = i % kDwChunk, jc = i / kDwChunk;
+            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int f = 4 * jc + e;
+                if (f < T.K_real) {
+                    float hi, lo; tf32_split(vv[e], hi, lo);
+                    const uint32_t off = umma_off(f, bl, SBO);
+                    *reinterpret_cast<float *>(Ahi + off) = hi;
+                    *reinterpret_cast<float *>(Alo + off) = lo;
+                }
             }
         }
     }
@@ -321,18 +365,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
     // B = dZ^T : element (row o, col b)
     const int och = T.N_pad / 4;
-    for (int i = tid; i < kDwChunk * och; i += kTcThreads) {
-        const int bl = i % kDwChunk, jc = i / kDwChunk;
-        const int b = b0 + bl;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < a.B) v = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
-        const float vv[4] = { v.x, v.y, v.z, v.w };
+    for (int i0 = tid; i0 < kDwChunk * och; i0 += 4 * kTcThreads) {
+        float4 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float hi, lo; tf32_split(vv[e], hi, lo);
-            const uint32_t off = umma_off(4 * jc + e, bl, SBO);
-            *reinterpret_cast<float *>(Bhi + off) = hi;
-            *reinterpret_cast<float *>(Blo + off) = lo;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < kDwChunk * och) {
+                const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
+                if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i >= kDwChunk * och) continue;
+            const int bl = i % kDwChunk, jc = i / kDwChunk;
+            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float hi, lo; tf32_split(vv[e], hi, lo);
+                const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+                *reinterpret_cast<float *>(Bhi + off) = hi;
+                *reinterpret_cast<float *>(Blo + off) = lo;
+            }
         }
     }
     fence_proxy_async();
