@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--pool", type=int, default=2048, help="scenario pool size (host RRT)")
     ap.add_argument("--eps", type=float, default=0.1)
     ap.add_argument("--tc", type=int, default=1, help="1 = tcgen05 3xTF32 tensor-core path for the Q-network (default), 0 = fp32 CUDA cores")
+    ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
+                    help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -129,7 +131,7 @@ def config_dict(a, world):
                         % (a.envs, world, a.algo.upper(), a.net, "-".join(map(str, NETS[a.net][0])), a.batch, a.replay),
             "envs_per_gpu": a.envs, "global_envs": a.envs * world, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
             "net": a.net, "algo": a.algo, "replay_per_gpu": a.replay, "eps": a.eps, "scenario_pool": a.pool,
-            "parallelism": "dp%d (env shards + replay shards per GPU, gradient all-reduce)" % world,
+            "parallelism": "dp%d (env shards + replay shards per GPU, %s)" % (world, "one-shot NVLink all-reduce fused into the Adam kernel" if a.dp == "fused" else "NCCL gradient all-reduce"),
             "l2": "replay ring %d MB/GPU > 126 MB L2, fully prefilled before timing; sampled rows come from all of it"
                   % (a.replay * 412 // 1000000)}
 
@@ -233,12 +235,19 @@ def run_ours(a):
     L.init_params(0)                       # same seed on every rank: replicas start identical
     tc_on = L.set_tensor_cores(bool(a.tc))
     stream = torch.cuda.current_stream(dev)
+    if world > 1 and a.dp == "fused":
+        L.connect_peers(dist, rank, world)
 
     def iterate(k):
         """k lockstep iterations.  1 GPU: the fused C loop.  N GPUs: env/act/ring per rank, local gradient,
         NCCL all-reduce of the gradient vector, identical Adam step on every rank."""
         if world == 1:
             engine.train_run(env, L, k, a.eps, 1, True, want_stats=False)
+            return
+        if a.dp == "fused":
+            for _ in range(k):
+                engine.train_run(env, L, 1, a.eps, 1, False, want_stats=False)
+                L.update_dp(B * world)
             return
         gt = L.grad_tensor()
         for _ in range(k):
@@ -294,23 +303,33 @@ def run_ours(a):
     # ---- roofline pass: per-kernel CUDA-event time (rank 0's GPU; same workload, events between kernels)
     if rank == 0:
         kp = engine.train_profile(env, L, min(a.steps, 200), a.eps) / float(min(a.steps, 200))   # ms per launch
-        names = ("act_eps_greedy", "env_step", "td_update", "reduce_adam")
+        names = ("act_eps_greedy", "env_step", "td_target", "fwd_bwd", "weight_grad", "reduce_adam")
         fwd = FWD_FLOPS[a.net]
-        n_fwd = 3 if a.algo == "dqn" else 4         # fwd local(s), fwd target(s') [, fwd local(s')], bwd ~ 2 fwd -> +2
-        upd_flops = (n_fwd + 1) * fwd * B           # 4x fwd (DQN) / 5x fwd (DDQN) per sample
-        alg_bytes = {"act_eps_greedy": ACT_BYTES * N, "env_step": ENV_STEP_BYTES * N, "td_update": TRANSITION_BYTES * B,
-                     "reduce_adam": 28 * L.P}
-        alg_flops = {"act_eps_greedy": fwd * N, "env_step": 0, "td_update": upd_flops, "reduce_adam": 0}
+        n_tgt = 1 if a.algo == "dqn" else 2          # target fwd (+ local fwd on s' for double DQN)
+        # per sampled transition 4x fwd (DQN) / 5x fwd (DDQN) = target pass(es) + fwd on s + backward (2 fwd)
+        if tc_on:
+            alg_flops = {"act_eps_greedy": fwd * N, "env_step": 0, "td_target": n_tgt * fwd * B, "fwd_bwd": 2 * fwd * B,
+                         "weight_grad": fwd * B, "reduce_adam": 0}
+            alg_bytes = {"act_eps_greedy": ACT_BYTES * N, "env_step": ENV_STEP_BYTES * N, "td_target": (OBS * 4 + 9) * B * n_tgt,
+                         "fwd_bwd": (OBS * 4 + 8) * B, "weight_grad": OBS * 4 * B, "reduce_adam": 28 * L.P}
+        else:
+            alg_flops = {"act_eps_greedy": fwd * N, "env_step": 0, "td_target": 0, "fwd_bwd": (n_tgt + 3) * fwd * B,
+                         "weight_grad": 0, "reduce_adam": 0}
+            alg_bytes = {"act_eps_greedy": ACT_BYTES * N, "env_step": ENV_STEP_BYTES * N, "td_target": 0,
+                         "fwd_bwd": TRANSITION_BYTES * B, "weight_grad": 0, "reduce_adam": 28 * L.P}
         kernels = {}
         for n_, t_ in zip(names, kp):
+            if t_ <= 0:
+                continue
             kernels[n_] = {"ms": float(t_), "share": float(t_ / kp.sum()), "GBps": alg_bytes[n_] / (t_ * 1e-3) / 1e9,
                            "TFLOPs": alg_flops[n_] / (t_ * 1e-3) / 1e12}
-        dom = names[int(np.argmax(kp))]
-        if dom in ("td_update", "act_eps_greedy"):
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        if alg_flops[dom] > 0:
             ach = kernels[dom]["TFLOPs"]
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sustained"], "traffic": None,
-                    "note": "fp32 CUDA-core MLP path measured against the %s bf16 tensor peak; its HBM view is %.1f GB/s of %.0f"
+                    "note": ("3xTF32 tcgen05 path: 3 tensor-core products per algorithmic product, " if tc_on else "fp32 CUDA-core path, ")
+                            + "measured against the %s bf16 tensor peak; HBM view %.1f GB/s of %.0f"
                             % (pk["src"], kernels[dom]["GBps"], pk["hbm"])}
         else:
             ach = kernels[dom]["GBps"]

@@ -87,8 +87,9 @@ SIGNATURES = {
     "uavrl_learner_hard_update": (C.c_int, [VP, VP]),
     "uavrl_learner_lockstep_restart": (C.c_int, [VP]),
     "uavrl_learner_set_tensor_cores": (C.c_int, [VP, C.c_int32]),
-    "uavrl_learner_comm_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
-    "uavrl_learner_set_peers": (C.c_int, [VP, C.c_int32, C.c_int32, C.POINTER(VP), C.POINTER(VP)]),
+    "uavrl_learner_comm_init": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
+    "uavrl_learner_comm_connect": (C.c_int, [VP, VP, VP]),
+    "uavrl_learner_update_dp": (C.c_int, [VP, VP, C.c_int32, VP, VP]),
     "uavrl_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),
     "uavrl_train_profile": (C.c_int, [VP, VP, C.c_int32, C.c_float, VP, VP]),
     "uavrl_last_error": (C.c_char_p, []),

@@ -577,6 +577,117 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     }
 }
 
+// ---- data-parallel pair.  (1) reduce this rank's partials into its symmetric buffer and, once the whole grid is
+// done, raise this rank's flag on every peer (remote stores over NVLink).  (2) wait for every rank's flag, read
+// all gradient vectors through peer-mapped memory, sum in rank order, Adam.
+__global__ void __launch_bounds__(256)
+reduce_publish_kernel(int P, int nparts, int n_loss_parts, float inv_b, const float *__restrict__ partials,
+                      const float *__restrict__ loss_partials, float *__restrict__ my_grad, unsigned *counter,
+                      unsigned *const *peer_flags, int rank, int world, unsigned epoch)
+{
+    __shared__ float red[4][64];
+    const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + ix;
+    float g = 0.f;
+    if (i < P) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+        int c = cg;
+        for (; c + 28 < nparts; c += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(c + 4 * u) * P + i];
+        }
+        for (; c < nparts; c += 4) acc[0] += partials[(size_t)c * P + i];
+        g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    }
+    red[cg][ix] = g;
+    __syncthreads();
+    if (cg == 0 && i < P) my_grad[i] = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
+    if (blockIdx.x == 0 && threadIdx.x >= 224) {                 // last warp of block 0: this rank's loss share
+        const int lane = threadIdx.x & 31;
+        float s = 0.f;
+        for (int c = lane; c < n_loss_parts; c += 32) s += loss_partials[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) my_grad[P] = s * inv_b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev == gridDim.x - 1) {                             // the whole gradient vector is in place
+            *counter = 0u;
+            __threadfence_system();
+            for (int q = 0; q < world; ++q) {
+                volatile unsigned *f = peer_flags[q] + rank;
+                *f = epoch;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+allreduce_adam_kernel(AdamArgs a, float *const *peer_grads, int buf_off, const unsigned *my_flags, unsigned epoch,
+                      float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
+                      float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
+                      const int32_t *__restrict__ img_map, float *__restrict__ tc_local, float *__restrict__ tc_target,
+                      const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, const int32_t *__restrict__ tc_hi2,
+                      const int32_t *__restrict__ tc_lo2, float *__restrict__ loss_out)
+{
+    if (threadIdx.x < a.world) {                                  // one thread per peer spins on that peer's flag
+        while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) { }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.P) {
+        float g = 0.f;
+        for (int q = 0; q < a.world; ++q) g += ld_relaxed_sys(peer_grads[q] + buf_off + i);     // fixed rank order
+        grad[i] = g;
+        float mi = m[i], vi = v[i], p = local[i];
+        mi = mi + (g - mi) * a.beta1_c;
+        vi = vi * a.beta2 + a.beta2_c * g * g;
+        const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+        p = p - a.step_size * (mi / denom);
+        m[i] = mi; v[i] = vi; local[i] = p;
+        const int im = img_map[i];
+        img_local[im] = p;
+        if (a.hard) { target[i] = p; img_target[im] = p; }
+        if (tc_local) {
+            const int ih = tc_hi[i], il = tc_lo[i];
+            float hi = p, lo = 0.f;
+            if (il >= 0) tf32_split(p, hi, lo);
+            tc_local[ih] = hi;
+            if (il >= 0) tc_local[il] = lo;
+            const int ih2 = tc_hi2[i], il2 = tc_lo2[i];
+            if (ih2 >= 0) { tc_local[ih2] = hi; tc_local[il2] = lo; }
+            if (a.hard) {
+                tc_target[ih] = hi;
+                if (il >= 0) tc_target[il] = lo;
+                if (ih2 >= 0) { tc_target[ih2] = hi; tc_target[il2] = lo; }
+            }
+        }
+    }
+    if (i == 0 && loss_out) {
+        float s = 0.f;
+        for (int q = 0; q < a.world; ++q) s += ld_relaxed_sys(peer_grads[q] + buf_off + a.P);
+        *loss_out = s;
+    }
+}
+
 __global__ void copy_kernel(int n, const float *__restrict__ src, float *__restrict__ dst)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -630,7 +741,7 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
 }
 
 static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
-                              cudaStream_t st, cudaEvent_t mid);
+                              cudaStream_t st, cudaEvent_t *mid, bool partials_only = false);
 
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
                   cudaStream_t st)
@@ -638,13 +749,15 @@ int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch
     return launch_update_impl(l, src, B, global_batch, loss_out, apply, st, nullptr);
 }
 
-int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t mid)
+// profiling form: mid[0] after the TD-target pass, mid[1] after the forward/backward kernel, mid[2] after the
+// weight-gradient kernel (== mid[1] on the CUDA-core path); the optimiser kernel follows
+int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t *mid)
 {
     return launch_update_impl(l, src, B, B, l->loss_dev, true, st, mid);
 }
 
 static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
-                              cudaStream_t st, cudaEvent_t mid)
+                              cudaStream_t st, cudaEvent_t *mid, bool partials_only)
 {
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
@@ -675,6 +788,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
         if ((rc = launch_tc_forward(l, a, st))) return rc;
         y_in = l->y_buf;
     }
+    if (mid) UAVRL_CUDA(cudaEventRecord(mid[0], st));
     int nparts = grid, n_loss_parts = grid;
     if (y_in && l->tc_train_ok) {
         // the whole update on the tensor cores: forward + dX chain, then split-K weight gradients (tc_train.cu)
@@ -686,7 +800,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
             l->train_cap = B;
         }
         if ((B + 127) / 128 > l->max_ctas) return fail(UAVRL_ERR_INVALID, "batch too large for the gradient partial buffer");
-        int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st);
+        int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st, mid ? mid[1] : nullptr);
         if (rc) return rc;
     } else {
     UpdateArgs ua;
@@ -696,10 +810,13 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     ua.y_in = y_in;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
     UAVRL_LAUNCHED();
+    if (mid) UAVRL_CUDA(cudaEventRecord(mid[1], st));
     }
-    if (mid) UAVRL_CUDA(cudaEventRecord(mid, st));
+    if (mid) UAVRL_CUDA(cudaEventRecord(mid[2], st));
     l->last_nparts = nparts;
+    l->last_n_loss_parts = n_loss_parts;
     l->last_global_batch = global_batch;
+    if (partials_only) return 0;
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = l->net.P; a.nparts = nparts; a.n_loss_parts = n_loss_parts; a.apply = apply ? 1 : 0; a.world = l->world;
@@ -736,6 +853,42 @@ static int repack_images(uavrl_learner *l, cudaStream_t st)
                                                    (float *)l->tc_img_target);
         UAVRL_LAUNCHED();
     }
+    return 0;
+}
+
+static void fill_adam_args(uavrl_learner *l, AdamArgs &a)
+{
+    l->adam_t += 1;
+    const double b1 = 0.9, b2 = 0.999;
+    const double bc1 = 1.0 - pow(b1, (double)l->adam_t), bc2 = 1.0 - pow(b2, (double)l->adam_t);
+    a.step_size = (float)((double)l->cfg.lr / bc1);
+    a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
+    a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
+    a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
+}
+
+// local gradient partials (same kernels as the single-GPU update, no optimiser step), then the fused
+// publish / all-reduce+Adam pair
+int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, cudaStream_t st)
+{
+    int rc = launch_update_impl(l, src, B, global_batch, nullptr, false, st, nullptr, true);
+    if (rc) return rc;
+    l->flag_epoch += 1;
+    const int P = l->net.P;
+    const int buf_off = (int)((l->flag_epoch & 1u) * (unsigned)(P + 1));
+    reduce_publish_kernel<<<(P + 63) / 64, 256, 0, st>>>(P, l->last_nparts, l->last_n_loss_parts, 1.0f / (float)global_batch,
+                                                       l->partials, l->loss_partials, l->comm_grad + buf_off, l->comm_counter,
+                                                       l->peer_flag_dev, l->rank, l->world, l->flag_epoch);
+    UAVRL_LAUNCHED();
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.apply = 1; a.world = l->world;
+    fill_adam_args(l, a);
+    allreduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a, l->peer_grad_dev, buf_off, l->comm_flags, l->flag_epoch, l->grad,
+                                                         l->local, l->m, l->v, l->target, l->img_local, l->img_target, l->img_map,
+                                                         (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map,
+                                                         l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev);
+    UAVRL_LAUNCHED();
     return 0;
 }
 
@@ -800,7 +953,7 @@ int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
     if ((rc = dev_alloc(&l->local, P)) || (rc = dev_alloc(&l->target, P)) || (rc = dev_alloc(&l->m, P)) ||
         (rc = dev_alloc(&l->v, P)) || (rc = dev_alloc(&l->grad, P)) ||
         (rc = dev_alloc(&l->partials, P * (size_t)l->max_ctas)) || (rc = dev_alloc(&l->loss_partials, (size_t)l->max_ctas)) ||
-        (rc = dev_alloc(&l->loss_dev, 1)) || (rc = dev_alloc(&l->flags, 64)))
+        (rc = dev_alloc(&l->loss_dev, 1)))
         return rc;
     {
         const size_t wf = (size_t)l->net.smem_w_floats;
@@ -841,7 +994,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
     if (!l) return 0;
     cudaSetDevice(l->cfg.device);
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
-                     l->r_act, l->r_rew, l->r_done, l->flags, l->peer_grads_dev, l->peer_flags_dev, l->img_local, l->img_target,
+                     l->r_act, l->r_rew, l->r_done, l->comm_grad, l->comm_flags, l->comm_counter, l->peer_grad_dev, l->peer_flag_dev, l->img_local, l->img_target,
                      l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf, l->tc_hi2_map,
                      l->tc_lo2_map, l->act_buf, l->dz_buf };
     for (void *p : ptrs) cudaFree(p);
@@ -1045,30 +1198,60 @@ int uavrl_learner_lockstep_restart(uavrl_learner *l)
     return 0;
 }
 
-int uavrl_learner_comm_buffers(uavrl_learner *l, void **grad_dev, void **flag_dev, size_t *grad_bytes, size_t *flag_bytes)
+// ------------------------------------------------------------------ fused NVLink all-reduce + Adam
+int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void *grad_handle_out, void *flag_handle_out)
 {
-    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
-    if (grad_dev) *grad_dev = l->grad;
-    if (flag_dev) *flag_dev = l->flags;
-    if (grad_bytes) *grad_bytes = (size_t)l->net.P * 4;
-    if (flag_bytes) *flag_bytes = 64 * sizeof(unsigned);
+    if (!l || world < 1 || world > 64 || rank < 0 || rank >= world || !grad_handle_out || !flag_handle_out)
+        return fail(UAVRL_ERR_INVALID, "bad rank/world/handle pointer");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    l->rank = rank; l->world = world;
+    if (!l->comm_grad) {
+        const size_t n = 2 * ((size_t)l->net.P + 1);
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_grad, n * sizeof(float)));
+        UAVRL_CUDA(cudaMemset(l->comm_grad, 0, n * sizeof(float)));
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, 64 * sizeof(unsigned)));
+        UAVRL_CUDA(cudaMemset(l->comm_flags, 0, 64 * sizeof(unsigned)));
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_counter, sizeof(unsigned)));
+        UAVRL_CUDA(cudaMemset(l->comm_counter, 0, sizeof(unsigned)));
+    }
+    cudaIpcMemHandle_t hg, hf;
+    UAVRL_CUDA(cudaIpcGetMemHandle(&hg, l->comm_grad));
+    UAVRL_CUDA(cudaIpcGetMemHandle(&hf, l->comm_flags));
+    memcpy(grad_handle_out, &hg, sizeof(hg));
+    memcpy(flag_handle_out, &hf, sizeof(hf));
     return 0;
 }
 
-int uavrl_learner_set_peers(uavrl_learner *l, int32_t rank, int32_t world, void *const *peer_grad_ptrs,
-                            void *const *peer_flag_ptrs)
+int uavrl_learner_comm_connect(uavrl_learner *l, const void *grad_handles, const void *flag_handles)
 {
-    if (!l || world < 1 || rank < 0 || rank >= world) return fail(UAVRL_ERR_INVALID, "bad rank/world");
+    if (!l || !grad_handles || !flag_handles || !l->comm_grad) return fail(UAVRL_ERR_STATE, "uavrl_learner_comm_connect before comm_init");
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
-    l->rank = rank; l->world = world;
-    if (peer_grad_ptrs && peer_flag_ptrs) {
-        cudaFree(l->peer_grads_dev); cudaFree(l->peer_flags_dev);
-        UAVRL_CUDA(cudaMalloc((void **)&l->peer_grads_dev, sizeof(void *) * world));
-        UAVRL_CUDA(cudaMalloc((void **)&l->peer_flags_dev, sizeof(void *) * world));
-        UAVRL_CUDA(cudaMemcpy(l->peer_grads_dev, peer_grad_ptrs, sizeof(void *) * world, cudaMemcpyHostToDevice));
-        UAVRL_CUDA(cudaMemcpy(l->peer_flags_dev, peer_flag_ptrs, sizeof(void *) * world, cudaMemcpyHostToDevice));
+    for (int q = 0; q < l->world; ++q) {
+        if (q == l->rank) { l->peer_grad_host[q] = l->comm_grad; l->peer_flag_host[q] = l->comm_flags; continue; }
+        cudaIpcMemHandle_t hg, hf;
+        memcpy(&hg, (const char *)grad_handles + (size_t)q * sizeof(hg), sizeof(hg));
+        memcpy(&hf, (const char *)flag_handles + (size_t)q * sizeof(hf), sizeof(hf));
+        UAVRL_CUDA(cudaIpcOpenMemHandle(&l->peer_grad_host[q], hg, cudaIpcMemLazyEnablePeerAccess));
+        UAVRL_CUDA(cudaIpcOpenMemHandle(&l->peer_flag_host[q], hf, cudaIpcMemLazyEnablePeerAccess));
     }
+    cudaFree(l->peer_grad_dev); cudaFree(l->peer_flag_dev);
+    UAVRL_CUDA(cudaMalloc((void **)&l->peer_grad_dev, sizeof(void *) * l->world));
+    UAVRL_CUDA(cudaMalloc((void **)&l->peer_flag_dev, sizeof(void *) * l->world));
+    UAVRL_CUDA(cudaMemcpy(l->peer_grad_dev, l->peer_grad_host, sizeof(void *) * l->world, cudaMemcpyHostToDevice));
+    UAVRL_CUDA(cudaMemcpy(l->peer_flag_dev, l->peer_flag_host, sizeof(void *) * l->world, cudaMemcpyHostToDevice));
+    l->comm_ready = true;
     return 0;
+}
+
+int uavrl_learner_update_dp(uavrl_learner *l, const int32_t *idx_tape_dev, int32_t global_batch, float *loss_dev, void *stream)
+{
+    if (!l || global_batch <= 0) return fail(UAVRL_ERR_INVALID, "bad argument");
+    if (!l->comm_ready) return fail(UAVRL_ERR_STATE, "uavrl_learner_update_dp before uavrl_learner_comm_connect");
+    UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    l->epoch += 1;
+    if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay holds <= batch_size transitions");
+    BatchSrc src = replay_source(l, idx_tape_dev);
+    return launch_update_dp(l, src, l->cfg.batch_size, global_batch, loss_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -114,13 +114,17 @@ struct uavrl_learner {
     int64_t count = 0;                // valid transitions
     bool frame0_valid = false;
     uint64_t act_calls = 0;
-    // data-parallel
+    // data-parallel: one-shot NVLink all-reduce fused with Adam (symmetric buffers exchanged through CUDA IPC)
     int32_t rank = 0, world = 1;
-    void **peer_grads_dev = nullptr;  // device array of `world` pointers
-    void **peer_flags_dev = nullptr;
-    unsigned *flags = nullptr;        // [64] own flag words (symmetric)
+    float *comm_grad = nullptr;       // own, [2][P+1]: double-buffered gradient vector (+ loss partial)
+    unsigned *comm_flags = nullptr;   // own, [64]: slot q is raised by rank q
+    unsigned *comm_counter = nullptr; // last-block detection of the publish kernel
+    float **peer_grad_dev = nullptr;  // device array [world]: every rank's comm_grad as mapped on THIS device
+    unsigned **peer_flag_dev = nullptr;
+    void *peer_grad_host[64] = { nullptr }, *peer_flag_host[64] = { nullptr };
+    bool comm_ready = false;
     unsigned flag_epoch = 0;
-    int last_nparts = 0;
+    int last_nparts = 0, last_n_loss_parts = 0;
     int last_global_batch = 0;
 };
 
@@ -189,7 +193,8 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,
                   bool apply, cudaStream_t st);
-int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t mid);
+int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, cudaStream_t st);
+int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t *mid);
 int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **act, float **rew, uint8_t **done);
 void lockstep_commit(uavrl_learner *l);
 BatchSrc replay_source(uavrl_learner *l, const int32_t *idx_tape);

@@ -31,7 +31,7 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
 // tensor-core training path (tc_train.cu): forward + dX chain, then split-K dW; gradients land in l->partials
 int tc_train_init(uavrl_learner *l);
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
-                    int *n_loss_parts, cudaStream_t st);
+                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain = nullptr);
 size_t tc_smem_bytes(const TcNet &tc);
 int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st);
 int tc_init(uavrl_learner *l);        // builds the TC images/maps; leaves l->tc_ok = false when the net does not fit

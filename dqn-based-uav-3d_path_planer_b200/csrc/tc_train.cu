@@ -459,7 +459,7 @@ int tc_train_init(uavrl_learner *l)
 }
 
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
-                    int *n_loss_parts, cudaStream_t st)
+                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain)
 {
     const TcNet &tc = l->tc;
     TcTrainArgs a;
@@ -471,6 +471,7 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     tc_train_kernel<<<grid, kTcThreads, train_smem_bytes(tc, a.R), st>>>(tc, a);
     UAVRL_LAUNCHED();
+    if (after_chain) UAVRL_CUDA(cudaEventRecord(after_chain, st));
     TcDwArgs d;
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;

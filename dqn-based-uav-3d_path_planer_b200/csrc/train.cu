@@ -79,13 +79,14 @@ extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_i
         return fail(UAVRL_ERR_STATE, "uavrl_train_profile needs a warmed-up lockstep env/learner pair");
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<cudaEvent_t> ev((size_t)n_iters * 5);
+    constexpr int NE = 7;                      // events per iteration -> 6 intervals
+    std::vector<cudaEvent_t> ev((size_t)n_iters * NE);
     for (auto &e : ev) UAVRL_CUDA(cudaEventCreate(&e));
     int rc;
     for (int it = 0; it < n_iters; ++it) {
         float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
         lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
-        cudaEvent_t *e = &ev[(size_t)it * 5];
+        cudaEvent_t *e = &ev[(size_t)it * NE];
         UAVRL_CUDA(cudaEventRecord(e[0], st));
         if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[1], st));
@@ -95,16 +96,15 @@ extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_i
         l->epoch += 1;
         if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay not warmed up");
         BatchSrc src = replay_source(l, nullptr);
-        // launch_update = td kernel + reduce/adam kernel; split the pair with an event in between
-        if ((rc = launch_update_split(l, src, l->cfg.batch_size, st, e[3]))) return rc;
-        UAVRL_CUDA(cudaEventRecord(e[4], st));
+        if ((rc = launch_update_split(l, src, l->cfg.batch_size, st, &e[3]))) return rc;   // records e[3], e[4], e[5]
+        UAVRL_CUDA(cudaEventRecord(e[6], st));
     }
     UAVRL_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < 4; ++k) ms_out[k] = 0.f;
+    for (int k = 0; k < NE - 1; ++k) ms_out[k] = 0.f;
     for (int it = 0; it < n_iters; ++it)
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NE - 1; ++k) {
             float ms = 0.f;
-            UAVRL_CUDA(cudaEventElapsedTime(&ms, ev[(size_t)it * 5 + k], ev[(size_t)it * 5 + k + 1]));
+            UAVRL_CUDA(cudaEventElapsedTime(&ms, ev[(size_t)it * NE + k], ev[(size_t)it * NE + k + 1]));
             ms_out[k] += ms;
         }
     for (auto &e : ev) cudaEventDestroy(e);

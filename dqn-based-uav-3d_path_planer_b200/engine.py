@@ -266,6 +266,22 @@ class Learner:
         arr = (C.c_float * self.P).from_address(ptr) if False else None  # noqa: F841 (device memory: no host view)
         return _DevView(ptr, self.P, self.device).tensor()
 
+    def connect_peers(self, dist, rank, world):
+        """Exchange the CUDA IPC handles of the symmetric gradient / flag buffers over torch.distributed and map
+        every peer's buffers (NVLink P2P) -- enables update_dp(), the fused one-shot all-reduce + Adam."""
+        hg = (C.c_ubyte * 64)(); hf = (C.c_ubyte * 64)()
+        check(_lib.lib().uavrl_learner_comm_init(self.h, rank, world, hg, hf))
+        mine = torch.tensor(list(bytes(hg)) + list(bytes(hf)), dtype=torch.uint8, device=self.device)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        allh = torch.stack(allh).cpu().numpy()
+        g = np.ascontiguousarray(allh[:, :64]); f = np.ascontiguousarray(allh[:, 64:])
+        check(_lib.lib().uavrl_learner_comm_connect(self.h, _ptr(g), _ptr(f)))
+        dist.barrier(device_ids=[self.device.index])
+
+    def update_dp(self, global_batch, idx_tape=None, loss=None):
+        check(_lib.lib().uavrl_learner_update_dp(self.h, _ptr(idx_tape), int(global_batch), _ptr(loss), _stream(self.device)))
+
     def apply_grads(self):
         check(_lib.lib().uavrl_learner_apply_grads(self.h, _stream(self.device)))
 
@@ -300,7 +316,8 @@ def train_run(env, learner, n_iters, eps, updates_per_iter=1, do_update=True, wa
 
 
 def train_profile(env, learner, n_iters, eps):
-    """Per-kernel device time (ms, summed over n_iters) of {act, env_step, td_update, reduce_adam}."""
-    ms = np.zeros(4, np.float32)
+    """Per-kernel device time (ms, summed over n_iters) of
+    {act, env_step, td_target, fwd_bwd, weight_grad, reduce_adam}."""
+    ms = np.zeros(6, np.float32)
     check(_lib.lib().uavrl_train_profile(env.h, learner.h, int(n_iters), float(eps), _ptr(ms), _stream(env.device)))
     return ms

@@ -197,14 +197,18 @@ int uavrl_learner_hard_update(uavrl_learner *l, void *stream);   /* DuelingDQN_T
  * restarts empty (envs that end episodes restart by themselves with auto_reset and need no call). */
 int uavrl_learner_lockstep_restart(uavrl_learner *l);
 
-/* One-shot NVLink all-reduce fused with Adam: every rank reads all peers' gradient vectors over
- * peer-mapped memory in rank order (bit-identical replicas) inside the optimiser kernel.
- * peer_grad_ptrs / peer_flag_ptrs: device pointers valid on THIS device (cudaIpcOpenMemHandle),
- * one per rank, own rank included. */
-int uavrl_learner_comm_buffers(uavrl_learner *l, void **grad_dev, void **flag_dev, size_t *grad_bytes,
-                               size_t *flag_bytes);
-int uavrl_learner_set_peers(uavrl_learner *l, int32_t rank, int32_t world, void *const *peer_grad_ptrs,
-                            void *const *peer_flag_ptrs);
+/* One-shot NVLink all-reduce fused with the optimiser (data-parallel training, one process per GPU):
+ *   uavrl_learner_comm_init     allocate this rank's symmetric gradient buffer + flag words, return their
+ *                               CUDA IPC handles (64 bytes each) for exchange (e.g. torch.distributed.all_gather)
+ *   uavrl_learner_comm_connect  open every rank's handles (grad_handles / flag_handles: [world][64] bytes)
+ *   uavrl_learner_update_dp     epoch += 1; local gradient (loss scaled by 1/global_batch) -> reduced into the
+ *                               symmetric buffer -> flags raised on every peer over NVLink -> the optimiser kernel
+ *                               waits for all ranks, reads all `world` gradient vectors through peer-mapped memory,
+ *                               sums them in rank order (bit-identical replicas) and applies Adam.  No NCCL call.
+ * loss_dev (optional) receives the GLOBAL batch loss. */
+int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void *grad_handle_out, void *flag_handle_out);
+int uavrl_learner_comm_connect(uavrl_learner *l, const void *grad_handles, const void *flag_handles);
+int uavrl_learner_update_dp(uavrl_learner *l, const int32_t *idx_tape_dev, int32_t global_batch, float *loss_dev, void *stream);
 
 /* ------------------------------------------------------------------ fused lockstep training loop
  * PathPlan_City.run_thread_OffPolicy + update (Envs/PathPlan_City.py:364-385,757-776) for all envs:
@@ -222,9 +226,10 @@ int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps
                     int32_t updates_per_iter, int32_t do_update, uavrl_train_stats *stats_host,
                     void *stream);
 
-/* The same loop with a CUDA event recorded on `stream` before/after every kernel: ms_out[4] receives the
- * summed device time of {act, env_step, td_update, reduce_adam} over the n_iters iterations (bench.py's
- * roofline pass; event gaps make the loop slower, never use it for throughput). */
+/* The same loop with a CUDA event recorded on `stream` before/after every kernel: ms_out[6] receives the
+ * summed device time of {act, env_step, td_target, fwd_bwd, weight_grad, reduce_adam} over the n_iters
+ * iterations (bench.py's roofline pass; on the CUDA-core path td_target and weight_grad are 0 because
+ * fwd_bwd does everything; event gaps make the loop slower, never use it for throughput). */
 int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, float *ms_out, void *stream);
 
 const char *uavrl_last_error(void);

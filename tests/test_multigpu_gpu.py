@@ -55,6 +55,23 @@ if rank == 0:
     np.testing.assert_allclose(L.get_params(1), S.get_params(1), atol=3e-6)
     assert L.counters() == S.counters() == (4, 4)
     print("DP_OK")
+# ---- fused one-shot NVLink all-reduce + Adam (no NCCL on the update path) vs the NCCL path above
+F = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DDQN, batch_size=B, replay_capacity=B + 1, update_loop=2, device=rank)
+F.set_params(g["ddqn_qvalue3_local0"], 0); F.set_params(g["ddqn_qvalue3_target0"], 1)
+F.push(dev(s[sl]), dev(a[sl], torch.int32), dev(r[sl]), dev(s2[sl]), dev(d[sl], torch.uint8))
+F.push(dev(s[:1]), dev(a[:1], torch.int32), dev(r[:1]), dev(s2[:1]), dev(d[:1], torch.uint8))
+F.connect_peers(dist, rank, world)
+loss = torch.zeros(1, device="cuda:%%d" %% rank)
+for it in range(4):
+    F.update_dp(B * world, idx_tape=idx, loss=loss)
+torch.cuda.synchronize()
+assert np.array_equal(F.get_params(0), L.get_params(0)), "fused all-reduce+Adam differs from NCCL all-reduce + Adam"
+assert np.array_equal(F.get_params(1), L.get_params(1))
+assert F.counters() == L.counters()
+ls = [torch.zeros_like(loss) for _ in range(world)]; dist.all_gather(ls, loss)
+assert all(torch.equal(ls[0], q) for q in ls) and float(loss) > 0          # every rank holds the same GLOBAL loss
+if rank == 0:
+    print("FUSED_OK")
 dist.barrier(device_ids=[rank])
 dist.destroy_process_group()
 '''
@@ -68,4 +85,4 @@ def test_two_rank_nccl_data_parallel(tmp_path):
            "--master-port", "29577", str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "DP_OK" in r.stdout
+    assert "DP_OK" in r.stdout and "FUSED_OK" in r.stdout
