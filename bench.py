@@ -201,7 +201,7 @@ def run_reference_arm(a):
            "dtype": "f64 env / f32 learner", "data": "synthetic", "config": config_dict(a, 1),
            "cpu_baseline": {"value": v, "unit": "env_steps/s", "cores": nthreads, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out, default=float))
+    print(json.dumps(out, default=float), flush=True)
 
 
 # ============================================================================ GPU arm
@@ -219,6 +219,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     dims, b, p = load_city()
@@ -366,9 +367,13 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     if rank == 0:
-        print(json.dumps(out, default=float))
+        print(json.dumps(out, default=float), flush=True)
+    sys.stdout.flush()
     if world > 1:
         dist.barrier(device_ids=[local])
+    L.close()
+    env.close()
+    if world > 1:
         dist.destroy_process_group()
 
 

@@ -993,6 +993,12 @@ int uavrl_learner_destroy(uavrl_learner *l)
 {
     if (!l) return 0;
     cudaSetDevice(l->cfg.device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < l->world && l->comm_ready; ++q) {
+        if (q == l->rank) continue;
+        if (l->peer_grad_host[q]) cudaIpcCloseMemHandle(l->peer_grad_host[q]);
+        if (l->peer_flag_host[q]) cudaIpcCloseMemHandle(l->peer_flag_host[q]);
+    }
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
                      l->r_act, l->r_rew, l->r_done, l->comm_grad, l->comm_flags, l->comm_counter, l->peer_grad_dev, l->peer_flag_dev, l->img_local, l->img_target,
                      l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf, l->tc_hi2_map,
