@@ -219,8 +219,18 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on fd 1 at communicator creation: park stdout on stderr meanwhile so that
+        # this process's stdout carries the ONE JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     dims, b, p = load_city()
     city = engine.City(dims[0], dims[1], dims[2], b)
@@ -246,9 +256,7 @@ def run_ours(a):
             engine.train_run(env, L, k, a.eps, 1, True, want_stats=False)
             return
         if a.dp == "fused":
-            for _ in range(k):
-                engine.train_run(env, L, 1, a.eps, 1, False, want_stats=False)
-                L.update_dp(B * world)
+            engine.train_run_dp(env, L, k, a.eps, B * world)
             return
         gt = L.grad_tensor()
         for _ in range(k):

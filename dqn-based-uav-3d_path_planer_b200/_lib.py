@@ -91,6 +91,7 @@ SIGNATURES = {
     "uavrl_learner_comm_connect": (C.c_int, [VP, VP, VP]),
     "uavrl_learner_update_dp": (C.c_int, [VP, VP, C.c_int32, VP, VP]),
     "uavrl_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),
+    "uavrl_train_run_dp": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, VP]),
     "uavrl_train_profile": (C.c_int, [VP, VP, C.c_int32, C.c_float, VP, VP]),
     "uavrl_last_error": (C.c_char_p, []),
     "uavrl_version": (C.c_char_p, []),

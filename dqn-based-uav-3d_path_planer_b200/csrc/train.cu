@@ -72,6 +72,35 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
     return 0;
 }
 
+extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, int32_t global_batch, void *stream)
+{
+    if (!env || !l || n_iters < 0 || global_batch <= 0) return fail(UAVRL_ERR_INVALID, "bad argument");
+    if (l->mode != kReplayLockstep || l->cfg.lockstep_envs != env->d.n)
+        return fail(UAVRL_ERR_INVALID, "learner.lockstep_envs must equal env.n_envs");
+    if (!l->comm_ready) return fail(UAVRL_ERR_STATE, "uavrl_train_run_dp before uavrl_learner_comm_connect");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_train_run_dp before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    for (int it = 0; it < n_iters; ++it) {
+        float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
+        lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
+        if (!l->frame0_valid) {
+            if ((rc = launch_env_observe(env->d, obs_t, st))) return rc;
+            l->frame0_valid = true;
+        }
+        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        lockstep_commit(l);
+        l->epoch += 1;
+        // every rank must take part in every all-reduce: the caller warms the replay up first
+        if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay holds <= batch_size transitions (warm up with uavrl_train_run first)");
+        BatchSrc src = replay_source(l, nullptr);
+        if ((rc = launch_update_dp(l, src, l->cfg.batch_size, global_batch, l->loss_dev, st))) return rc;
+    }
+    return 0;
+}
+
 extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, float *ms_out, void *stream)
 {
     if (!env || !l || n_iters <= 0 || !ms_out) return fail(UAVRL_ERR_INVALID, "bad argument");

@@ -321,3 +321,8 @@ def train_profile(env, learner, n_iters, eps):
     ms = np.zeros(6, np.float32)
     check(_lib.lib().uavrl_train_profile(env.h, learner.h, int(n_iters), float(eps), _ptr(ms), _stream(env.device)))
     return ms
+
+
+def train_run_dp(env, learner, n_iters, eps, global_batch):
+    """uavrl_train_run_dp: lockstep iterations whose update is the fused NVLink all-reduce + Adam."""
+    check(_lib.lib().uavrl_train_run_dp(env.h, learner.h, int(n_iters), float(eps), int(global_batch), _stream(env.device)))

@@ -226,6 +226,10 @@ int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps
                     int32_t updates_per_iter, int32_t do_update, uavrl_train_stats *stats_host,
                     void *stream);
 
+/* Data-parallel form of uavrl_train_run (after uavrl_learner_comm_connect): every iteration ends with
+ * uavrl_learner_update_dp on this rank's replay shard; global_batch = batch_size x world. */
+int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, int32_t global_batch, void *stream);
+
 /* The same loop with a CUDA event recorded on `stream` before/after every kernel: ms_out[6] receives the
  * summed device time of {act, env_step, td_target, fwd_bwd, weight_grad, reduce_adam} over the n_iters
  * iterations (bench.py's roofline pass; on the CUDA-core path td_target and weight_grad are 0 because
