@@ -16,7 +16,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("uav_oracle.c", "dqn_oracle.c", "uav_oracle.h", "dqn_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("uav_oracle.c", "dqn_oracle.c", "sac_oracle.c", "uav_oracle.h", "dqn_oracle.h", "sac_oracle.h")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
@@ -61,6 +61,9 @@ def lib():
         _lib.ora_fly_power.argtypes = [C.c_double] * 10
         _lib.ora_net_param_count.restype = C.c_int64
         _lib.ora_dqn_update.restype = C.c_float
+        _lib.ora_sac_update.restype = C.c_float
+        _lib.ora_sac_actor_params.restype = C.c_int64
+        _lib.ora_sac_critic_params.restype = C.c_int64
     return _lib
 
 
@@ -311,3 +314,58 @@ class OracleTrainLoop:
             j = self.rng.choice(self.count, self.B, replace=False)
             loss, _ = self.learner.update(self.S[j], self.A[j], self.R[j], self.S2[j], self.D[j])
         return loss
+
+
+# ------------------------------------------------------------------ SAC continuous (sac_oracle.c)
+class SacCfg(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32), ("action_bound", C.c_float),
+                ("actor_lr", C.c_float), ("critic_lr", C.c_float), ("alpha_lr", C.c_float), ("target_entropy", C.c_float),
+                ("gamma", C.c_float), ("tau", C.c_float)]
+
+
+class SacState(C.Structure):
+    _fields_ = [(k, C.POINTER(C.c_float)) for k in ("actor", "c1", "c2", "t1", "t2", "actor_m", "actor_v", "c1_m", "c1_v", "c2_m", "c2_v")] + \
+               [("log_alpha", C.c_float), ("la_m", C.c_float), ("la_v", C.c_float), ("step", C.c_int64)]
+
+
+class OracleSac:
+    def __init__(self, actor, c1, c2, t1, t2, log_alpha, actor_lr=1e-4, critic_lr=1e-3, alpha_lr=1e-4, target_entropy=1.0,
+                 gamma=0.99, tau=0.05, obs_dim=100, hidden=64, act_dim=2, action_bound=1.0):
+        self.cfg = SacCfg(obs_dim, hidden, act_dim, action_bound, actor_lr, critic_lr, alpha_lr, target_entropy, gamma, tau)
+        self.arr = {k: np.array(v, np.float32).copy() for k, v in dict(actor=actor, c1=c1, c2=c2, t1=t1, t2=t2).items()}
+        for k in ("actor", "c1", "c2"):
+            self.arr[k + "_m"] = np.zeros_like(self.arr[k]); self.arr[k + "_v"] = np.zeros_like(self.arr[k])
+        self.st = SacState()
+        for k, v in self.arr.items():
+            setattr(self.st, k, _p(v, C.c_float))
+        self.st.log_alpha = float(log_alpha)
+        assert lib().ora_sac_actor_params(C.byref(self.cfg)) == self.arr["actor"].size
+        assert lib().ora_sac_critic_params(C.byref(self.cfg)) == self.arr["c1"].size
+
+    @property
+    def log_alpha(self):
+        return float(self.st.log_alpha)
+
+    def actor_forward(self, s, eps):
+        s = np.ascontiguousarray(s, np.float32); eps = np.ascontiguousarray(eps, np.float32)
+        B = s.shape[0]
+        a = np.zeros((B, self.cfg.act_dim), np.float32); lp = np.zeros_like(a)
+        lib().ora_sac_actor_forward(C.byref(self.cfg), _p(self.arr["actor"], C.c_float), _p(s, C.c_float), _p(eps, C.c_float),
+                                    C.c_int32(B), _p(a, C.c_float), _p(lp, C.c_float))
+        return a, lp
+
+    def critic_forward(self, which, s, a):
+        s = np.ascontiguousarray(s, np.float32); a = np.ascontiguousarray(a, np.float32)
+        q = np.zeros((s.shape[0], self.cfg.act_dim), np.float32)
+        lib().ora_sac_critic_forward(C.byref(self.cfg), _p(self.arr[which], C.c_float), _p(s, C.c_float), _p(a, C.c_float),
+                                     C.c_int32(s.shape[0]), _p(q, C.c_float))
+        return q
+
+    def update(self, s, a, r, s2, d, eps_next, eps_cur):
+        f = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
+        s, a, r, s2, d, e1, e2 = map(f, (s, a, r, s2, d, eps_next, eps_cur))
+        l1, l2, la = C.c_float(), C.c_float(), C.c_float()
+        loss = lib().ora_sac_update(C.byref(self.cfg), C.byref(self.st), _p(s, C.c_float), _p(a, C.c_float), _p(r, C.c_float),
+                                    _p(s2, C.c_float), _p(d, C.c_float), _p(e1, C.c_float), _p(e2, C.c_float), C.c_int32(s.shape[0]),
+                                    C.byref(l1), C.byref(l2), C.byref(la))
+        return float(loss), float(l1.value), float(l2.value)

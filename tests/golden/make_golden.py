@@ -17,6 +17,8 @@ outputs of the reference itself, produced here and committed as small .npz fixtu
                    built only from the reference's own primitives.  This script ASSERTS that for the
                    three actions with (j,l)=(1,2) UAV27 is bit-identical to the reference's
                    update_PathPlan on every recorded step, then records episodes over all 27.
+  sac_golden.npz   SAC continuous update (Trainer/SAC_Trainer.py:317-379) with injected reparameterisation noise:
+                   batches, noise, parameter snapshots of actor / critics / targets, log_alpha, actor loss.
   dqn_golden.npz   learner math: the reference's DuelingDQN_Trainer.update, DDQN_Trainer /
                    DQN_Trainer.learn_off_policy (Trainer/*.py) run on fixed batches with torch CPU
                    fp32: initial params, batches, per-step loss, gradients, post-Adam params,
@@ -429,6 +431,76 @@ def gen_dqn(out):
     out["eps_schedule"] = np.asarray(vals, np.float64)
 
 
+def gen_sac(out):
+    """SAC continuous (Trainer/SAC_Trainer.py:317-379, nets BaseClass/BaseCNN.py:459-500) with the
+    reparameterisation noise injected: Normal.rsample is patched to consume recorded eps tensors."""
+    from FactoryClass.TrainerFactory import TrainerFactory
+    rng = np.random.default_rng(11)
+    B, K = 64, 6
+    SNAP = [0, 2, 5]
+    eps_queue = []
+
+    def rsample(self, sample_shape=torch.Size()):
+        e = eps_queue.pop(0)
+        assert e.shape == self.loc.shape
+        return self.loc + self.scale * e
+    orig = torch.distributions.Normal.rsample
+    torch.distributions.Normal.rsample = rsample
+    try:
+        torch.manual_seed(4321)
+        param = {"Trainer_Type": "SAC_Trainer", "Is_Train": "1", "IsPriority_Replay": "0", "name": "golden_sac",
+                 "actor": {"NetWork": "PolicyNetContinuous_SAC", "h": "1", "w": "100", "channel": "1", "action_bound": "1",
+                           "hiden_dim": "64", "output": "2", "lr": "0.0001"},
+                 "critic": {"NetWork": "QValueNetContinuous_SAC", "h": "1", "w": "100", "channel": "1", "hiden_dim": "64",
+                            "action_dim": "2", "lr": "0.001"},
+                 "SAC_param": {"IS_Continuous": "1", "alpha_lr": "0.0001", "target_entropy": "1", "gamma": "0.99", "tau": "0.05"},
+                 "replay_size": "10000", "LEARNING_RATE": "0.0005", "Batch_Size": str(B), "max_epoch": "100",
+                 "save_loop": "1000000000"}
+        tr = TrainerFactory().Create_Trainer(param)
+        assert tr is not None
+        tr.replay_memory.memory = [0] * (B + 1)            # only its length gates training (:327)
+        for nm in ("actor", "critic_1", "critic_2", "target_critic_1", "target_critic_2"):
+            out["sac_%s0" % nm] = flat_params(getattr(tr, nm))
+        out["sac_log_alpha0"] = np.float32(tr.log_alpha.item())
+        out["sac_hparams"] = np.array([1e-4, 1e-3, 1e-4, 1.0, 0.99, 0.05], np.float64)  # actor_lr critic_lr alpha_lr target_entropy gamma tau
+        keys = ("s", "a", "r", "s2", "d", "eps_next", "eps_cur")
+        rec = {k: [] for k in keys}
+        snaps = {nm: [] for nm in ("actor", "critic_1", "critic_2", "target_critic_1", "target_critic_2")}
+        la, losses = [], []
+        for step in range(K):
+            s, _, r, s2, d = synth_batch(rng, B, 27)
+            a = rng.uniform(-1, 1, size=(B, 2)).astype(np.float32)
+            e1 = rng.normal(size=(B, 2)).astype(np.float32); e2 = rng.normal(size=(B, 2)).astype(np.float32)
+            eps_queue[:] = [torch.tensor(e1), torch.tensor(e2)]
+            for k, v in zip(keys, (s, a, r, s2, d, e1, e2)):
+                rec[k].append(v)
+            td = {"states": s.tolist(), "actions": a.tolist(), "next_states": s2.tolist(), "rewards": r.tolist(), "dones": d.tolist()}
+            res = tr.update(td)
+            assert not eps_queue
+            losses.append(float(res["loss"]))
+            la.append(tr.log_alpha.item())
+            if step in SNAP:
+                for nm in snaps:
+                    snaps[nm].append(flat_params(getattr(tr, nm)))
+        for k in keys:
+            out["sac_" + k] = np.stack(rec[k])
+        out["sac_snap"] = np.asarray(SNAP, np.int32)
+        for nm in snaps:
+            out["sac_" + nm] = np.stack(snaps[nm])
+        out["sac_log_alpha"] = np.asarray(la, np.float32)
+        out["sac_actor_loss"] = np.asarray(losses, np.float32)
+        # get_action KAT (SAC_Trainer.py:444-448): action list of one state, noise injected
+        acts, e_list = [], []
+        for i in range(8):
+            e = rng.normal(size=(1, 2)).astype(np.float32)
+            eps_queue[:] = [torch.tensor(e)]
+            acts.append(tr.get_action(rec["s"][0][i], 0.0)); e_list.append(e[0])
+        out["sac_act_eps"] = np.stack(e_list); out["sac_act_out"] = np.asarray(acts, np.float32)
+        print("sac: actor", out["sac_actor0"].size, "critic", out["sac_critic_10"].size, "actor losses", losses[:3], "log_alpha", la[:2])
+    finally:
+        torch.distributions.Normal.rsample = orig
+
+
 if __name__ == "__main__":
     random.seed(42); np.random.seed(42); torch.manual_seed(42)
     env_out, env27_out, dqn_out = {}, {}, {}
@@ -437,5 +509,8 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "env27_golden.npz"), **env27_out)
     gen_dqn(dqn_out)
     np.savez_compressed(os.path.join(HERE, "dqn_golden.npz"), **dqn_out)
-    for f in ("env_golden.npz", "env27_golden.npz", "dqn_golden.npz"):
+    sac_out = {}
+    gen_sac(sac_out)
+    np.savez_compressed(os.path.join(HERE, "sac_golden.npz"), **sac_out)
+    for f in ("env_golden.npz", "env27_golden.npz", "dqn_golden.npz", "sac_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
