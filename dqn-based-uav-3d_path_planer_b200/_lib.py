@@ -14,7 +14,7 @@ LIB_PATH = _build.LIB
 OBS_DIM = 100
 MAX_HIDDEN = 4
 
-ACT_CONT_F32, ACT_CONT_F64, ACT_DISCRETE27 = 0, 1, 2
+ACT_CONT_F32, ACT_CONT_F64, ACT_DISCRETE27, ACT_CONT_F32X2 = 0, 1, 2, 3
 ALGO_DQN, ALGO_DDQN, ALGO_DUELING = 0, 1, 2
 INFO_NAMES = ("normal", "success", "lose")
 
@@ -44,6 +44,13 @@ class LearnerConfig(C.Structure):
                 ("n_actions", C.c_int32), ("dueling", C.c_int32), ("algo", C.c_int32),
                 ("lr", C.c_float), ("gamma", C.c_float), ("batch_size", C.c_int32),
                 ("update_loop", C.c_int32), ("replay_capacity", C.c_int64),
+                ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32)]
+
+
+class SacConfig(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32), ("action_bound", C.c_float),
+                ("actor_lr", C.c_float), ("critic_lr", C.c_float), ("alpha_lr", C.c_float), ("target_entropy", C.c_float),
+                ("gamma", C.c_float), ("tau", C.c_float), ("batch_size", C.c_int32), ("replay_capacity", C.c_int64),
                 ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32)]
 
 
@@ -91,6 +98,16 @@ SIGNATURES = {
     "uavrl_learner_comm_connect": (C.c_int, [VP, VP, VP]),
     "uavrl_learner_update_dp": (C.c_int, [VP, VP, C.c_int32, VP, VP]),
     "uavrl_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),
+    "uavrl_sac_create": (C.c_int, [C.POINTER(SacConfig), C.POINTER(VP)]),
+    "uavrl_sac_destroy": (C.c_int, [VP]),
+    "uavrl_sac_param_count": (C.c_int64, [VP, C.c_int32]),
+    "uavrl_sac_set_params": (C.c_int, [VP, C.c_int32, VP]),
+    "uavrl_sac_get_params": (C.c_int, [VP, C.c_int32, VP]),
+    "uavrl_sac_set_scalars": (C.c_int, [VP, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64]),
+    "uavrl_sac_get_scalars": (C.c_int, [VP, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "uavrl_sac_act": (C.c_int, [VP, VP, C.c_int32, VP, VP, VP]),
+    "uavrl_sac_update_batch": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "uavrl_sac_train_run": (C.c_int, [VP, VP, C.c_int32, C.c_int32, C.POINTER(TrainStats), VP]),
     "uavrl_train_run_dp": (C.c_int, [VP, VP, C.c_int32, C.c_float, C.c_int32, VP]),
     "uavrl_train_profile": (C.c_int, [VP, VP, C.c_int32, C.c_float, VP, VP]),
     "uavrl_last_error": (C.c_char_p, []),

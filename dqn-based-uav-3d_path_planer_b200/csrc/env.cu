@@ -107,6 +107,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
                 double act;
                 if (action_kind == UAVRL_ACT_CONT_F32) act = (double)static_cast<const float *>(actions)[e];
                 else if (action_kind == UAVRL_ACT_CONT_F64) act = static_cast<const double *>(actions)[e];
+                else if (action_kind == UAVRL_ACT_CONT_F32X2) act = (double)static_cast<const float *>(actions)[2 * e];
                 else act = (double)static_cast<const int32_t *>(actions)[e];
                 const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
                 const double *q = d.pool_sub + (size_t)scen * d.K * 3;
@@ -398,7 +399,7 @@ int uavrl_env_step(uavrl_env *env, int32_t action_kind, const void *actions_dev,
                    uint8_t *ended_dev, void *stream)
 {
     if (!env || !actions_dev) return fail(UAVRL_ERR_INVALID, "null argument");
-    if (action_kind < 0 || action_kind > 2) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
+    if (action_kind < 0 || action_kind > 3) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
     if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_step before uavrl_env_reset");
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     return launch_env_step(env->d, action_kind, actions_dev, next_obs_dev, reward_dev, done_dev, info_dev,
@@ -410,7 +411,7 @@ int uavrl_env_step_host(uavrl_env *env, int32_t action_kind, const void *actions
                         uint8_t *ended_host)
 {
     if (!env || !actions_host) return fail(UAVRL_ERR_INVALID, "null argument");
-    if (action_kind < 0 || action_kind > 2) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
+    if (action_kind < 0 || action_kind > 3) return fail(UAVRL_ERR_INVALID, "unknown action_kind");
     if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_step_host before uavrl_env_reset");
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     const size_t n = (size_t)env->d.n;
@@ -421,7 +422,7 @@ int uavrl_env_step_host(uavrl_env *env, int32_t action_kind, const void *actions
         UAVRL_CUDA(cudaMalloc((void **)&env->h_flags_dev, n * 4));
     }
     cudaStream_t st = env->own_stream;
-    const size_t asz = (action_kind == UAVRL_ACT_CONT_F64) ? 8 : 4;
+    const size_t asz = (action_kind == UAVRL_ACT_CONT_F64 || action_kind == UAVRL_ACT_CONT_F32X2) ? 8 : 4;
     UAVRL_CUDA(cudaMemcpyAsync(env->h_act_dev, actions_host, n * asz, cudaMemcpyHostToDevice, st));
     uint8_t *f = env->h_flags_dev;
     int rc = launch_env_step(env->d, action_kind, env->h_act_dev, obs_host ? env->h_obs_dev : nullptr,

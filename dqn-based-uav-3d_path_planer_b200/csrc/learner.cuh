@@ -14,7 +14,8 @@ constexpr int kMaxLayers = UAVRL_MAX_HIDDEN + 1;   // trunk layers + (combined) 
 struct LayerDev {
     int32_t in, out;                  // out of the head = n_actions (+1 value row when dueling)
     int32_t w_off, b_off;             // offsets in the flat state_dict-ordered parameter vector
-    int32_t w2_off, b2_off;           // dueling head only: fc_V.weight / fc_V.bias (row `out-1`)
+    int32_t w2_off, b2_off;           // second head block (rows out_main..out-1): dueling fc_V, SAC actor fc_std; -1 if none
+    int32_t out_main;                 // rows served by (w_off, b_off)
     int32_t smem_w, smem_b;           // offsets (floats) inside the smem weight area
 };
 
@@ -34,7 +35,8 @@ enum ReplayMode { kReplayPaired = 0, kReplayLockstep = 1, kBatchExplicit = 2 };
 struct BatchSrc {
     int32_t mode;
     const float *frames;              // replay observation rows [rows][in_dim]
-    const int32_t *act;               // [slots]
+    const int32_t *act;               // [slots] discrete action index (DQN family)
+    const float *act2;                // [slots][2] continuous action (SAC); nullptr otherwise
     const float *rew;                 // [slots]
     const uint8_t *done_u8;           // [slots]  (replay)          } one of the two
     const float *done_f32;            // [B]      (explicit batch)  }
@@ -162,14 +164,15 @@ __device__ __forceinline__ uint64_t perm_index(uint64_t i, uint64_t M, const uin
 }
 
 // batch position gb -> the transition's state row, next-state row and metadata
-struct Transition { const float *s, *s2; int a; float r, d; };
+struct Transition { const float *s, *s2; int a; float r, d, ax, ay; };
 __device__ __forceinline__ Transition resolve_transition(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4])
 {
     Transition t;
     if (src.mode == kBatchExplicit) {
         t.s = src.frames + (size_t)gb * in_dim;
         t.s2 = src.s2_rows + (size_t)gb * in_dim;
-        t.a = src.act[gb]; t.r = src.rew[gb]; t.d = src.done_f32[gb];
+        t.a = src.act ? src.act[gb] : 0; t.r = src.rew[gb]; t.d = src.done_f32[gb];
+        t.ax = src.act2 ? src.act2[2 * gb] : 0.f; t.ay = src.act2 ? src.act2[2 * gb + 1] : 0.f;
         return t;
     }
     const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb] : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
@@ -184,11 +187,29 @@ __device__ __forceinline__ Transition resolve_transition(const BatchSrc &src, in
     }
     t.s = src.frames + (size_t)row * in_dim;
     t.s2 = src.frames + (size_t)row2 * in_dim;
-    t.a = src.act[slot]; t.r = src.rew[slot]; t.d = src.done_u8[slot] ? 1.f : 0.f;
+    t.a = src.act ? src.act[slot] : 0; t.r = src.rew[slot]; t.d = src.done_u8[slot] ? 1.f : 0.f;
+    t.ax = src.act2 ? src.act2[2 * slot] : 0.f; t.ay = src.act2 ? src.act2[2 * slot + 1] : 0.f;
     return t;
 }
 #endif
 
+// optimiser kernel arguments (reduce_adam_kernel, learner.cu; also launched by sac.cu)
+struct AdamArgs {
+    int P, nparts, apply, hard, world, n_loss_parts;
+    float step_size, beta1_c, beta2, beta2_c, eps, bc2_sqrt, inv_b;
+};
+
+#if defined(__CUDACC__)
+__global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
+                                   float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
+                                   float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
+                                   const int32_t *__restrict__ img_map, float *__restrict__ tc_local, float *__restrict__ tc_target,
+                                   const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, const int32_t *__restrict__ tc_hi2,
+                                   const int32_t *__restrict__ tc_lo2, float *__restrict__ loss_out);
+#endif
+
+// generic MLP description: trunk widths + head = `head_main` rows (+ `head_extra` rows from a second parameter block)
+int build_mlp(int in_dim, int n_hidden, const int32_t *hidden, int head_main, int head_extra, NetDev &n);
 int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,

@@ -42,7 +42,7 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
         T.lo_off = off; off += bytes;
         if (T.K_pad > maxK) maxK = T.K_pad;
         T.w_off = L.w_off; T.b_off = L.b_off; T.w2_off = L.w2_off; T.b2_off = L.b2_off;
-        T.out_main = (L.w2_off >= 0) ? L.out - 1 : L.out;
+        T.out_main = L.out_main;
         k_pad = T.N_pad;
     }
     tc.bias_base = off;
@@ -84,7 +84,7 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
         for (int o = 0; o < L.out; ++o) {
             const bool vrow = (o >= out_main);                   // dueling value row
             for (int k = 0; k < L.in; ++k) {
-                const size_t pi = vrow ? (size_t)L.w2_off + k : (size_t)L.w_off + (size_t)o * L.in + k;
+                const size_t pi = vrow ? (size_t)L.w2_off + (size_t)(o - out_main) * L.in + k : (size_t)L.w_off + (size_t)o * L.in + k;
                 hi_map[pi] = elem(T.K_pad, T.hi_off, o, k);
                 lo_map[pi] = elem(T.K_pad, T.lo_off, o, k);
                 if (l > 0) {                                      // W^T: row k, column o
@@ -92,7 +92,7 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
                     lo2_map[pi] = elem(T.N_pad, T.t_lo_off, k, o);
                 }
             }
-            hi_map[vrow ? (size_t)L.b2_off : (size_t)L.b_off + o] = tc.bias_base / 4 + T.bias_off + o;
+            hi_map[vrow ? (size_t)L.b2_off + (o - out_main) : (size_t)L.b_off + o] = tc.bias_base / 4 + T.bias_off + o;
         }
     }
     (void)c;

@@ -40,8 +40,6 @@ struct TcDwArgs {
     float *partials;                   // [n_chunks][P]
 };
 
-static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
-
 // issue hi*hi + hi*lo + lo*hi over `ksteps` K-steps (single thread)
 __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                              uint32_t idesc, int ksteps)
@@ -415,8 +413,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
                 const int o = c0 + j;
                 if (o < T.N_real) {
                     const bool vrow = o >= T.out_main;                                   // dueling value head row
-                    if (f < T.K_real) part[vrow ? T.w2_off + f : T.w_off + o * T.K_real + f] = v[j];
-                    else part[vrow ? T.b2_off : T.b_off + o] = v[j];
+                    if (f < T.K_real) part[vrow ? T.w2_off + (o - T.out_main) * T.K_real + f : T.w_off + o * T.K_real + f] = v[j];
+                    else part[vrow ? T.b2_off + (o - T.out_main) : T.b_off + o] = v[j];
                 }
             }
         }

@@ -326,3 +326,78 @@ def train_profile(env, learner, n_iters, eps):
 def train_run_dp(env, learner, n_iters, eps, global_batch):
     """uavrl_train_run_dp: lockstep iterations whose update is the fused NVLink all-reduce + Adam."""
     check(_lib.lib().uavrl_train_run_dp(env.h, learner.h, int(n_iters), float(eps), int(global_batch), _stream(env.device)))
+
+
+class SacLearner:
+    """SAC continuous (the reference's shipped trainer, config/Trainer.xml) on one GPU."""
+    ROLES = ("actor", "critic_1", "critic_2", "target_critic_1", "target_critic_2")
+
+    def __init__(self, obs_dim=OBS_DIM, hidden=64, act_dim=2, action_bound=1.0, actor_lr=1e-4, critic_lr=1e-3, alpha_lr=1e-4,
+                 target_entropy=1.0, gamma=0.99, tau=0.05, batch_size=64, replay_capacity=10000, lockstep_envs=0, seed=42, device=0):
+        self.device = torch.device("cuda", device)
+        c = _lib.SacConfig(obs_dim, hidden, act_dim, action_bound, actor_lr, critic_lr, alpha_lr, target_entropy, gamma, tau,
+                           batch_size, replay_capacity, lockstep_envs, seed, device)
+        self.cfg = c
+        self.h = C.c_void_p()
+        check(_lib.lib().uavrl_sac_create(C.byref(c), C.byref(self.h)))
+        self.P = [int(_lib.lib().uavrl_sac_param_count(self.h, r)) for r in range(5)]
+
+    def close(self):
+        if self.h:
+            _lib.lib().uavrl_sac_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, role, flat):
+        flat = np.ascontiguousarray(flat, np.float32)
+        check(_lib.lib().uavrl_sac_set_params(self.h, role, _ptr(flat)))
+
+    def get_params(self, role):
+        n = self.P[role] if role < 5 else self.P[(role - 5) % 3]
+        out = np.zeros(n, np.float32)
+        check(_lib.lib().uavrl_sac_get_params(self.h, role, _ptr(out)))
+        return out
+
+    def init_params(self, seed=0):
+        """nn.Linear default init for actor and the two critics; targets copy the critics (SAC_Trainer.py:33-34)."""
+        g = torch.Generator().manual_seed(seed)
+        o, h, a = self.cfg.obs_dim, self.cfg.hidden, self.cfg.act_dim
+
+        def lin(out, fi):
+            b = 1.0 / np.sqrt(fi)
+            return [(torch.rand(out * fi, generator=g) * 2 - 1) * b, (torch.rand(out, generator=g) * 2 - 1) * b]
+        self.set_params(0, torch.cat(lin(h, o) + lin(a, h) + lin(a, h)).numpy())
+        for r in (1, 2):
+            flat = torch.cat(lin(h, o + a) + lin(h, h) + lin(a, h)).numpy()
+            self.set_params(r, flat); self.set_params(r + 2, flat)
+
+    def scalars(self):
+        la, m, v = C.c_float(), C.c_float(), C.c_float()
+        e, t = C.c_int64(), C.c_int64()
+        check(_lib.lib().uavrl_sac_get_scalars(self.h, C.byref(la), C.byref(m), C.byref(v), C.byref(e), C.byref(t)))
+        return dict(log_alpha=la.value, la_m=m.value, la_v=v.value, epoch=e.value, adam_step=t.value)
+
+    def set_scalars(self, log_alpha, la_m=0.0, la_v=0.0, epoch=0, adam_step=0):
+        check(_lib.lib().uavrl_sac_set_scalars(self.h, float(log_alpha), float(la_m), float(la_v), int(epoch), int(adam_step)))
+
+    def act(self, obs, eps=None):
+        n = obs.shape[0]
+        a = torch.empty((n, self.cfg.act_dim), dtype=torch.float32, device=self.device)
+        check(_lib.lib().uavrl_sac_act(self.h, _ptr(obs), n, _ptr(eps), _ptr(a), _stream(self.device)))
+        return a
+
+    def update_batch(self, s, a, r, s2, d, eps_next=None, eps_cur=None, losses=None):
+        check(_lib.lib().uavrl_sac_update_batch(self.h, s.shape[0], _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(d), _ptr(eps_next),
+                                                _ptr(eps_cur), _ptr(losses), _stream(self.device)))
+
+
+def sac_train_run(env, sac, n_iters, do_update=True, want_stats=True):
+    st = _lib.TrainStats()
+    check(_lib.lib().uavrl_sac_train_run(env.h, sac.h, int(n_iters), int(bool(do_update)), C.byref(st) if want_stats else None,
+                                         _stream(env.device)))
+    return st

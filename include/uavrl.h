@@ -41,7 +41,8 @@ typedef enum { UAVRL_INFO_NORMAL = 0, UAVRL_INFO_SUCCESS = 1, UAVRL_INFO_LOSE = 
 typedef enum {
     UAVRL_ACT_CONT_F32 = 0,          /* steering fraction a0 = action[0] in [-1,1]  (UAV.py:407,414) */
     UAVRL_ACT_CONT_F64 = 1,          /* same, double (exact replay of reference tapes) */
-    UAVRL_ACT_DISCRETE27 = 2         /* int32 k in 0..26: documented extension, see DESIGN.md */
+    UAVRL_ACT_DISCRETE27 = 2,        /* int32 k in 0..26: documented extension, see DESIGN.md */
+    UAVRL_ACT_CONT_F32X2 = 3         /* float [n][2] as SAC's get_action returns it; only action[0] steers (UAV.py:414) */
 } uavrl_action_kind;
 
 typedef enum { UAVRL_ALGO_DQN = 0, UAVRL_ALGO_DDQN = 1, UAVRL_ALGO_DUELING = 2 } uavrl_algo;
@@ -225,6 +226,44 @@ typedef struct {
 int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps,
                     int32_t updates_per_iter, int32_t do_update, uavrl_train_stats *stats_host,
                     void *stream);
+
+/* ------------------------------------------------------------------ SAC, continuous actions (BASELINE config 5)
+ * SAC_Trainer (Trainer/SAC_Trainer.py) with PolicyNetContinuous_SAC / QValueNetContinuous_SAC (BaseClass/BaseCNN.py:459-500):
+ * actor obs->hidden->{mu, sigma}, twin critics [obs, action]->hidden->hidden->action_dim, their targets, learnable log_alpha
+ * (init ln 0.01).  The reference's quirks are kept: [B, action_dim]-shaped critic outputs / TD target / losses and the
+ * doubly applied tanh in the log-prob correction. */
+typedef struct uavrl_sac uavrl_sac;
+typedef struct {
+    int32_t obs_dim, hidden, act_dim;     /* <w>, <hiden_dim>, <output>/<action_dim> of config/Trainer.xml: 100, 64, 2 */
+    float action_bound;                   /* <action_bound> */
+    float actor_lr, critic_lr, alpha_lr;  /* actor.lr, critic.lr, SAC_param.alpha_lr */
+    float target_entropy, gamma, tau;     /* SAC_param */
+    int32_t batch_size;                   /* Batch_Size */
+    int64_t replay_capacity;              /* replay_size */
+    int32_t lockstep_envs;                /* > 0: frame-ring replay fed by uavrl_sac_train_run */
+    uint64_t seed;
+    int32_t device;
+} uavrl_sac_config;
+
+int uavrl_sac_create(const uavrl_sac_config *cfg, uavrl_sac **out);
+int uavrl_sac_destroy(uavrl_sac *s);
+/* role: 0 actor, 1 critic_1, 2 critic_2, 3 target_critic_1, 4 target_critic_2 (flat state_dict order:
+ * actor = fc1, fc_mu, fc_std; critic = fc1, fc2, fc_out); 5..7 Adam exp_avg of actor/critic_1/critic_2, 8..10 exp_avg_sq */
+int64_t uavrl_sac_param_count(const uavrl_sac *s, int32_t role);
+int uavrl_sac_set_params(uavrl_sac *s, int32_t role, const float *params_host);
+int uavrl_sac_get_params(uavrl_sac *s, int32_t role, float *params_host);
+int uavrl_sac_set_scalars(uavrl_sac *s, float log_alpha, float la_exp_avg, float la_exp_avg_sq, int64_t epoch, int64_t adam_step);
+int uavrl_sac_get_scalars(uavrl_sac *s, float *log_alpha, float *la_exp_avg, float *la_exp_avg_sq, int64_t *epoch, int64_t *adam_step);
+/* SAC_Trainer.get_action (:444-448): actions_dev [n][2] = tanh(mu + sigma*eps)*bound; eps_dev [n][2] injects the
+ * reparameterisation noise (NULL = Philox Box-Muller) */
+int uavrl_sac_act(uavrl_sac *s, const float *obs_dev, int32_t n, const float *eps_dev, float *actions_dev, void *stream);
+/* SAC_Trainer.update (:317-379, continuous) on an explicit batch: s [B][obs], a [B][2], r [B], s2 [B][obs], d [B];
+ * eps_next / eps_cur [B][2] = noise of the two actor evaluations (NULL = Philox); losses_dev (optional) [4] =
+ * {actor_loss, critic_1_loss, critic_2_loss, d alpha_loss / d log_alpha}. */
+int uavrl_sac_update_batch(uavrl_sac *s, int32_t B, const float *s_dev, const float *a_dev, const float *r_dev, const float *s2_dev,
+                           const float *d_dev, const float *eps_next_dev, const float *eps_cur_dev, float *losses_dev, void *stream);
+/* PathPlan_City.run_thread_OffPolicy + update with the SAC trainer and the reference's continuous step, N envs in lockstep */
+int uavrl_sac_train_run(uavrl_env *env, uavrl_sac *s, int32_t n_iters, int32_t do_update, uavrl_train_stats *stats_host, void *stream);
 
 /* Data-parallel form of uavrl_train_run (after uavrl_learner_comm_connect): every iteration ends with
  * uavrl_learner_update_dp on this rank's replay shard; global_batch = batch_size x world. */
