@@ -160,15 +160,19 @@ class PathPlan_City_B200:
         many episodes ended as there are UAVs (every UAV finished one episode on average; finished UAVs
         restart from the scenario pool, which is the reference's per-episode UAV.reset())."""
         self.Reset_Result(eps_rate)
-        if not self.discrete:
-            raise ValueError("DQN-family trainers need update_function_name = update_PathPlan27")
         learner = self.Trainer._learner
+        is_sac = isinstance(learner, engine.SacLearner)
+        if is_sac == self.discrete:
+            raise ValueError("SAC needs update_function_name = update_PathPlan (continuous); the DQN family needs update_PathPlan27")
         t0 = time.time()
         ended = steps = updates = coll = n_s = n_l = 0
         reward_sum, loss, chunk, iters = 0.0, 0.0, 16, 0
         max_iters = 64 * self.uav_params.max_step
         while ended < self.num_UAV and iters < max_iters:
-            st = engine.train_run(self.batch, learner, chunk, eps_rate, 1, bool(self.Trainer.Is_Train))
+            if is_sac:
+                st = engine.sac_train_run(self.batch, learner, chunk, bool(self.Trainer.Is_Train))
+            else:
+                st = engine.train_run(self.batch, learner, chunk, eps_rate, 1, bool(self.Trainer.Is_Train))
             ended += st.episodes_ended; steps += st.env_steps; updates += st.updates; coll += st.collisions
             n_s += st.n_success; n_l += st.n_lose; reward_sum += st.sum_reward; loss = st.last_loss
             iters += chunk

@@ -118,3 +118,49 @@ def test_env_plugin_runs_an_episode_from_xml(tmp_path):
     s = env.states()
     ns, r, d, infos = env.Move_Agents(np.full(256, 13, np.int32))
     assert s.shape == ns.shape == (256, 100) and set(infos) <= {"normal", "success", "lose"}
+
+
+def test_sac_plugin_and_shipped_configuration(tmp_path):
+    """The configuration the reference ships (SAC_Trainer + continuous update_PathPlan, config/Trainer.xml + UAV.xml),
+    expressed with the B200 plug-ins: trainer API (get_action -> [a0, a1], update(transition_dict), save / Load_Mod in
+    the reference's <role>_SAC_<name>.pth files) and an episode of the env plug-in."""
+    import importlib
+    from uavrl_b200.plugins import xmlconfig
+    sac_golden = np.load(os.path.join(ROOT, "tests", "golden", "sac_golden.npz"))
+    tdict = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "Trainer_SAC_B200.xml"))["Trainer"]
+    tdict.update(name="UAV_0", model_path=str(tmp_path), Batch_Size="64", replay_size="4096")
+    mod = importlib.import_module("uavrl_b200.plugins.SAC_Trainer_B200")
+    tr = mod.SAC_Trainer_B200(tdict)
+    g = sac_golden
+    a = tr.get_action(g["sac_s"][0][0], 0.1)
+    assert isinstance(a, list) and len(a) == 2 and all(-1 < x < 1 for x in a)
+    td = {"states": g["sac_s"][0].tolist(), "actions": g["sac_a"][0].tolist(), "next_states": g["sac_s2"][0].tolist(),
+          "rewards": g["sac_r"][0].tolist(), "dones": g["sac_d"][0].tolist()}
+    res = tr.update(td)
+    assert res["sum_epoch"] == 1 and np.isfinite(float(res["loss"]))
+    assert tr.update({"states": [[]], "actions": [], "next_states": [], "rewards": [], "dones": []})["sum_epoch"] == 2
+    tr.save()
+    assert sorted(os.listdir(tmp_path)) == ["actor_SAC_UAV_0.pth", "critic_1_SAC_UAV_0.pth", "critic_2_SAC_UAV_0.pth"]
+    ck = torch.load(os.path.join(tmp_path, "critic_1_SAC_UAV_0.pth"), weights_only=False)
+    assert list(ck["model"]) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_out.weight", "fc_out.bias"]
+    assert ck["model"]["fc1.weight"].shape == (64, 102) and ck["model"]["fc_out.weight"].shape == (2, 64)   # the 2-wide critic
+    tr2 = mod.SAC_Trainer_B200(tdict)
+    for role in range(3):
+        assert np.array_equal(tr2._learner.get_params(role), tr._learner.get_params(role))
+        assert np.array_equal(tr2._learner.get_params(5 + role), tr._learner.get_params(5 + role))
+    assert tr2.epoch == 2
+    # env plug-in with the continuous step + SAC trainer
+    cwd = os.getcwd(); os.chdir(ROOT)
+    try:
+        env_dict = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "PathPlan_City_B200.xml"))["simulator"]["env"]
+        env_dict.update(num_UAV="128", scenario_pool="256")
+        env_dict["Agent"]["xml_path_agent"] = "./configs/UAV_continuous_B200.xml"
+        env_dict["Agent"]["Trainer"]["Trainer_path"] = "./configs/Trainer_SAC_B200.xml"
+        envmod = importlib.import_module("uavrl_b200.plugins.PathPlan_City_B200")
+        env = envmod.PathPlan_City_B200(env_dict)
+    finally:
+        os.chdir(cwd)
+    info = env.run_eposide(0.1)
+    assert info["episodes"] >= 128 and info["env_steps"] == 128 * info["step"] and np.isfinite(info["loss"])
+    ns, r, d, infos = env.Move_Agents(np.zeros(128, np.float32))
+    assert ns.shape == (128, 100)
