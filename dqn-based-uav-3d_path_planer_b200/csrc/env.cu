@@ -246,6 +246,16 @@ int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st)
 
 }  // namespace uavrl
 
+namespace uavrl {
+void free_pool(EnvDev &d)
+{
+    cudaFree((void *)d.pool_start); cudaFree((void *)d.pool_goal); cudaFree((void *)d.pool_v0);
+    cudaFree((void *)d.pool_sub); cudaFree((void *)d.pool_nsub); cudaFree((void *)d.pool_alias);
+    d.pool_start = d.pool_goal = d.pool_v0 = d.pool_sub = nullptr;
+    d.pool_nsub = nullptr; d.pool_alias = nullptr;
+}
+}  // namespace uavrl
+
 using namespace uavrl;
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -308,13 +318,6 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
     return 0;
 }
 
-static void free_pool(EnvDev &d)
-{
-    cudaFree((void *)d.pool_start); cudaFree((void *)d.pool_goal); cudaFree((void *)d.pool_v0);
-    cudaFree((void *)d.pool_sub); cudaFree((void *)d.pool_nsub); cudaFree((void *)d.pool_alias);
-    d.pool_start = d.pool_goal = d.pool_v0 = d.pool_sub = nullptr;
-    d.pool_nsub = nullptr; d.pool_alias = nullptr;
-}
 
 int uavrl_env_destroy(uavrl_env *env)
 {

@@ -50,4 +50,5 @@ namespace uavrl {
 int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st);
 int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st);
+void free_pool(EnvDev &d);            // scenario.cu replaces the pool with a device-generated one
 }  // namespace uavrl

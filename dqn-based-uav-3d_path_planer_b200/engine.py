@@ -95,6 +95,18 @@ class EnvBatch:
                                             _ptr(n_sub), _ptr(al)))
         self.pool_size = P
 
+    def generate_pool(self, n, seed=42, rrt_step=30):
+        """Reset draws + RRT on the device, straight into the env's pool (same scenarios as make_scenarios + set_pool)."""
+        check(_lib.lib().uavrl_env_generate_pool(self.h, int(n), C.c_uint64(seed), int(rrt_step), _stream(self.device)))
+        self.pool_size = int(n)
+
+    def get_pool(self):
+        P = self.pool_size
+        start = np.zeros((P, 3)); goal = np.zeros((P, 3)); v0 = np.zeros((P, 3))
+        sub = np.zeros((P, self.K, 3)); n_sub = np.zeros(P, np.int32)
+        check(_lib.lib().uavrl_env_get_pool(self.h, _ptr(start), _ptr(goal), _ptr(v0), _ptr(sub), _ptr(n_sub)))
+        return dict(start=start, goal=goal, v0=v0, sub=sub, n_sub=n_sub)
+
     def reset(self, first_scenario=0):
         check(_lib.lib().uavrl_env_reset(self.h, int(first_scenario), _stream(self.device)))
 

@@ -88,6 +88,15 @@ int uavrl_make_scenarios(const uavrl_env_config *cfg, uint64_t seed, int32_t n_s
                          int32_t rrt_step, double *start_host, double *goal_host,
                          double *heading_host, double *subgoals_host, int32_t *n_sub_host);
 
+/* The same generator as a device kernel (one thread per scenario): fills the env's device pool
+ * directly -- replaces uavrl_make_scenarios + uavrl_env_set_pool, bit-identical scenarios for the same
+ * (seed, index); replaces UAV.reset (UAV.py:335-366) + RRTPlanner.getPath (PathPlan/RRT.py:63-105) for the pool.
+ * Synchronises `stream`.  uavrl_env_get_pool copies the current pool back (any pointer may be NULL):
+ * start[P][3], goal[P][3], v0[P][3] = (Vx, Vy, |V|), subgoals[P][K][3], n_sub[P]. */
+int uavrl_env_generate_pool(uavrl_env *env, int32_t n_scenarios, uint64_t seed, int32_t rrt_step, void *stream);
+int uavrl_env_get_pool(uavrl_env *env, double *start_host, double *goal_host, double *v0_host,
+                       double *subgoals_host, int32_t *n_sub_host);
+
 /* UAV.state() -> state_PathPlan (UAV.py:515-567): obs_dev [n_envs][100] float32. */
 int uavrl_env_observe(uavrl_env *env, float *obs_dev, void *stream);
 

@@ -86,3 +86,34 @@ def test_host_scenario_generator(env_golden):
         assert (seg <= 30 + 1e-9).all()                                                          # steer(), step 30
         assert city.threaten_rate(sub[s, :k]).sum() == 0                                         # nodes are collision free
     assert 8 <= np.median(n_sub) <= 40
+
+
+def test_scenario_generator_matches_reference_statistics(env_golden):
+    """Statistical pin of rrt_core.cuh against 400 resets of the reference's own UAV.reset -> RRT
+    (tests/golden/rrt_golden.npz): sub-goal counts, chain length and detour ratio follow the same distributions
+    (two-sample Kolmogorov-Smirnov), segment lengths never exceed the RRT step."""
+    from scipy import stats
+    g = env_golden
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "rrt_golden.npz"))
+    cfg = _lib.EnvConfig()
+    b = np.ascontiguousarray(g["buildings"])
+    cfg.n_envs, cfg.max_subgoals = 1, 64
+    cfg.len, cfg.width, cfg.h = g["dims"]
+    cfg.max_v, cfg.min_v, cfg.steering_angle, cfg.max_step = g["uav_params"][0], g["uav_params"][1], g["uav_params"][2], 150
+    cfg.n_buildings, cfg.buildings_host = b.shape[0], b.ctypes.data_as(C.POINTER(C.c_double))
+    P, K = 2000, 64
+    start = np.zeros((P, 3)); goal = np.zeros((P, 3)); heading = np.zeros(P); sub = np.zeros((P, K, 3))
+    n_sub = np.zeros(P, np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert _lib.lib().uavrl_make_scenarios(C.byref(cfg), 99, P, 30, vp(start), vp(goal), vp(heading), vp(sub), vp(n_sub)) == 0
+    chain = np.zeros(P); seg_max = np.zeros(P)
+    for s in range(P):
+        seg = np.linalg.norm(np.diff(sub[s, :n_sub[s]], axis=0), axis=1)
+        chain[s], seg_max[s] = seg.sum(), seg.max()
+    straight = np.linalg.norm(goal - start, axis=1)
+    assert seg_max.max() <= 30 + 1e-9 and ref["seg_max"].max() <= 30 + 1e-9
+    for ours, theirs, what in ((n_sub, ref["n_sub"], "n_sub"), (chain, ref["chain"], "chain length"),
+                               (chain / straight, ref["chain"] / ref["straight"], "detour ratio"),
+                               (start[:, 0], ref["start"][:, 0], "start x"), (goal[:, 1], ref["goal"][:, 1], "goal y")):
+        p = stats.ks_2samp(ours, theirs).pvalue
+        assert p > 1e-3, "%s: KS p=%.2e (ours mean %.3f, reference mean %.3f)" % (what, p, np.mean(ours), np.mean(theirs))

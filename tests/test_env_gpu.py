@@ -197,3 +197,38 @@ def test_full_size_invariants_65536(env_golden, env27_golden):
         digests.append((tot_r, float(obs.double().sum()), st["px"].sum()))
     assert digests[0] == digests[1]
     env.close()
+
+
+def test_device_pool_generator_equals_host_generator(env_golden, env27_golden):
+    """uavrl_env_generate_pool (one GPU thread per scenario: reset draws + RRT) writes the SAME pool as the
+    host generator + uavrl_env_set_pool for the same seed -- every start / goal / sub-goal bit-for-bit -- and envs
+    stepped from it follow the same trajectories."""
+    import time
+    from uavrl_b200 import engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    N, P, K = 512, 1024, 64
+    a = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    b = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    sc = a.make_scenarios(P, seed=31)
+    a.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    b.generate_pool(P, seed=31)
+    pa, pb = a.get_pool(), b.get_pool()
+    for k in ("start", "goal", "sub", "n_sub"):
+        assert np.array_equal(pa[k], pb[k]), k
+        assert np.array_equal(pb[k], sc[k]), k
+    np.testing.assert_allclose(pb["v0"], pa["v0"], rtol=0, atol=4e-16)      # cos/sin: CUDA libm vs glibc
+    assert (pb["n_sub"] >= 2).all() and (pb["n_sub"] <= K).all()
+    a.reset(0); b.reset(0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(200):
+        act = torch.randint(0, 27, (N,), generator=g, device="cuda", dtype=torch.int32)
+        oa, ob = a.step(act), b.step(act)
+        for k in ("done", "info", "collision", "ended"):
+            assert torch.equal(oa[k], ob[k]), (k, t)
+        assert torch.allclose(oa["obs"], ob["obs"], rtol=0, atol=1e-6)
+    # throughput of the generator itself, device vs host threads (printed with -s)
+    t0 = time.perf_counter(); b.generate_pool(8192, seed=5); t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter(); a.make_scenarios(8192, seed=5); t_host = time.perf_counter() - t0
+    print("\npool of 8192 scenarios: device %.1f ms, host threads %.1f ms" % (1e3 * t_dev, 1e3 * t_host))
+    assert np.array_equal(b.get_pool()["n_sub"], a.make_scenarios(8192, seed=5)["n_sub"])
+    a.close(); b.close()
