@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--tc", type=int, default=1, help="1 = tcgen05 3xTF32 tensor-core path for the Q-network (default), 0 = fp32 CUDA cores")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
+    ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -232,6 +233,7 @@ def run_ours(a):
             os.dup2(saved, 1)
             os.close(saved)
 
+    _lib.lib().uavrl_set_pdl(int(a.pdl))
     dims, b, p = load_city()
     city = engine.City(dims[0], dims[1], dims[2], b)
     params = engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
@@ -305,7 +307,8 @@ def run_ours(a):
                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64 env state / f32 obs+learner", "data": "synthetic",
-               "config": dict(config_dict(a, world), qnet_path=("tcgen05 3xTF32 (fp32-grade)" if tc_on else "fp32 CUDA cores")),
+               "config": dict(config_dict(a, world), qnet_path=("tcgen05 3xTF32 (fp32-grade)" if tc_on else "fp32 CUDA cores"),
+                              launch="programmatic dependent launch" if a.pdl else "serialised"),
                "clocks": clocks, "gpu_launches": int(launches),
                "host_wall_ms_per_step": 1e3 * t_wall / a.steps}
 

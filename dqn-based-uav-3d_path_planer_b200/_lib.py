@@ -70,6 +70,7 @@ SIGNATURES = {
     "uavrl_env_set_pool": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP]),
     "uavrl_env_reset": (C.c_int, [VP, C.c_int32, VP]),
     "uavrl_make_scenarios": (C.c_int, [C.POINTER(EnvConfig), C.c_uint64, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
+    "uavrl_set_pdl": (C.c_int, [C.c_int32]),
     "uavrl_env_generate_pool": (C.c_int, [VP, C.c_int32, C.c_uint64, C.c_int32, VP]),
     "uavrl_env_get_pool": (C.c_int, [VP, VP, VP, VP, VP, VP]),
     "uavrl_env_observe": (C.c_int, [VP, VP, VP]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 #include <string>
 
@@ -35,6 +36,40 @@ inline int fail(int code, const std::string &msg)
         ::uavrl::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
         UAVRL_CUDA(cudaGetLastError());                                                       \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// Inside the lockstep loops every kernel depends on its predecessor, so each kernel boundary would cost a full
+// drain + launch + prologue.  Kernels of the loop are launched with programmaticStreamSerialization: a CTA of
+// kernel k+1 may start while kernel k is still running, does what does not depend on k (TMEM allocation, mbarrier
+// init, TMA of weights / loads of state last written >= 2 kernels back) and then blocks in griddepcontrol.wait
+// until k has completed and its writes are visible.  Every loop kernel triggers its dependents right after its own
+// wait, so kernel k+1 only ever overlaps kernel k (everything <= k-1 is complete when k+1's prologue runs).
+// Launched without the attribute, both instructions are no-ops.
+extern std::atomic<int> g_pdl;            // uavrl_set_pdl(); default on
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
+// which loop kernel was launched last on the learner's stream (decides what a prologue may touch before its wait)
+enum PdlPrev { kPdlNone = 0, kPdlAct, kPdlEnv, kPdlTd, kPdlTrain, kPdlDw, kPdlAdam };
+// TcArgs.pdl / kernel flags
+constexpr int kPdlOn = 1, kPdlEarlyWeights = 2, kPdlEarlyRows = 4;
 
 template <class T>
 inline int dev_alloc(T **p, size_t n)

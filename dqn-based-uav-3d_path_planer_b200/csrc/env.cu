@@ -29,6 +29,7 @@ namespace uavrl {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_pdl{1};
 
 __device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
 {
@@ -85,6 +86,10 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
     for (int i = tid; i < d.k.n_cyl * 6; i += kEnvThreads)
         reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
     __syncthreads();
+    // PDL: the predecessor in the lockstep loops is the act kernel, which only writes `actions`; per-env state and
+    // the pool were last written by the previous env step.  Warp 0 loads its state first and waits just before it
+    // reads the action; the other warps have nothing to do until phase 2.
+    if (tid >= 32) { pdl_wait(); pdl_trigger(); }
 
     if (tid < 32) {
         const int e = e0 + tid;
@@ -104,6 +109,8 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
             int scen = d.scen[e];
             mask = cull_mask(d, s_cyl, s.px, s.py);
             if (DO_STEP) {
+                pdl_wait();
+                pdl_trigger();
                 double act;
                 if (action_kind == UAVRL_ACT_CONT_F32) act = (double)static_cast<const float *>(actions)[e];
                 else if (action_kind == UAVRL_ACT_CONT_F64) act = static_cast<const double *>(actions)[e];
@@ -223,14 +230,16 @@ __global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, u
 }
 
 int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
-                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st)
+                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st, bool pdl)
 {
     if (d.n <= kSmallBatchEnvs) {
         const int blocks = (d.n + kEnvsPerBlockSmall - 1) / kEnvsPerBlockSmall;
-        env_kernel<true, kEnvsPerBlockSmall><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+        UAVRL_CUDA(launch_kernel(env_kernel<true, kEnvsPerBlockSmall>, dim3(blocks), dim3(kEnvThreads), 0, st, pdl, d, action_kind, actions, obs,
+                                 reward, done, info, coll, ended));
     } else {
         const int blocks = (d.n + kEnvsPerBlockLarge - 1) / kEnvsPerBlockLarge;
-        env_kernel<true, kEnvsPerBlockLarge><<<blocks, kEnvThreads, 0, st>>>(d, action_kind, actions, obs, reward, done, info, coll, ended);
+        UAVRL_CUDA(launch_kernel(env_kernel<true, kEnvsPerBlockLarge>, dim3(blocks), dim3(kEnvThreads), 0, st, pdl, d, action_kind, actions, obs,
+                                 reward, done, info, coll, ended));
     }
     UAVRL_LAUNCHED();
     return 0;
@@ -262,6 +271,7 @@ using namespace uavrl;
 extern "C" {
 
 const char *uavrl_last_error(void) { return g_last_error.c_str(); }
+int uavrl_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0); return 0; }
 const char *uavrl_version(void) { return "uavrl-b200 0.1 (sm_100a)"; }
 int64_t uavrl_launch_count(void) { return (int64_t)g_launches.load(); }
 

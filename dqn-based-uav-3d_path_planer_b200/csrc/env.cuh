@@ -48,7 +48,7 @@ struct uavrl_env {
 namespace uavrl {
 // launched by env.cu and by the fused training loop (train.cu)
 int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
-                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st);
+                    uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st, bool pdl = false);
 int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st);
 void free_pool(EnvDev &d);            // scenario.cu replaces the pool with a device-generated one
 }  // namespace uavrl

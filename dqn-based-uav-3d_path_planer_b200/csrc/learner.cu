@@ -275,6 +275,8 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
+    pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
+    pdl_trigger();
     float g = 0.f;
     if (i < a.P && a.nparts > 0) {
         // 4 groups x 8 independent loads in flight per thread: the partials are L2 resident, latency bound
@@ -494,6 +496,7 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
     act_kernel<<<grid, kNetThreads, act_smem_bytes(l->net), st>>>(l->net, l->img_local, obs, n, eps, is_train, u_tape,
                                                                 rand_tape, l->cfg.seed ^ 0xAC7ull, l->act_calls++,
                                                                 actions, nullptr, q_out, n_tiles);
+    l->pdl_prev = kPdlNone;
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -567,6 +570,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     ua.inv_global_b = 1.0f / (float)global_batch;
     ua.y_in = y_in;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
+    l->pdl_prev = kPdlNone;
     UAVRL_LAUNCHED();
     if (mid) UAVRL_CUDA(cudaEventRecord(mid[1], st));
     }
@@ -574,7 +578,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     l->last_nparts = nparts;
     l->last_n_loss_parts = n_loss_parts;
     l->last_global_batch = global_batch;
-    if (partials_only) return 0;
+    if (partials_only) { l->pdl_prev = kPdlNone; return 0; }     // the data-parallel pair that follows is launched plainly
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = l->net.P; a.nparts = nparts; a.n_loss_parts = n_loss_parts; a.apply = apply ? 1 : 0; a.world = l->world;
@@ -588,10 +592,12 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
         a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
         a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
     }
-    reduce_adam_kernel<<<(a.P + 63) / 64, 256, 0, st>>>(a, l->partials, l->loss_partials, l->grad, l->local, l->m, l->v,
-                                                       l->target, l->img_local, l->img_target, l->img_map,
-                                                       (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map,
-                                                       l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev);
+    const bool chain = l->pdl_chain && g_pdl.load();
+    UAVRL_CUDA(launch_kernel(reduce_adam_kernel, dim3((a.P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw && !mid, a,
+                             l->partials, l->loss_partials, l->grad, l->local, l->m, l->v, l->target, l->img_local, l->img_target,
+                             l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map,
+                             l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev));
+    l->pdl_prev = chain ? kPdlAdam : kPdlNone;
     UAVRL_LAUNCHED();
     return 0;
 }

@@ -115,6 +115,9 @@ struct uavrl_learner {
     int64_t head = 0;                 // paired: next slot to write ; lockstep: frame holding obs_t
     int64_t count = 0;                // valid transitions
     bool frame0_valid = false;
+    // programmatic dependent launch chain of the lockstep loops (common.cuh)
+    bool pdl_chain = false;
+    int pdl_prev = 0;
     uint64_t act_calls = 0;
     // data-parallel: one-shot NVLink all-reduce fused with Adam (symmetric buffers exchanged through CUDA IPC)
     int32_t rank = 0, world = 1;

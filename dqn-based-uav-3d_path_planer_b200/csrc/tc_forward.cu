@@ -121,7 +121,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     TC_TRACE(1);
-    if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    // PDL prologue (common.cuh): the weight image may be fetched before the wait when the predecessor does not write
+    // it (TD passes after the env step); the first tile's rows may be gathered before the wait when the predecessor
+    // does not write them (act after the optimiser kernel: observations were written two kernels back).
+    const bool early_w = (a.pdl & kPdlEarlyWeights) != 0;
+    bool waited = (a.pdl & kPdlEarlyRows) == 0;
+    if (tid == 0 && early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    if (waited) {
+        pdl_wait();
+        pdl_trigger();
+        if (tid == 0 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     uint32_t pkey[4];
@@ -179,6 +189,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             }
         }
         TC_TRACE(2);
+        if (!waited) {
+            pdl_wait();
+            pdl_trigger();
+            waited = true;
+            if (tid == 0 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+        }
         if (!wready) { mbar_wait(&wbar, 0); wready = true; }
         TC_TRACE(3);
         fence_proxy_async();
@@ -314,7 +330,20 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 32 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 32 * sizeof(long long))); a.trace = tr; }
-    tc_forward_kernel<<<grid, kTcThreads, tc_smem_bytes(l->tc), st>>>(l->tc, a);
+    // PDL chain state (see common.cuh): what this kernel may touch before its griddepcontrol.wait
+    const int prev = (l->pdl_chain && g_pdl.load()) ? l->pdl_prev : kPdlNone;
+    a.pdl = 0;
+    if (prev != kPdlNone) {
+        a.pdl = kPdlOn;
+        if (a.mode == kTcAct) {
+            if (prev == kPdlAdam) a.pdl |= kPdlEarlyRows;          // obs frame written by the env step, weights by Adam
+            else if (prev == kPdlEnv) a.pdl |= kPdlEarlyWeights;   // collection-only loop: weights untouched, obs just written
+        } else if (prev == kPdlEnv || prev == kPdlTd) {
+            a.pdl |= kPdlEarlyWeights;                             // neither the env step nor a TD pass writes weight images
+        }
+    }
+    UAVRL_CUDA(launch_kernel(tc_forward_kernel, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a));
+    l->pdl_prev = l->pdl_chain ? (a.mode == kTcAct ? kPdlAct : kPdlTd) : kPdlNone;
     UAVRL_LAUNCHED();
     if (trace_on) {
         long long h[32];

@@ -23,6 +23,7 @@ struct TcArgs {
     float *q_out;                      // optional [n][A]
     float *y_out;                      // TD modes: y[b] = r + gamma * next_q * (1 - d)
     float gamma;
+    int32_t pdl;                       // kPdlOn | kPdlEarlyWeights | kPdlEarlyRows (set by launch_tc_forward)
     long long *trace;                  // debug: CTA 0 / thread 0 writes clock64() at stage boundaries (UAVRL_TC_TRACE=1)
 };
 

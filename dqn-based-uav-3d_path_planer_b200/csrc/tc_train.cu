@@ -106,7 +106,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    // PDL: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
+    // precedes this kernel), so it is fetched before the wait; y and the sampled rows come after it
     if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar); }
+    pdl_wait();
+    pdl_trigger();
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     uint32_t pkey[4];
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
         }
         rows[tid] = p;
     }
+    pdl_wait();                 // activations / dZ of the training chain (the predecessor) are read from here on
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -467,14 +473,19 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     a.R = (B >= 64 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
     a.n_tiles = (B + a.R - 1) / a.R;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
-    tc_train_kernel<<<grid, kTcThreads, train_smem_bytes(tc, a.R), st>>>(tc, a);
+    const bool chain = l->pdl_chain && g_pdl.load();
+    UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st,
+                             chain && l->pdl_prev == kPdlTd, tc, a));
+    l->pdl_prev = chain ? kPdlTrain : kPdlNone;
     UAVRL_LAUNCHED();
     if (after_chain) UAVRL_CUDA(cudaEventRecord(after_chain, st));
     TcDwArgs d;
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
     d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
-    tc_dw_kernel<<<d.n_chunks * tc.n_layers, kTcThreads, dw_smem_bytes(tc), st>>>(tc, d);
+    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
+                             chain && !after_chain, tc, d));
+    l->pdl_prev = chain ? kPdlDw : kPdlNone;
     UAVRL_LAUNCHED();
     *n_grad_parts = d.n_chunks;
     *n_loss_parts = grid;

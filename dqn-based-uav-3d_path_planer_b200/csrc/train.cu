@@ -32,6 +32,8 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
         UAVRL_CUDA(cudaMemcpy(&r0, env->d.stat_reward, sizeof(r0), cudaMemcpyDeviceToHost));
     }
     int64_t updates = 0;
+    l->pdl_chain = true; l->pdl_prev = kPdlNone;          // the first kernel of the loop is launched plainly
+    struct ChainOff { uavrl_learner *l; ~ChainOff() { l->pdl_chain = false; l->pdl_prev = kPdlNone; } } chain_off{ l };
     for (int it = 0; it < n_iters; ++it) {
         float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
         lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
@@ -42,7 +44,9 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
         // Choose_Action2 -> Trainer.get_action (PathPlan_City.py:338-346)
         if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
         // Move_Agent + replay add (PathPlan_City.py:371-382): reward/done land in the ring slots
-        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
+                                  l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
+        l->pdl_prev = kPdlEnv;
         lockstep_commit(l);
         if (do_update) {
             for (int u = 0; u < updates_per_iter; ++u) {  // PathPlan_City.update -> Trainer.update (:757-776)
@@ -82,6 +86,8 @@ extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_it
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    l->pdl_chain = true; l->pdl_prev = kPdlNone;
+    struct ChainOff { uavrl_learner *l; ~ChainOff() { l->pdl_chain = false; l->pdl_prev = kPdlNone; } } chain_off{ l };
     for (int it = 0; it < n_iters; ++it) {
         float *obs_t, *obs_next, *rew; int32_t *act; uint8_t *done;
         lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
@@ -90,7 +96,9 @@ extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_it
             l->frame0_valid = true;
         }
         if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
-        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
+                                  l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
+        l->pdl_prev = kPdlEnv;
         lockstep_commit(l);
         l->epoch += 1;
         // every rank must take part in every all-reduce: the caller warms the replay up first

@@ -288,6 +288,9 @@ const char *uavrl_last_error(void);
 const char *uavrl_version(void);
 /* number of kernel launches issued by this library in the calling process since load (bench.py) */
 int64_t uavrl_launch_count(void);
+/* Programmatic dependent launch inside the lockstep loops (each kernel's prologue overlaps its predecessor's
+ * tail; results are unchanged).  Process-wide switch, default 1; 0 launches every kernel fully serialised. */
+int uavrl_set_pdl(int32_t on);
 
 #ifdef __cplusplus
 }

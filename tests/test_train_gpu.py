@@ -71,3 +71,39 @@ def test_training_loop_learns_and_counts(env_golden, env27_golden):
     # ring wrapped (200 iterations through 65 frames) and stayed consistent
     assert L.replay_size() == N * 64
     env.close(); L.close()
+
+
+@pytest.mark.parametrize("algo", ["dqn", "ddqn"])
+def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo):
+    """Programmatic dependent launch inside the loop (kernel k+1's prologue overlaps kernel k's tail,
+    uavrl_set_pdl) is a scheduling change only: 150 lockstep iterations with it on and off end in bit-identical
+    parameters, replay contents, env state and counters."""
+    from uavrl_b200 import _lib, engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    N = 1024
+    out = []
+    try:
+        for pdl in (1, 0):
+            _lib.lib().uavrl_set_pdl(pdl)
+            env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
+            sc = env.make_scenarios(1024, seed=8)
+            env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+            env.reset(0)
+            L = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DQN if algo == "dqn" else engine.ALGO_DDQN,
+                               batch_size=N, replay_capacity=N * 32, lockstep_envs=N, seed=1, update_loop=3)
+            L.init_params(0)
+            engine.train_run(env, L, 8, eps=1.0, do_update=False)            # collection-only chain: act -> env -> act
+            st = engine.train_run(env, L, 150, eps=0.2)
+            torch.cuda.synchronize()
+            s, a, r, s2, d = L.gather(np.arange(L.replay_size()))
+            es = env.get_state()
+            out.append(dict(p=L.get_params(0), t=L.get_params(1), s=s, a=a, r=r, d=d, px=es["px"], step=es["step"],
+                            stats=(st.env_steps, st.updates, st.episodes_ended, st.collisions, st.n_success, st.n_lose,
+                                   st.sum_reward, st.last_loss)))
+            env.close(); L.close()
+    finally:
+        _lib.lib().uavrl_set_pdl(1)
+    a, b = out
+    assert a["stats"] == b["stats"] and a["stats"][1] == 150
+    for k in ("p", "t", "s", "a", "r", "d", "px", "step"):
+        assert np.array_equal(a[k], b[k]), k
