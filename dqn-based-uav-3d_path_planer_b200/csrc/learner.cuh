@@ -70,6 +70,8 @@ struct TcNet {
     int32_t a_bytes;                   // bytes of ONE A-operand buffer (hi or lo): 128 rows x max K_pad
     int32_t max_k;                     // max K_pad over layers
     int32_t act_stride, dz_stride;     // floats per sample in the activation / derivative scratch
+    int32_t concat;                    // 1: [B_hi ; B_lo] concatenated products (umma.cuh issue_3xtf32), 0: three passes
+    int32_t dstride, tmem_cols;        // TMEM columns per accumulator buffer (two buffers alternate between layers) / allocated
     TcLayer L[kMaxLayers];
 };
 

@@ -62,6 +62,15 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
     tc.train_img_bytes = rup(toff, 16);
     tc.a_bytes = (int)umma_tile_bytes(kTcTile, maxK);
     tc.max_k = maxK;
+    {   // accumulator columns: N_pad per product block; the concatenated scheme keeps hi*hi+lo*hi and hi*lo side by side
+        static const bool three_pass = getenv("UAVRL_TC_3PASS") != nullptr;
+        int maxN = 32;
+        for (int l = 0; l < net.n_layers; ++l) if (tc.L[l].N_pad > maxN) maxN = tc.L[l].N_pad;
+        tc.concat = three_pass ? 0 : 1;
+        const int need = (tc.concat ? 2 : 1) * maxN;
+        tc.dstride = need <= 64 ? 64 : need <= 128 ? 128 : 256;
+        tc.tmem_cols = 2 * tc.dstride;
+    }
     // per-sample scratch: act = inputs of layers 1.. (K_pad each), dz = output derivatives of every layer (N_pad each)
     int ao = 0, dzo = 0;
     for (int l = 0; l < net.n_layers; ++l) {
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     __shared__ float s_rew[kTcTile], s_done[kTcTile];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols);
     if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); }
     tc_fence_before();
     __syncthreads();
@@ -206,23 +215,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
         for (int l = 0; l < tc.n_layers; ++l) {
             const TcLayer T = tc.L[l];
             const uint32_t sbo = umma_sbo(T.K_pad);
-            const uint32_t dcol = (uint32_t)(l & 1) * 128u;
+            const uint32_t dcol = (uint32_t)(l & 1) * (uint32_t)tc.dstride;
+            const uint32_t second = tc.concat ? (uint32_t)T.N_pad : 0u;       // column offset of the hi*lo block
             if (tid == 0) {
-                // one thread issues 3 x K/8 MMAs.  Descriptors differ only in the 14-bit start-address field:
+                // one thread issues the layer's MMAs.  Descriptors differ only in the 14-bit start-address field:
                 // the next K step (two 16-byte chunks = 2*LBO bytes) is +16 in units of 16 B.
-                const uint32_t idesc = umma_idesc_tf32(kTcTile, T.N_pad);
-                const uint64_t a_hi = umma_desc(smem_u32(Ahi), sbo), a_lo = umma_desc(smem_u32(Alo), sbo);
-                const uint64_t b_hi = umma_desc(smem_u32(W + T.hi_off), sbo), b_lo = umma_desc(smem_u32(W + T.lo_off), sbo);
-                const uint32_t d = tmem + dcol;
-                const int ksteps = T.K_pad / 8;
-                constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
-                uint64_t da = a_hi, db = b_hi;
-                umma_tf32(d, da, db, idesc, 0u);                                   // hi * hi (first MMA overwrites D)
-                for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
-                da = a_hi; db = b_lo;
-                for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }   // hi * lo
-                da = a_lo; db = b_hi;
-                for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }   // lo * hi
+                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                             T.K_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             TC_TRACE(5 + 3 * l);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);
+                    tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 h, lo4;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 // head epilogue: Q row of this sample, then the mode's output
                 if (half == 0 && live) {
                     float q[32];
-                    tmem_ld32(taddr, q);
+                    tmem_ld32_sum(taddr, second, q);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     TC_TRACE(20);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
     TC_TRACE(21);
 }
 

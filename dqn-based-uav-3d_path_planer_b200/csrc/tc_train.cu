@@ -40,20 +40,6 @@ struct TcDwArgs {
     float *partials;                   // [n_chunks][P]
 };
 
-// issue hi*hi + hi*lo + lo*hi over `ksteps` K-steps (single thread)
-__device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                             uint32_t idesc, int ksteps)
-{
-    constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
-    uint64_t da = a_hi, db = b_hi;
-    umma_tf32(d, da, db, idesc, 0u);
-    for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
-    da = a_hi; db = b_lo;
-    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
-    da = a_lo; db = b_hi;
-    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
-}
-
 // Gather R rows (pointers in rows[]) into the layer-0 A operand.  All of a thread's loads are issued before any
 // is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.
 __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo)
@@ -100,17 +86,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __shared__ float s_loss;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols);
     if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); s_loss = 0.f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     // PDL: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
-    // precedes this kernel), so it is fetched before the wait; y and the sampled rows come after it
+    // precedes this kernel), so it is fetched before the wait, and so are the first tile's sampled rows and actions
+    // (replay frames / actions were written by the env step and the act kernel, also >= 2 back); only y is the
+    // predecessor's output
     if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar); }
-    pdl_wait();
-    pdl_trigger();
+    bool waited = false;
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     uint32_t pkey[4];
@@ -125,15 +112,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         const int base = tile * R;
         if (tid < R) {
             const int b = base + tid;
-            const float *p = nullptr; int act = 0; float y = 0.f;
+            const float *p = nullptr; int act = 0;
             if (b < a.B) {
                 const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
-                p = t.s; act = t.a; y = a.y[b];
+                p = t.s; act = t.a;
             }
-            rows[tid] = p; s_act[tid] = act; s_y[tid] = y;
+            rows[tid] = p; s_act[tid] = act;
         }
         __syncthreads();
         build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
+        if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
+        if (tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
         if (!wready) { mbar_wait(&wbar, 0); wready = true; }
         fence_proxy_async();
         tc_fence_before();
@@ -146,11 +135,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         for (int l = 0; l < nl; ++l) {
             const TcLayer T = tc.L[l];
             const uint32_t sbo = umma_sbo(T.K_pad);
-            const uint32_t dcol = (uint32_t)(l & 1) * 128u;
+            const uint32_t dcol = (uint32_t)(l & 1) * (uint32_t)tc.dstride;
+            const uint32_t second = tc.concat ? (uint32_t)T.N_pad : 0u;
             if (tid == 0) {
                 issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo),
-                             umma_idesc_tf32(kTcTile, T.N_pad), T.K_pad / 8);
+                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                             T.K_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             mbar_wait(&mbar, mphase);
@@ -163,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 float *act_row = a.act_buf + (size_t)gb * tc.act_stride + tc.L[l + 1].act_off;
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);
+                    tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 x, h, lo4;
@@ -181,7 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 if (half == 0 && live) {
                     float q[32];
-                    tmem_ld32(taddr, q);
+                    tmem_ld32_sum(taddr, second, q);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -234,11 +224,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         for (int l = nl - 1; l >= 1; --l) {
             const TcLayer T = tc.L[l];
             const uint32_t sbo = umma_sbo(T.N_pad);             // reduction runs over this layer's outputs
-            const uint32_t dcol = (uint32_t)((l + 1) & 1) * 128u;       // the head used (nl-1)&1: alternate from there
+            const uint32_t dcol = (uint32_t)((l + 1) & 1) * (uint32_t)tc.dstride;     // the head used (nl-1)&1: alternate from there
+            const uint32_t second = tc.concat ? (uint32_t)T.K_pad : 0u;
             if (tid == 0) {
                 issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                             umma_desc(smem_u32(W + T.t_hi_off), sbo), umma_desc(smem_u32(W + T.t_lo_off), sbo),
-                             umma_idesc_tf32(kTcTile, T.K_pad), T.N_pad / 8);
+                             umma_desc(smem_u32(W + T.t_hi_off), sbo), umma_desc(smem_u32(W + T.t_lo_off), sbo), kTcTile, T.K_pad,
+                             T.N_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             // H_l (this layer's input, written by the forward epilogue of the same thread) is needed for ReLU':
@@ -265,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 const int c0 = half * 32 + cc * 64;
                 if (!(live && c0 < T.K_pad)) continue;
                 float v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
+                tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 hh = hpre[cc][j];
@@ -290,7 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     if (tid == 0) a.loss_partials[blockIdx.x] = s_loss;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
 }
 
 // ------------------------------------------------------------------ split-K weight gradients
@@ -308,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     __shared__ const float *rows[kDwChunk];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
     if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
     const int b0 = chunk * kDwChunk;
     if (tid < kDwChunk) {
@@ -325,12 +316,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
         }
         rows[tid] = p;
     }
-    pdl_wait();                 // activations / dZ of the training chain (the predecessor) are read from here on
-    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    // PDL: hidden activations and dZ come from the training chain (the predecessor); the layer-0 CTAs' A operand is
+    // built from replay rows (written >= 2 kernels back) and is gathered before the wait
+    if (l != 0) { pdl_wait(); pdl_trigger(); }
 
     // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row;
     // 4 loads are in flight per thread before any is split / stored
@@ -367,6 +359,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
         *reinterpret_cast<float *>(Ahi + off) = (f == T.K_real && rows[bl]) ? 1.f : 0.f;
         *reinterpret_cast<float *>(Alo + off) = 0.f;
     }
+    if (l == 0) { pdl_wait(); pdl_trigger(); }
     // B = dZ^T : element (row o, col b)
     const int och = T.N_pad / 4;
     for (int i0 = tid; i0 < kDwChunk * och; i0 += 4 * kTcThreads) {
@@ -401,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     tc_fence_after();
     if (tid == 0) {
         issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO), umma_desc(smem_u32(Alo), SBO), umma_desc(smem_u32(Bhi), SBO),
-                     umma_desc(smem_u32(Blo), SBO), umma_idesc_tf32(kTcTile, T.N_pad), kDwChunk / 8);
+                     umma_desc(smem_u32(Blo), SBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
         umma_commit(&mbar);
     }
     mbar_wait(&mbar, 0);
@@ -412,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
         if (quad * 32 >= rowsA) break;
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32_sum(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, tc.concat ? (uint32_t)T.N_pad : 0u, v);
         if (f < rowsA) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -427,7 +420,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
 }
 
 static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }

@@ -84,6 +84,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Accumulator read for the concatenated 3xTF32 scheme: columns [c, c+32) plus, when second_off != 0, the partner block
+// [second_off + c, ...) (the hi*lo product); both loads are in flight before the single wait.
+__device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t second_off, float (&v)[32])
+{
+    if (second_off == 0) { tmem_ld32(taddr, v); return; }
+    uint32_t r[32], s[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
+                   "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15]),
+                   "=r"(s[16]), "=r"(s[17]), "=r"(s[18]), "=r"(s[19]), "=r"(s[20]), "=r"(s[21]), "=r"(s[22]), "=r"(s[23]),
+                   "=r"(s[24]), "=r"(s[25]), "=r"(s[26]), "=r"(s[27]), "=r"(s[28]), "=r"(s[29]), "=r"(s[30]), "=r"(s[31])
+                 : "r"(taddr + second_off) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
+}
+
 // 3xTF32 split: hi = x rounded to TF32 (10-bit mantissa), lo = x - hi (exact).  hi*hi + hi*lo + lo*hi
 // reproduces the fp32 product to ~2^-21.
 __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
@@ -92,6 +119,32 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
     hi = __uint_as_float(h);
     lo = x - hi;
+}
+
+// Issue the three TF32 products of one layer (single thread), K = 8 * ksteps.
+//   concat: the B operand's hi and lo blocks are contiguous in SMEM ([B_hi ; B_lo] = 2N rows), so
+//     D[:, 0:2N]  = A_hi * [B_hi ; B_lo]^T   (one N = 2N instruction per K step: A_hi is read from SMEM once)
+//     D[:, 0:N]  += A_lo * B_hi^T
+//   -> 2 instructions per K step instead of 3; the epilogue adds D[:, c] + D[:, N + c] (tmem_ld32_sum).
+//   !concat: hi*hi + hi*lo + lo*hi accumulate into the same N columns (3 instructions per K step).
+__device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int M, int N,
+                                             int ksteps, bool concat)
+{
+    constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
+    const uint32_t idesc = umma_idesc_tf32(M, N);
+    uint64_t da = a_hi, db = b_hi;
+    if (concat) {
+        const uint32_t wide = umma_idesc_tf32(M, 2 * N);
+        umma_tf32(d, da, db, wide, 0u);
+        for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, wide, 1u); }
+    } else {
+        umma_tf32(d, da, db, idesc, 0u);
+        for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
+        da = a_hi; db = b_lo;
+        for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
+    }
+    da = a_lo; db = b_hi;
+    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
 }
 
 }  // namespace uavrl

@@ -73,7 +73,9 @@ class HostDrivenLoop:
                 L.compute_grads(B * self.world, loss=self.loss_d)
                 self.dist.all_reduce(L.grad_tensor(), op=self.dist.ReduceOp.SUM)
                 L.apply_grads()
+            # Trainer.update returns the loss as a tensor (the reference does too): its device->host copy is enqueued
+            # here and is complete at the next boundary that synchronises (get_action of the following step)
             self.loss_h.copy_(self.loss_d, non_blocking=True)
-            st.synchronize()
             self.obs_h, self.obs2_h = self.obs2_h, self.obs_h
+        st.synchronize()
         return float(self.loss_h[0])
