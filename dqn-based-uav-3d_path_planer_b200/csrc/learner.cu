@@ -225,8 +225,10 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
                 }
                 const int a = s_act[b];
                 const float diff = Q[b * 32 + a] - y;
-                lossb = diff * diff;
-                const float gq = 2.f * diff * ua.inv_global_b;
+                const float wb = src.is_w ? src.is_w[t * kTile + b] : 1.f;
+                if (src.abs_err) src.abs_err[t * kTile + b] = fabsf(diff);
+                lossb = wb * (diff * diff);
+                const float gq = (2.f * diff * wb) * ua.inv_global_b;
                 if (net.dueling) {
                     const float inv = 1.f / (float)nA;
                     for (int o = 0; o < nA; ++o) g[o] = gq * ((o == a ? 1.f : 0.f) - inv);
@@ -517,9 +519,17 @@ int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream
     return launch_update_impl(l, src, B, B, l->loss_dev, true, st, mid);
 }
 
-static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
+static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, int global_batch, float *loss_out, bool apply,
                               cudaStream_t st, cudaEvent_t *mid, bool partials_only)
 {
+    BatchSrc src = src_in;
+    const bool per_batch = l->per.enabled && src.mode != kBatchExplicit && !src.idx_tape;
+    if (per_batch) {
+        // ReplayTree.sample2 -> slots + importance weights; |Q - y| comes back for batch_update (end of this function)
+        int rc = per_sample(l, B, nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+        src.idx_tape = l->per.idx; src.idx_is_slot = 1; src.is_w = l->per.w; src.abs_err = l->per.abs_err;
+    }
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
     const float *y_in = nullptr;
@@ -578,7 +588,11 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
     l->last_nparts = nparts;
     l->last_n_loss_parts = n_loss_parts;
     l->last_global_batch = global_batch;
-    if (partials_only) { l->pdl_prev = kPdlNone; return 0; }     // the data-parallel pair that follows is launched plainly
+    if (partials_only) {
+        l->pdl_prev = kPdlNone;
+        if (per_batch) return per_set(l, B, l->per.idx, nullptr, l->per.abs_err, 1, st);
+        return 0;
+    }     // the data-parallel pair that follows is launched plainly
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = l->net.P; a.nparts = nparts; a.n_loss_parts = n_loss_parts; a.apply = apply ? 1 : 0; a.world = l->world;
@@ -599,6 +613,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int 
                              l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev));
     l->pdl_prev = chain ? kPdlAdam : kPdlNone;
     UAVRL_LAUNCHED();
+    if (per_batch) return per_set(l, B, l->per.idx, nullptr, l->per.abs_err, 1, st);      // ReplayTree.batch_update
     return 0;
 }
 
@@ -685,9 +700,15 @@ int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **
     return 0;
 }
 
-void lockstep_commit(uavrl_learner *l)
+void lockstep_commit(uavrl_learner *l, cudaStream_t st)
 {
     const int64_t N = l->cfg.lockstep_envs;
+    if (l->per.enabled) {
+        // the frame just completed becomes sampleable with the priority of an error-less push; the frame that now
+        // receives the next observations (the ring's oldest) stops being a transition
+        per_fill_range(l, l->head * N, 2 * N, per_new_priority(l->per), st, N, 0.0);
+        l->pdl_prev = kPdlNone;
+    }
     l->head = (l->head + 1) % l->ring_frames;
     const int64_t max_count = (l->ring_frames - 1) * N;
     l->count = (l->count + N > max_count) ? max_count : l->count + N;
@@ -768,6 +789,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
                      l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf, l->tc_hi2_map,
                      l->tc_lo2_map, l->act_buf, l->dz_buf };
     for (void *p : ptrs) cudaFree(p);
+    per_free(l);
     delete l;
     return 0;
 }
@@ -839,6 +861,10 @@ int uavrl_replay_push(uavrl_learner *l, int32_t n, const float *obs, const int32
     push_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(n, l->net.in_dim, l->head, l->slots, obs, act, rew, next_obs,
                                                              done, l->frames, l->r_act, l->r_rew, l->r_done);
     UAVRL_LAUNCHED();
+    if (l->per.enabled) {                                       // ReplayTree.push with error 0; uavrl_per_set_errors refines it
+        int rc = per_fill_range(l, l->head, n, per_new_priority(l->per), (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     l->head = (l->head + n) % l->slots;
     l->count = (l->count + n > l->slots) ? l->slots : l->count + n;
     return 0;
@@ -896,6 +922,18 @@ int uavrl_learner_update_batch(uavrl_learner *l, int32_t B, const float *s, cons
     BatchSrc src;
     memset(&src, 0, sizeof(src));
     src.mode = kBatchExplicit; src.frames = s; src.s2_rows = s2; src.act = a; src.rew = r; src.done_f32 = d;
+    return do_update(l, src, B, B, loss_dev, true, stream);
+}
+
+int uavrl_learner_update_batch_per(uavrl_learner *l, int32_t B, const float *s, const int32_t *a, const float *r, const float *s2,
+                                   const float *d, const float *is_weights, float *abs_err_out, float *loss_dev, void *stream)
+{
+    if (!l || B <= 0 || !s || !a || !r || !s2 || !d) return fail(UAVRL_ERR_INVALID, "bad argument");
+    l->epoch += 1;
+    BatchSrc src;
+    memset(&src, 0, sizeof(src));
+    src.mode = kBatchExplicit; src.frames = s; src.s2_rows = s2; src.act = a; src.rew = r; src.done_f32 = d;
+    src.is_w = is_weights; src.abs_err = abs_err_out;
     return do_update(l, src, B, B, loss_dev, true, stream);
 }
 
@@ -965,6 +1003,13 @@ int uavrl_learner_lockstep_restart(uavrl_learner *l)
     if (l->mode != kReplayLockstep) return 0;
     l->count = 0;
     l->frame0_valid = false;
+    if (l->per.enabled) {
+        UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+        UAVRL_CUDA(cudaDeviceSynchronize());
+        UAVRL_CUDA(cudaMemset(l->per.leaf, 0, (size_t)l->per.cap * 8));
+        UAVRL_CUDA(cudaMemset(l->per.l1, 0, (size_t)l->per.n1 * 8));
+        UAVRL_CUDA(cudaMemset(l->per.l2, 0, (size_t)l->per.n2 * 8));
+    }
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // learner.cuh -- Q-network / replay / optimiser state of one learner (device-resident) + host handle.
 #pragma once
 #include "common.cuh"
+#include "per.cuh"
 
 namespace uavrl {
 
@@ -41,7 +42,10 @@ struct BatchSrc {
     const uint8_t *done_u8;           // [slots]  (replay)          } one of the two
     const float *done_f32;            // [B]      (explicit batch)  }
     const float *s2_rows;             // explicit: next-state rows [B][in]
-    const int32_t *idx_tape;          // optional injected logical indices [B]
+    const int32_t *idx_tape;          // optional injected indices [B]: logical (k-th oldest), or physical slots if idx_is_slot
+    int32_t idx_is_slot;
+    const float *is_w;                // optional per-sample importance weights (prioritised replay): loss = mean(w (Q-y)^2)
+    float *abs_err;                   // optional out: |Q - y| per sample (ReplayTree.batch_update input)
     int64_t count, oldest;            // valid transitions, logical index of the oldest
     int64_t cap;                      // paired: slots ; lockstep: frames in the ring
     int32_t n_envs;                   // lockstep only
@@ -120,6 +124,9 @@ struct uavrl_learner {
     // programmatic dependent launch chain of the lockstep loops (common.cuh)
     bool pdl_chain = false;
     int pdl_prev = 0;
+    // prioritised replay (per.cuh); off unless uavrl_per_enable was called
+    uavrl::PerDev per = {};
+    uint64_t per_calls = 0;
     uint64_t act_calls = 0;
     // data-parallel: one-shot NVLink all-reduce fused with Adam (symmetric buffers exchanged through CUDA IPC)
     int32_t rank = 0, world = 1;
@@ -183,12 +190,12 @@ __device__ __forceinline__ Transition resolve_transition(const BatchSrc &src, in
     const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb] : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
     int64_t slot, row, row2;
     if (src.mode == kReplayLockstep) {
-        const int64_t f = (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
+        const int64_t f = src.idx_is_slot ? (int64_t)(j / src.n_envs) : (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
         const int64_t e = (int64_t)(j % src.n_envs);
         slot = f * src.n_envs + e; row = slot;
         row2 = ((f + 1) % src.cap) * src.n_envs + e;
     } else {
-        slot = (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+        slot = src.idx_is_slot ? (int64_t)j : (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
     }
     t.s = src.frames + (size_t)row * in_dim;
     t.s2 = src.frames + (size_t)row2 * in_dim;
@@ -222,6 +229,6 @@ int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch
 int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, cudaStream_t st);
 int launch_update_split(uavrl_learner *l, const BatchSrc &src, int B, cudaStream_t st, cudaEvent_t *mid);
 int lockstep_begin(uavrl_learner *l, float **obs_t, float **obs_next, int32_t **act, float **rew, uint8_t **done);
-void lockstep_commit(uavrl_learner *l);
+void lockstep_commit(uavrl_learner *l, cudaStream_t st = nullptr);
 BatchSrc replay_source(uavrl_learner *l, const int32_t *idx_tape);
 }  // namespace uavrl

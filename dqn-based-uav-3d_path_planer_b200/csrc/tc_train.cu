@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     float gq = 0.f;
                     if (mine) {
                         const float diff = qa - s_y[row];
-                        atomicAdd(&s_loss, diff * diff);
-                        gq = 2.f * diff * a.inv_global_b;
+                        const float wb = a.src.is_w ? a.src.is_w[gb] : 1.f;
+                        if (a.src.abs_err) a.src.abs_err[gb] = fabsf(diff);
+                        atomicAdd(&s_loss, wb * (diff * diff));
+                        gq = (2.f * diff * wb) * a.inv_global_b;
                     }
                     float g[32];
                     const float inv = 1.f / (float)nA;
@@ -324,28 +326,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // built from replay rows (written >= 2 kernels back) and is gathered before the wait
     if (l != 0) { pdl_wait(); pdl_trigger(); }
 
-    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row;
-    // 4 loads are in flight per thread before any is split / stored
-    const int fch = (T.K_real + 3) / 4;
-    for (int i0 = tid; i0 < kDwChunk * fch; i0 += 4 * kTcThreads) {
-        float4 v[4];
+    // A = [act ; 1]^T : element (row f, col b).  The SMEM bank of an element is ((f & 7) * 4 + (b & 3)) mod 32 (LBO and
+    // SBO are multiples of 128 B), so a warp covers 8 features x 4 samples per store: 32 distinct banks.  A warp
+    // handles a (4-sample, 8-feature) patch per step: lane -> (f & 7 = lane >> 2, b & 3 = lane & 3); its global reads
+    // are four 32-byte segments (L2 resident scratch / replay rows); 8 loads are in flight per thread.
+    {
+        const int fgroups = (T.K_real + 7) / 8, patches = (kDwChunk / 4) * fgroups;
+        const int fl = lane >> 2, bl4 = lane & 3;
+        for (int p0 = warp; p0 < patches; p0 += 8 * (kTcThreads / 32)) {
+            float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-        }
+            for (int u = 0; u < 8; ++u) {
+                const int pp = p0 + u * (kTcThreads / 32);
+                v[u] = 0.f;
+                if (pp < patches) {
+                    const int bq = pp % (kDwChunk / 4), fg = pp / (kDwChunk / 4);
+                    const int bl = 4 * bq + bl4, f = 8 * fg + fl;
+                    if (f < T.K_real && rows[bl]) v[u] = __ldg(rows[bl] + f);
+                }
+            }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            if (i >= kDwChunk * fch) continue;
-            const int bl = i % kDwChunk, jc = i / kDwChunk;
-            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int f = 4 * jc + e;
+            for (int u = 0; u < 8; ++u) {
+                const int pp = p0 + u * (kTcThreads / 32);
+                if (pp >= patches) continue;
+                const int bq = pp % (kDwChunk / 4), fg = pp / (kDwChunk / 4);
+                const int bl = 4 * bq + bl4, f = 8 * fg + fl;
                 if (f < T.K_real) {
-                    float hi, lo; tf32_split(vv[e], hi, lo);
+                    float hi, lo; tf32_split(v[u], hi, lo);
                     const uint32_t off = umma_off(f, bl, SBO);
                     *reinterpret_cast<float *>(Ahi + off) = hi;
                     *reinterpret_cast<float *>(Alo + off) = lo;
@@ -360,29 +367,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
         *reinterpret_cast<float *>(Alo + off) = 0.f;
     }
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    // B = dZ^T : element (row o, col b)
-    const int och = T.N_pad / 4;
-    for (int i0 = tid; i0 < kDwChunk * och; i0 += 4 * kTcThreads) {
-        float4 v[4];
+    // B = dZ^T : element (row o, col b), same conflict-free patch walk
+    {
+        const int ogroups = T.N_pad / 8, patches = (kDwChunk / 4) * ogroups;
+        const int ol = lane >> 2, bl4 = lane & 3;
+        for (int p0 = warp; p0 < patches; p0 += 8 * (kTcThreads / 32)) {
+            float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < kDwChunk * och) {
-                const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
-                if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+            for (int u = 0; u < 8; ++u) {
+                const int pp = p0 + u * (kTcThreads / 32);
+                v[u] = 0.f;
+                if (pp < patches) {
+                    const int bq = pp % (kDwChunk / 4), og = pp / (kDwChunk / 4);
+                    const int b = b0 + 4 * bq + bl4;
+                    if (b < a.B) v[u] = a.dz_buf[(size_t)b * tc.dz_stride + T.dz_off + 8 * og + ol];
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            if (i >= kDwChunk * och) continue;
-            const int bl = i % kDwChunk, jc = i / kDwChunk;
-            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float hi, lo; tf32_split(vv[e], hi, lo);
-                const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+            for (int u = 0; u < 8; ++u) {
+                const int pp = p0 + u * (kTcThreads / 32);
+                if (pp >= patches) continue;
+                const int bq = pp % (kDwChunk / 4), og = pp / (kDwChunk / 4);
+                float hi, lo; tf32_split(v[u], hi, lo);
+                const uint32_t off = umma_off(8 * og + ol, 4 * bq + bl4, SBO);
                 *reinterpret_cast<float *>(Bhi + off) = hi;
                 *reinterpret_cast<float *>(Blo + off) = lo;
             }

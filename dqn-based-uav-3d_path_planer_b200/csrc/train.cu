@@ -47,7 +47,7 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
         if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
                                   l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
         l->pdl_prev = kPdlEnv;
-        lockstep_commit(l);
+        lockstep_commit(l, st);
         if (do_update) {
             for (int u = 0; u < updates_per_iter; ++u) {  // PathPlan_City.update -> Trainer.update (:757-776)
                 l->epoch += 1;
@@ -99,7 +99,7 @@ extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_it
         if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
                                   l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
         l->pdl_prev = kPdlEnv;
-        lockstep_commit(l);
+        lockstep_commit(l, st);
         l->epoch += 1;
         // every rank must take part in every all-reduce: the caller warms the replay up first
         if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay holds <= batch_size transitions (warm up with uavrl_train_run first)");
@@ -129,7 +129,7 @@ extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_i
         UAVRL_CUDA(cudaEventRecord(e[1], st));
         if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[2], st));
-        lockstep_commit(l);
+        lockstep_commit(l, st);
         l->epoch += 1;
         if (l->count <= l->cfg.batch_size) return fail(UAVRL_ERR_STATE, "replay not warmed up");
         BatchSrc src = replay_source(l, nullptr);

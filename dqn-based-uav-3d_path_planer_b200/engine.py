@@ -268,6 +268,36 @@ class Learner:
         check(_lib.lib().uavrl_learner_update_batch(self.h, s.shape[0], _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(d),
                                                     _ptr(loss), _stream(self.device)))
 
+    def update_batch_per(self, s, a, r, s2, d, is_weights=None, abs_err_out=None, loss=None):
+        """update_batch with per-sample importance weights in the loss and |Q - y| written back (prioritised replay)."""
+        check(_lib.lib().uavrl_learner_update_batch_per(self.h, s.shape[0], _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(d),
+                                                        _ptr(is_weights), _ptr(abs_err_out), _ptr(loss), _stream(self.device)))
+
+    # -- prioritised replay (SumTree + ReplayTree of the reference, BaseClass/replay_buffer.py:57-223)
+    def per_enable(self, alpha=-1.0, beta0=-1.0, beta_inc=-1.0, eps=-1.0, err_upper=-1.0):
+        check(_lib.lib().uavrl_per_enable(self.h, alpha, beta0, beta_inc, eps, err_upper))
+        self.per_slots = int(self.cfg.replay_capacity) if not self.cfg.lockstep_envs else None
+
+    def per_sample(self, batch, u_tape=None):
+        """ReplayTree.sample2: (slots int32 [B], importance weights float32 [B]) on the device."""
+        slots = torch.empty(batch, dtype=torch.int32, device=self.device)
+        w = torch.empty(batch, dtype=torch.float32, device=self.device)
+        check(_lib.lib().uavrl_per_sample(self.h, int(batch), _ptr(u_tape), _ptr(slots), _ptr(w), _stream(self.device)))
+        return slots, w
+
+    def per_set_errors(self, slots, abs_err, clip=True):
+        check(_lib.lib().uavrl_per_set_errors(self.h, slots.shape[0], _ptr(slots), _ptr(abs_err), int(bool(clip)),
+                                              _stream(self.device)))
+
+    def per_set_priorities(self, slots, priorities):
+        check(_lib.lib().uavrl_per_set_priorities(self.h, slots.shape[0], _ptr(slots), _ptr(priorities), _stream(self.device)))
+
+    def per_state(self, n_slots):
+        leaves = np.zeros(int(n_slots), np.float64)
+        total, beta = C.c_double(), C.c_double()
+        check(_lib.lib().uavrl_per_get(self.h, _ptr(leaves), C.byref(total), C.byref(beta)))
+        return leaves, total.value, beta.value
+
     def compute_grads(self, global_batch, idx_tape=None, loss=None):
         check(_lib.lib().uavrl_learner_compute_grads(self.h, _ptr(idx_tape), int(global_batch), _ptr(loss),
                                                      _stream(self.device)))

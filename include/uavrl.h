@@ -284,6 +284,34 @@ int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float 
  * fwd_bwd does everything; event gaps make the loop slower, never use it for throughput). */
 int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_iters, float eps, float *ms_out, void *stream);
 
+/* ---- prioritised experience replay ------------------------------------------------------------
+ * Replaces SumTree + ReplayTree (BaseClass/replay_buffer.py:57-223): priorities per replay slot, stratified sampling
+ * over `batch` equal segments of int(total), importance weights (n p / total)^-beta / max, beta += beta_inc per
+ * sampling call (capped at 1), batch_update with (min(|err| + eps, err_upper))^alpha.  Arguments < 0 take the
+ * reference's constants (alpha 0.6, beta 0.4, beta_inc 0.001, eps 0.01, err_upper 1).  Enable before the first
+ * transition is stored.  Once enabled:
+ *   - uavrl_replay_push / the lockstep loops give new transitions the priority of ReplayTree.push with error 0;
+ *   - uavrl_learner_update / uavrl_train_run sample through it, minimise mean(w_i (Q - y)^2) and write
+ *     |Q - y| back with the batch_update rule.  (The reference multiplies the weights into the already averaged loss,
+ *     SAC_Trainer.py:348-352, which cannot be back-propagated; the per-sample form is the documented deviation.)
+ * uavrl_per_sample = ReplayTree.sample2 (:186-213): physical slot indices (tree index = slot + capacity - 1) and
+ * weights; u_tape_dev (optional, [batch] doubles in [0,1)) replaces the uniform draws.  uavrl_per_set_errors:
+ * clip = 0 is ReplayTree.push's rule (:152-154), clip = 1 batch_update's (:216-223).  uavrl_per_set_priorities is
+ * SumTree.update with explicit values.  uavrl_per_get copies the leaves [slots] to the host. */
+int uavrl_per_enable(uavrl_learner *l, double alpha, double beta0, double beta_inc, double eps, double err_upper);
+int uavrl_per_sample(uavrl_learner *l, int32_t batch, const double *u_tape_dev, int32_t *slots_out_dev,
+                     float *weights_out_dev, void *stream);
+int uavrl_per_set_errors(uavrl_learner *l, int32_t n, const int32_t *slots_dev, const float *abs_err_dev, int32_t clip,
+                         void *stream);
+int uavrl_per_set_priorities(uavrl_learner *l, int32_t n, const int32_t *slots_dev, const double *priorities_dev,
+                             void *stream);
+int uavrl_per_get(uavrl_learner *l, double *leaves_host, double *total_out, double *beta_out);
+/* Trainer.update(transition_dict) with 'weights' (and |TD error| back for batch_update): uavrl_learner_update_batch
+ * with per-sample importance weights in the loss; is_weights_dev / abs_err_out_dev may be NULL. */
+int uavrl_learner_update_batch_per(uavrl_learner *l, int32_t batch, const float *obs_dev, const int32_t *act_dev,
+                                   const float *rew_dev, const float *next_obs_dev, const float *done_dev,
+                                   const float *is_weights_dev, float *abs_err_out_dev, float *loss_dev, void *stream);
+
 const char *uavrl_last_error(void);
 const char *uavrl_version(void);
 /* number of kernel launches issued by this library in the calling process since load (bench.py) */

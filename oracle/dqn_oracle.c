@@ -100,10 +100,14 @@ void ora_act(const ora_net *n, const float *params, const float *x, int32_t B, f
     }
 }
 
-float ora_dqn_update(const ora_net *n, int32_t algo, float *local, const float *target,
+/* is_w / abs_err_out: prioritised-replay form of the update (NULL = the reference's plain MSE): loss =
+ * mean(w_i (Q-y)^2), |Q-y| per sample returned for ReplayTree.batch_update.  The reference multiplies the importance
+ * weights into the loss the same way (SAC_Trainer.py:348-352) but on the already averaged loss, which is not
+ * back-propagatable; the per-sample form is the standard one. */
+static float dqn_update_impl(const ora_net *n, int32_t algo, float *local, const float *target,
                      float *m, float *v, int64_t *t,
                      const float *s, const int32_t *a, const float *r, const float *s2,
-                     const float *d, int32_t B, float gamma, float lr, float *grads_out)
+                     const float *d, int32_t B, float gamma, float lr, float *grads_out, const float *is_w, float *abs_err_out)
 {
     const int64_t P = ora_net_param_count(n);
     const int nl = n_layers(n);
@@ -134,8 +138,10 @@ float ora_dqn_update(const ora_net *n, int32_t algo, float *local, const float *
             }
             const float y = r[b] + (gamma * next_q * (1.f - d[b]));       /* :99 / :114 / :171 */
             const float diff = q[a[b]] - y;
-            lsum += (double)diff * diff;
-            const float gq = 2.f * diff / (float)B;                       /* d mean((Q-y)^2) / dQ */
+            const float wb = is_w ? is_w[b] : 1.f;
+            if (abs_err_out) abs_err_out[b] = fabsf(diff);
+            lsum += (double)(wb * (diff * diff));
+            const float gq = (2.f * diff * wb) / (float)B;                /* d mean(w (Q-y)^2) / dQ */
             /* backward through the head(s) */
             float dh[MAXW], dh_prev[MAXW];
             const int top = n->n_hidden;          /* index of the A / plain head */
@@ -207,4 +213,18 @@ float ora_dqn_update(const ora_net *n, int32_t algo, float *local, const float *
     }
     free(G);
     return (float)(loss_sum / (double)B);
+}
+
+float ora_dqn_update(const ora_net *n, int32_t algo, float *local, const float *target, float *m, float *v, int64_t *t,
+                     const float *s, const int32_t *a, const float *r, const float *s2, const float *d, int32_t B,
+                     float gamma, float lr, float *grads_out)
+{
+    return dqn_update_impl(n, algo, local, target, m, v, t, s, a, r, s2, d, B, gamma, lr, grads_out, 0, 0);
+}
+
+float ora_dqn_update_per(const ora_net *n, int32_t algo, float *local, const float *target, float *m, float *v, int64_t *t,
+                         const float *s, const int32_t *a, const float *r, const float *s2, const float *d, int32_t B,
+                         float gamma, float lr, float *grads_out, const float *is_w, float *abs_err_out)
+{
+    return dqn_update_impl(n, algo, local, target, m, v, t, s, a, r, s2, d, B, gamma, lr, grads_out, is_w, abs_err_out);
 }

@@ -47,6 +47,10 @@ float ora_dqn_update(const ora_net *n, int32_t algo, float *local, const float *
                      const float *s, const int32_t *a, const float *r, const float *s2,
                      const float *d, int32_t B, float gamma, float lr, float *grads_out);
 
+/* prioritised-replay form: per-sample importance weights in the loss, |TD error| out (see dqn_oracle.c) */
+float ora_dqn_update_per(const ora_net *n, int32_t algo, float *local, const float *target, float *m, float *v, int64_t *t,
+                         const float *s, const int32_t *a, const float *r, const float *s2, const float *d, int32_t B,
+                         float gamma, float lr, float *grads_out, const float *is_w, float *abs_err_out);
 #ifdef __cplusplus
 }
 #endif

@@ -61,9 +61,23 @@ def lib():
         _lib.ora_fly_power.argtypes = [C.c_double] * 10
         _lib.ora_net_param_count.restype = C.c_int64
         _lib.ora_dqn_update.restype = C.c_float
+        _lib.ora_dqn_update_per.restype = C.c_float
         _lib.ora_sac_update.restype = C.c_float
         _lib.ora_sac_actor_params.restype = C.c_int64
         _lib.ora_sac_critic_params.restype = C.c_int64
+        _lib.ora_per_create.restype = C.c_void_p
+        _lib.ora_per_create.argtypes = [C.c_int32]
+        _lib.ora_per_destroy.argtypes = [C.c_void_p]
+        _lib.ora_per_push.argtypes = [C.c_void_p, C.c_float]
+        _lib.ora_per_add.argtypes = [C.c_void_p, C.c_double]
+        _lib.ora_per_sample.restype = C.c_double
+        _lib.ora_per_sample.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.ora_per_batch_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.ora_per_leaves.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.ora_per_total.restype = C.c_double
+        _lib.ora_per_total.argtypes = [C.c_void_p]
+        _lib.ora_per_n_entries.restype = C.c_int32
+        _lib.ora_per_n_entries.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -240,8 +254,9 @@ class OracleLearner:
         self.gamma, self.lr, self.update_loop = gamma, lr, update_loop
         self.epoch = 0
 
-    def update(self, s, a, r, s2, d):
-        """DuelingDQN_Trainer.update :150-184 (epoch += 1, step, hard update every Update_loop)."""
+    def update(self, s, a, r, s2, d, is_w=None):
+        """DuelingDQN_Trainer.update :150-184 (epoch += 1, step, hard update every Update_loop).  With is_w: the
+        prioritised-replay form (weighted loss); returns (loss, grads, abs_err) then."""
         self.epoch += 1
         s = np.ascontiguousarray(s, np.float32)
         s2 = np.ascontiguousarray(s2, np.float32)
@@ -249,15 +264,21 @@ class OracleLearner:
         r = np.ascontiguousarray(r, np.float32)
         d = np.ascontiguousarray(d, np.float32)
         grads = np.zeros_like(self.local)
-        loss = lib().ora_dqn_update(
-            C.byref(self.net), C.c_int32(self.algo), _p(self.local, C.c_float),
-            _p(self.target, C.c_float), _p(self.m, C.c_float), _p(self.v, C.c_float),
-            C.byref(self.t), _p(s, C.c_float), _p(a, C.c_int32), _p(r, C.c_float),
-            _p(s2, C.c_float), _p(d, C.c_float), C.c_int32(s.shape[0]), C.c_float(self.gamma),
-            C.c_float(self.lr), _p(grads, C.c_float))
+        args = [C.byref(self.net), C.c_int32(self.algo), _p(self.local, C.c_float),
+                _p(self.target, C.c_float), _p(self.m, C.c_float), _p(self.v, C.c_float),
+                C.byref(self.t), _p(s, C.c_float), _p(a, C.c_int32), _p(r, C.c_float),
+                _p(s2, C.c_float), _p(d, C.c_float), C.c_int32(s.shape[0]), C.c_float(self.gamma),
+                C.c_float(self.lr), _p(grads, C.c_float)]
+        abs_err = None
+        if is_w is None:
+            loss = lib().ora_dqn_update(*args)
+        else:
+            w = np.ascontiguousarray(is_w, np.float32)
+            abs_err = np.zeros(s.shape[0], np.float32)
+            loss = lib().ora_dqn_update_per(*args, _p(w, C.c_float), _p(abs_err, C.c_float))
         if self.epoch % self.update_loop == 0:
             self.target[:] = self.local          # hard_update, :199-202
-        return float(loss), grads
+        return (float(loss), grads) if is_w is None else (float(loss), grads, abs_err)
 
 
 def set_threads(n=0):
@@ -369,3 +390,47 @@ class OracleSac:
                                     _p(s2, C.c_float), _p(d, C.c_float), _p(e1, C.c_float), _p(e2, C.c_float), C.c_int32(s.shape[0]),
                                     C.byref(l1), C.byref(l2), C.byref(la))
         return float(loss), float(l1.value), float(l2.value)
+
+
+class OraclePer:
+    """The reference's SumTree + ReplayTree (BaseClass/replay_buffer.py:57-223), sequential C restatement."""
+
+    def __init__(self, capacity):
+        self.cap = int(capacity)
+        self.h = lib().ora_per_create(self.cap)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ora_per_destroy(self.h)
+            self.h = None
+
+    def push(self, abs_err):
+        for e in np.atleast_1d(np.asarray(abs_err, np.float32)):
+            lib().ora_per_push(self.h, float(e))
+
+    def add(self, priorities):
+        for p in np.atleast_1d(np.asarray(priorities, np.float64)):
+            lib().ora_per_add(self.h, float(p))
+
+    def sample(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        idx = np.zeros(len(u), np.int64); w = np.zeros(len(u), np.float64)
+        beta = lib().ora_per_sample(self.h, len(u), u.ctypes.data, idx.ctypes.data, w.ctypes.data)
+        return idx, w, beta
+
+    def batch_update(self, tree_idx, abs_err):
+        ti = np.ascontiguousarray(tree_idx, np.int64); ae = np.ascontiguousarray(abs_err, np.float32)
+        lib().ora_per_batch_update(self.h, len(ti), ti.ctypes.data, ae.ctypes.data)
+
+    def leaves(self):
+        out = np.zeros(self.cap, np.float64)
+        lib().ora_per_leaves(self.h, out.ctypes.data)
+        return out
+
+    @property
+    def total(self):
+        return lib().ora_per_total(self.h)
+
+    @property
+    def n_entries(self):
+        return lib().ora_per_n_entries(self.h)
