@@ -38,7 +38,9 @@ struct TcDwArgs {
     int32_t B, n_chunks, P;
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_chunks][P]
+    long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
 };
+#define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
 // Gather R rows (pointers in rows[]) into the layer-0 A operand.  All of a thread's loads are issued before any
 // is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     __shared__ const float *rows[kDwChunk];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
+    DW_TRACE(0);
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
     if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
     const int b0 = chunk * kDwChunk;
@@ -325,34 +328,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // PDL: hidden activations and dZ come from the training chain (the predecessor); the layer-0 CTAs' A operand is
     // built from replay rows (written >= 2 kernels back) and is gathered before the wait
     if (l != 0) { pdl_wait(); pdl_trigger(); }
+    DW_TRACE(1);
 
-    // A = [act ; 1]^T : element (row f, col b).  The SMEM bank of an element is ((f & 7) * 4 + (b & 3)) mod 32 (LBO and
-    // SBO are multiples of 128 B), so a warp covers 8 features x 4 samples per store: 32 distinct banks.  A warp
-    // handles a (4-sample, 8-feature) patch per step: lane -> (f & 7 = lane >> 2, b & 3 = lane & 3); its global reads
-    // are four 32-byte segments (L2 resident scratch / replay rows); 8 loads are in flight per thread.
-    {
-        const int fgroups = (T.K_real + 7) / 8, patches = (kDwChunk / 4) * fgroups;
-        const int fl = lane >> 2, bl4 = lane & 3;
-        for (int p0 = warp; p0 < patches; p0 += 8 * (kTcThreads / 32)) {
-            float v[8];
+    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row;
+    // 4 loads are in flight per thread before any is split / stored
+    const int fch = (T.K_real + 3) / 4;
+    for (int i0 = tid; i0 < kDwChunk * fch; i0 += 4 * kTcThreads) {
+        float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int pp = p0 + u * (kTcThreads / 32);
-                v[u] = 0.f;
-                if (pp < patches) {
-                    const int bq = pp % (kDwChunk / 4), fg = pp / (kDwChunk / 4);
-                    const int bl = 4 * bq + bl4, f = 8 * fg + fl;
-                    if (f < T.K_real && rows[bl]) v[u] = __ldg(rows[bl] + f);
-                }
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int pp = p0 + u * (kTcThreads / 32);
-                if (pp >= patches) continue;
-                const int bq = pp % (kDwChunk / 4), fg = pp / (kDwChunk / 4);
-                const int bl = 4 * bq + bl4, f = 8 * fg + fl;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i >= kDwChunk * fch) continue;
+            const int bl = i % kDwChunk, jc = i / kDwChunk;
+            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int f = 4 * jc + e;
                 if (f < T.K_real) {
-                    float hi, lo; tf32_split(v[u], hi, lo);
+                    float hi, lo; tf32_split(vv[e], hi, lo);
                     const uint32_t off = umma_off(f, bl, SBO);
                     *reinterpret_cast<float *>(Ahi + off) = hi;
                     *reinterpret_cast<float *>(Alo + off) = lo;
@@ -360,36 +359,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
             }
         }
     }
+    DW_TRACE(2);
     for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
         const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
         const uint32_t off = umma_off(f, bl, SBO);
         *reinterpret_cast<float *>(Ahi + off) = (f == T.K_real && rows[bl]) ? 1.f : 0.f;
         *reinterpret_cast<float *>(Alo + off) = 0.f;
     }
+    DW_TRACE(3);
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    // B = dZ^T : element (row o, col b), same conflict-free patch walk
-    {
-        const int ogroups = T.N_pad / 8, patches = (kDwChunk / 4) * ogroups;
-        const int ol = lane >> 2, bl4 = lane & 3;
-        for (int p0 = warp; p0 < patches; p0 += 8 * (kTcThreads / 32)) {
-            float v[8];
+    // B = dZ^T : element (row o, col b)
+    const int och = T.N_pad / 4;
+    for (int i0 = tid; i0 < kDwChunk * och; i0 += 4 * kTcThreads) {
+        float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int pp = p0 + u * (kTcThreads / 32);
-                v[u] = 0.f;
-                if (pp < patches) {
-                    const int bq = pp % (kDwChunk / 4), og = pp / (kDwChunk / 4);
-                    const int b = b0 + 4 * bq + bl4;
-                    if (b < a.B) v[u] = a.dz_buf[(size_t)b * tc.dz_stride + T.dz_off + 8 * og + ol];
-                }
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < kDwChunk * och) {
+                const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
+                if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int pp = p0 + u * (kTcThreads / 32);
-                if (pp >= patches) continue;
-                const int bq = pp % (kDwChunk / 4), og = pp / (kDwChunk / 4);
-                float hi, lo; tf32_split(v[u], hi, lo);
-                const uint32_t off = umma_off(8 * og + ol, 4 * bq + bl4, SBO);
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i >= kDwChunk * och) continue;
+            const int bl = i % kDwChunk, jc = i / kDwChunk;
+            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float hi, lo; tf32_split(vv[e], hi, lo);
+                const uint32_t off = umma_off(4 * jc + e, bl, SBO);
                 *reinterpret_cast<float *>(Bhi + off) = hi;
                 *reinterpret_cast<float *>(Blo + off) = lo;
             }
@@ -399,13 +400,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    DW_TRACE(4);
     if (tid == 0) {
         issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO), umma_desc(smem_u32(Alo), SBO), umma_desc(smem_u32(Bhi), SBO),
                      umma_desc(smem_u32(Blo), SBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
         umma_commit(&mbar);
     }
+    DW_TRACE(5);
     mbar_wait(&mbar, 0);
     tc_fence_after();
+    DW_TRACE(6);
     // epilogue: accumulator row f = input feature (or the ones row), column o = output unit
     float *part = a.partials + (size_t)chunk * a.P;
     const int f = quad * 32 + lane;
@@ -425,9 +429,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
             }
         }
     }
+    DW_TRACE(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
+    DW_TRACE(8);
 }
 
 static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }
@@ -483,10 +489,22 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
     d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
+    static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
+    long long *tr = nullptr;
+    if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }
     UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
                              chain && !after_chain, tc, d));
     l->pdl_prev = chain ? kPdlDw : kPdlNone;
     UAVRL_LAUNCHED();
+    if (trace_on) {
+        long long h[16];
+        UAVRL_CUDA(cudaStreamSynchronize(st));
+        UAVRL_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(tr);
+        fprintf(stderr, "[dw_trace] B=%d chunks=%d (CTA 0 = layer 0) cycles since start:", B, d.n_chunks);
+        for (int i = 1; i < 9; ++i) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     *n_grad_parts = d.n_chunks;
     *n_loss_parts = grid;
     return 0;

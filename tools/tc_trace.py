@@ -10,3 +10,10 @@ x = torch.randn(4096, 100, device="cuda")
 for _ in range(5):
     L.act(x, 0.1)
 torch.cuda.synchronize()
+# training kernels: [tc_trace] lines for the TD pass and [dw_trace] for the weight-gradient kernel (layer-0 CTA)
+B = 4096
+s = torch.randn(B, 100, device="cuda"); s2 = torch.randn(B, 100, device="cuda")
+a = torch.randint(0, 27, (B,), device="cuda", dtype=torch.int32); r = torch.randn(B, device="cuda"); d = torch.zeros(B, device="cuda")
+for _ in range(3):
+    L.update_batch(s, a, r, s2, d)
+torch.cuda.synchronize()
