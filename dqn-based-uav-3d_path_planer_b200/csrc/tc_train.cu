@@ -39,6 +39,7 @@ struct TcDwArgs {
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_chunks][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
+    int32_t swap_desc;                 // debug (UAVRL_DW_SWAP): exchange the LBO / SBO descriptor fields of the MN-major operands
 };
 #define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
@@ -436,12 +437,174 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     DW_TRACE(8);
 }
 
+// ------------------------------------------------------------------ split-K weight gradients, MN-major operands
+// dW_l^T[f][o] = sum_b [act_l ; 1][b][f] * dZ_l[b][o]: both operands are read with the reduction index b as the slow
+// one -- exactly the MN-major canonical layout (umma.cuh): a float4 of 4 consecutive features (outputs) of sample b is
+// ONE 16-byte SMEM store, consecutive lanes take consecutive samples (conflict-free), and every global load of a thread
+// is issued before the first is consumed.
+constexpr uint32_t kDwKStride = 128;                             // 8 samples x 16 B: core matrices adjacent in K are contiguous
+constexpr uint32_t kDwMnStride = (kDwChunk / 8) * kDwKStride;    // 2048 B per group of 4 features / outputs
+__global__ void __launch_bounds__(kTcThreads, 1) tc_dw_mn_kernel(TcNet tc, TcDwArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int l = blockIdx.x % tc.n_layers, chunk = blockIdx.x / tc.n_layers;
+    const TcLayer T = tc.L[l];
+    const int rowsA = T.K_real + 1;                            // input features + the all-ones row (bias gradient)
+    const int gA = (rowsA + 3) / 4, gB = T.N_pad / 4;           // 16-byte groups along MN
+    unsigned char *Ahi = smem, *Alo = Ahi + gA * kDwMnStride, *Bhi = Alo + gA * kDwMnStride, *Blo = Bhi + gB * kDwMnStride;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ const float *rows[kDwChunk];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
+    DW_TRACE(0);
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
+    if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
+    const int b0 = chunk * kDwChunk;
+    if (tid < kDwChunk) {
+        const int b = b0 + tid;
+        const float *p = nullptr;
+        if (b < a.B) {
+            if (l == 0) {
+                uint32_t pkey[4];
+                Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+                p = resolve_transition(a.src, b, tc.in_dim, pkey).s;
+            } else {
+                p = a.act_buf + (size_t)b * tc.act_stride + T.act_off;
+            }
+        }
+        rows[tid] = p;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    // PDL: hidden activations and dZ come from the training chain (the predecessor); the layer-0 CTAs' A operand is
+    // built from replay rows (written >= 2 kernels back) and is gathered before the wait
+    if (l != 0) { pdl_wait(); pdl_trigger(); }
+    DW_TRACE(1);
+    {   // A: K_real/4 feature groups x 128 samples, thread -> (sample = i % 128, group = i / 128)
+        const int fch = T.K_real / 4, total = kDwChunk * fch;   // K_real is a multiple of 4 (checked by tc_train_init)
+        constexpr int U = 13;                                   // 128 * 25 / 256 = 12.5 loads per thread for the 100-wide input
+        for (int i0 = tid; i0 < total; i0 += U * kTcThreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= total) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                float4 h, lo4;
+                tf32_split(v[u].x, h.x, lo4.x); tf32_split(v[u].y, h.y, lo4.y); tf32_split(v[u].z, h.z, lo4.z); tf32_split(v[u].w, h.w, lo4.w);
+                const uint32_t off = (uint32_t)jc * kDwMnStride + (uint32_t)bl * 16u;
+                *reinterpret_cast<float4 *>(Ahi + off) = h;
+                *reinterpret_cast<float4 *>(Alo + off) = lo4;
+            }
+        }
+        // the ones row (feature index K_real, first element of the next group) and the zero rows after it
+        if (tid < kDwChunk) {
+            const uint32_t off = (uint32_t)(T.K_real / 4) * kDwMnStride + (uint32_t)tid * 16u;
+            *reinterpret_cast<float4 *>(Ahi + off) = make_float4(rows[tid] ? 1.f : 0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(Alo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    DW_TRACE(3);
+    if (l == 0) { pdl_wait(); pdl_trigger(); }
+    {   // B: N_pad/4 output groups x 128 samples
+        const int och = T.N_pad / 4, total = kDwChunk * och;
+        constexpr int U = 8;
+        for (int i0 = tid; i0 < total; i0 += U * kTcThreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) {
+                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
+                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= total) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                float4 h, lo4;
+                tf32_split(v[u].x, h.x, lo4.x); tf32_split(v[u].y, h.y, lo4.y); tf32_split(v[u].z, h.z, lo4.z); tf32_split(v[u].w, h.w, lo4.w);
+                const uint32_t off = (uint32_t)jc * kDwMnStride + (uint32_t)bl * 16u;
+                *reinterpret_cast<float4 *>(Bhi + off) = h;
+                *reinterpret_cast<float4 *>(Blo + off) = lo4;
+            }
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    DW_TRACE(4);
+    if (tid == 0) {
+        const bool sw = a.swap_desc != 0;
+        issue_3xtf32(tmem, umma_desc_mn(smem_u32(Ahi), kDwKStride, kDwMnStride, sw), umma_desc_mn(smem_u32(Alo), kDwKStride, kDwMnStride, sw),
+                     umma_desc_mn(smem_u32(Bhi), kDwKStride, kDwMnStride, sw), umma_desc_mn(smem_u32(Blo), kDwKStride, kDwMnStride, sw),
+                     kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0, true, kDwKStride);
+        umma_commit(&mbar);
+    }
+    DW_TRACE(5);
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    DW_TRACE(6);
+    // epilogue: accumulator row f = input feature (or the ones row), column o = output unit
+    float *part = a.partials + (size_t)chunk * a.P;
+    const int f = quad * 32 + lane;
+    for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
+        if (quad * 32 >= rowsA) break;
+        float v[32];
+        tmem_ld32_sum(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, tc.concat ? (uint32_t)T.N_pad : 0u, v);
+        if (f < rowsA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int o = c0 + j;
+                if (o < T.N_real) {
+                    const bool vrow = o >= T.out_main;                                   // dueling value head row
+                    if (f < T.K_real) part[vrow ? T.w2_off + (o - T.out_main) * T.K_real + f : T.w_off + o * T.K_real + f] = v[j];
+                    else part[vrow ? T.b2_off + (o - T.out_main) : T.b_off + o] = v[j];
+                }
+            }
+        }
+    }
+    DW_TRACE(7);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
+    DW_TRACE(8);
+}
+
 static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }
 static size_t dw_smem_bytes(const TcNet &tc)
 {
     size_t mx = 0;
     for (int l = 0; l < tc.n_layers; ++l) {
         const size_t b = (size_t)2 * ((tc.L[l].K_real + 1 + 7) / 8 + tc.L[l].N_pad / 8) * umma_sbo(kDwChunk);
+        if (b > mx) mx = b;
+    }
+    return mx;
+}
+
+static size_t dw_mn_smem_bytes(const TcNet &tc)
+{
+    size_t mx = 0;
+    for (int l = 0; l < tc.n_layers; ++l) {
+        const size_t gA = (size_t)(tc.L[l].K_real + 1 + 3) / 4, gB = (size_t)tc.L[l].N_pad / 4;
+        // the M = 128 instruction reads 32 feature groups from each A buffer and 2*N_pad/4 groups from B_hi: everything it can
+        // touch must lie inside the CTA's allocation
+        size_t b = 2 * (gA + gB) * kDwMnStride;
+        const size_t reach = (gA + 32) * kDwMnStride;           // A_lo start + 32 groups
+        if (reach > b) b = reach;
         if (b > mx) mx = b;
     }
     return mx;
@@ -460,6 +623,9 @@ int tc_train_init(uavrl_learner *l)
     UAVRL_CUDA(cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
     UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
+    l->dw_mn = getenv("UAVRL_DW_KMAJOR") == nullptr && dw_mn_smem_bytes(tc) <= 227 * 1024;
+    for (int i = 0; i < tc.n_layers; ++i) if (tc.L[i].K_real % 4 != 0) l->dw_mn = false;
+    if (l->dw_mn) UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_mn_smem_bytes(tc)));
     const size_t cap = (size_t)l->cfg.batch_size;
     UAVRL_CUDA(cudaMalloc((void **)&l->act_buf, cap * (size_t)(tc.act_stride > 0 ? tc.act_stride : 4) * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, cap * (size_t)tc.dz_stride * 4));
@@ -492,8 +658,14 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }
-    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
-                             chain && !after_chain, tc, d));
+    static const bool swap_desc = getenv("UAVRL_DW_SWAP") != nullptr;
+    d.swap_desc = swap_desc ? 1 : 0;
+    if (l->dw_mn)
+        UAVRL_CUDA(launch_kernel(tc_dw_mn_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_mn_smem_bytes(tc), st,
+                                 chain && !after_chain, tc, d));
+    else
+        UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
+                                 chain && !after_chain, tc, d));
     l->pdl_prev = chain ? kPdlDw : kPdlNone;
     UAVRL_LAUNCHED();
     if (trace_on) {

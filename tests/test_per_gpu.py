@@ -116,6 +116,7 @@ def test_weighted_update_matches_oracle(tc):
     L.set_tensor_cores(bool(tc))
     net = O.make_net(100, [64, 64], 27, 0)
     ol = O.OracleLearner(net, O.ALGO_DDQN, L.get_params(0), gamma=0.99, lr=5e-4, update_loop=3)
+    ol.target[:] = L.get_params(1)                           # init_params draws q_target independently, like the reference
     rng = np.random.default_rng(11)
     for it in range(3):
         s = rng.standard_normal((B, 100)).astype(np.float32); s2 = rng.standard_normal((B, 100)).astype(np.float32)
