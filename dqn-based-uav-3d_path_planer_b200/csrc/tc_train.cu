@@ -331,31 +331,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
 
-    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row;
-    // 4 loads are in flight per thread before any is split / stored
+    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row; every
+    // load of a thread is in flight before the first is split / stored (one L2/HBM round trip per CTA)
     const int fch = (T.K_real + 3) / 4;
-    for (int i0 = tid; i0 < kDwChunk * fch; i0 += 4 * kTcThreads) {
-        float4 v[4];
+    {
+        constexpr int U = 13;                                  // 128 * 25 / 256 = 12.5 float4 per thread for the 100-wide input
+        for (int i0 = tid; i0 < kDwChunk * fch; i0 += U * kTcThreads) {
+            float4 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-        }
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+            }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            if (i >= kDwChunk * fch) continue;
-            const int bl = i % kDwChunk, jc = i / kDwChunk;
-            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= kDwChunk * fch) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int f = 4 * jc + e;
-                if (f < T.K_real) {
-                    float hi, lo; tf32_split(vv[e], hi, lo);
-                    const uint32_t off = umma_off(f, bl, SBO);
-                    *reinterpret_cast<float *>(Ahi + off) = hi;
-                    *reinterpret_cast<float *>(Alo + off) = lo;
+                for (int e = 0; e < 4; ++e) {
+                    const int f = 4 * jc + e;
+                    if (f < T.K_real) {
+                        float hi, lo; tf32_split(vv[e], hi, lo);
+                        const uint32_t off = umma_off(f, bl, SBO);
+                        *reinterpret_cast<float *>(Ahi + off) = hi;
+                        *reinterpret_cast<float *>(Alo + off) = lo;
+                    }
                 }
             }
         }
@@ -371,29 +374,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (l == 0) { pdl_wait(); pdl_trigger(); }
     // B = dZ^T : element (row o, col b)
     const int och = T.N_pad / 4;
-    for (int i0 = tid; i0 < kDwChunk * och; i0 += 4 * kTcThreads) {
-        float4 v[4];
+    {
+        constexpr int U = 8;
+        for (int i0 = tid; i0 < kDwChunk * och; i0 += U * kTcThreads) {
+            float4 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < kDwChunk * och) {
-                const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
-                if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < kDwChunk * och) {
+                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
+                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kTcThreads;
-            if (i >= kDwChunk * och) continue;
-            const int bl = i % kDwChunk, jc = i / kDwChunk;
-            const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= kDwChunk * och) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float hi, lo; tf32_split(vv[e], hi, lo);
-                const uint32_t off = umma_off(4 * jc + e, bl, SBO);
-                *reinterpret_cast<float *>(Bhi + off) = hi;
-                *reinterpret_cast<float *>(Blo + off) = lo;
+                for (int e = 0; e < 4; ++e) {
+                    float hi, lo; tf32_split(vv[e], hi, lo);
+                    const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+                    *reinterpret_cast<float *>(Bhi + off) = hi;
+                    *reinterpret_cast<float *>(Blo + off) = lo;
+                }
             }
         }
     }
@@ -623,7 +629,8 @@ int tc_train_init(uavrl_learner *l)
     UAVRL_CUDA(cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
     UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
-    l->dw_mn = getenv("UAVRL_DW_KMAJOR") == nullptr && dw_mn_smem_bytes(tc) <= 227 * 1024;
+    // MN-major operand variant (tc_dw_mn_kernel): experimental, results not yet validated -> opt-in only
+    l->dw_mn = getenv("UAVRL_DW_MN") != nullptr && dw_mn_smem_bytes(tc) <= 227 * 1024;
     for (int i = 0; i < tc.n_layers; ++i) if (tc.L[i].K_real % 4 != 0) l->dw_mn = false;
     if (l->dw_mn) UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_mn_smem_bytes(tc)));
     const size_t cap = (size_t)l->cfg.batch_size;

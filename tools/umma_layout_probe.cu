@@ -10,7 +10,7 @@
 #include "../dqn-based-uav-3d_path_planer_b200/csrc/umma.cuh"
 using namespace uavrl;
 
-constexpr int kFloats = 40 * 1024 / 4;          // probed A region: 40 KB
+constexpr int kFloats = 72 * 1024 / 4;          // probed region: 72 KB (M = 128 reads 32 groups x 2 KB = 64 KB)
 
 // mode 0: A MN-major probed (B K-major identity);  mode 1: B MN-major probed (A K-major identity rows 0..7)
 __global__ void __launch_bounds__(128) probe_kernel(float *D, int mode, int pass, uint32_t lbo, uint32_t sbo)
@@ -24,6 +24,9 @@ __global__ void __launch_bounds__(128) probe_kernel(float *D, int mode, int pass
     if (warp == 0) tmem_alloc(&tmem_base, 32);
     if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
     for (int i = tid; i < kFloats; i += 128) P[i] = (float)(pass == 0 ? (i % 1024) : (i / 1024));
+    if (mode == 2) {                                                  // sanity: K-major probe, K_pad = 8 (known-good path)
+        // nothing else: descriptor below uses LBO 128 / SBO 256 with a_major = 0
+    }
     constexpr uint32_t ISBO = umma_sbo(8);
     for (int i = tid; i < 128 * 8; i += 128) {
         const int r = i / 8, c = i % 8;
@@ -41,7 +44,8 @@ __global__ void __launch_bounds__(128) probe_kernel(float *D, int mode, int pass
         dp |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
         dp |= (uint64_t)1 << 46;
         const uint64_t di = umma_desc(smem_u32(I), ISBO);
-        if (mode == 0) umma_tf32(tb, dp, di, umma_idesc_tf32(128, 16) | (1u << 15), 0u);      // A MN-major, B K-major
+        if (mode == 2) umma_tf32(tb, dp, di, umma_idesc_tf32(128, 16), 0u);                   // A K-major (sanity)
+        else if (mode == 0) umma_tf32(tb, dp, di, umma_idesc_tf32(128, 16) | (1u << 15), 0u);      // A MN-major, B K-major
         else           umma_tf32(tb, di, dp, umma_idesc_tf32(128, 16) | (1u << 16), 0u);      // A K-major identity, B MN-major
         umma_commit(&bar);
     }
@@ -61,9 +65,11 @@ int main()
     cudaMalloc(&dD, 128 * 16 * 4);
     const size_t smem = kFloats * 4 + 128 * 8 * 4 + 1024;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const uint32_t cfgs[][2] = { { 128, 2048 }, { 2048, 128 }, { 128, 1024 }, { 256, 2048 } };
-    for (int mode = 0; mode < 2; ++mode)
+    const uint32_t cfgs[][2] = { { 128, 2048 }, { 2048, 128 }, { 128, 256 } };
+    const int modes[] = { 2, 0, 1 };
+    for (int mode : modes)
         for (auto &c : cfgs) {
+            if ((mode == 2) != (c[1] == 256)) continue;
             std::vector<float> lo(128 * 16), hi(128 * 16);
             for (int pass = 0; pass < 2; ++pass) {
                 probe_kernel<<<1, 128, smem>>>(dD, mode, pass, c[0], c[1]);
@@ -71,8 +77,8 @@ int main()
                 if (e != cudaSuccess) { printf("mode %d lbo %u sbo %u: %s\n", mode, c[0], c[1], cudaGetErrorString(e)); return 1; }
                 cudaMemcpy(pass ? hi.data() : lo.data(), dD, 128 * 16 * 4, cudaMemcpyDeviceToHost);
             }
-            printf("mode %d (%s MN-major probed)  LBO field %u  SBO field %u : float index read for (mn, k)\n", mode, mode ? "B" : "A", c[0], c[1]);
-            if (mode == 0) {
+            printf("mode %d (%s probed; 2 = K-major sanity)  LBO field %u  SBO field %u : float index read for (mn, k)\n", mode, mode ? "B" : "A", c[0], c[1]);
+            if (mode != 1) {
                 const int ms[] = { 0, 1, 2, 3, 4, 5, 8, 16, 32, 64, 100, 127 };
                 for (int m : ms) {
                     printf("  mn=%3d:", m);
