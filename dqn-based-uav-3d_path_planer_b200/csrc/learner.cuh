@@ -122,7 +122,6 @@ struct uavrl_learner {
     int64_t count = 0;                // valid transitions
     bool frame0_valid = false;
     // programmatic dependent launch chain of the lockstep loops (common.cuh)
-    bool dw_mn = false;               // weight-gradient kernel with MN-major operands (tc_train.cu)
     bool pdl_chain = false;
     int pdl_prev = 0;
     // prioritised replay (per.cuh); off unless uavrl_per_enable was called

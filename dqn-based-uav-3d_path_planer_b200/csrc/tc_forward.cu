@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
             rows[tid] = p; s_rew[tid] = r; s_done[tid] = d;
         }
         __syncthreads();
-        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout (4 loads in flight per thread)
+        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout (4 loads in flight per thread;
+        //      lanes walk the 8 rows of a core-matrix column first: conflict-free 16-byte stores)
         {
             const int K0 = tc.L[0].K_pad, chunks = K0 / 4, total = R * chunks;
             const uint32_t sbo = umma_sbo(K0);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                     const int i = i0 + u * kTcThreads;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i < total) {
-                        const int r = i / chunks, j = i - r * chunks;
+                        const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
                         if (rows[r] && 4 * j < tc.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
                     }
                 }
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 for (int u = 0; u < 4; ++u) {
                     const int i = i0 + u * kTcThreads;
                     if (i < total) {
-                        const int r = i / chunks, j = i - r * chunks;
+                        const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
                         float4 h, l;
                         tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                         const uint32_t off = umma_off(r, 4 * j, sbo);

@@ -39,12 +39,13 @@ struct TcDwArgs {
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_chunks][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
-    int32_t swap_desc;                 // debug (UAVRL_DW_SWAP): exchange the LBO / SBO descriptor fields of the MN-major operands
 };
 #define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
 // Gather R rows (pointers in rows[]) into the layer-0 A operand.  All of a thread's loads are issued before any
-// is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.
+// is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.  Consecutive lanes take
+// consecutive rows of an 8-row group (same 16-byte chunk): a quarter-warp's 16-byte stores then cover one whole core
+// matrix column = 128 contiguous bytes (lanes walking along a row would all hit the same 4 banks).
 __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo)
 {
     const int chunks = K0 / 4, total = R * chunks;
@@ -56,7 +57,7 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
             const int i = i0 + u * kTcThreads;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < total) {
-                const int r = i / chunks, j = i - r * chunks;
+                const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
                 if (rows[r] && 4 * j < in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
             }
         }
@@ -64,7 +65,7 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kTcThreads;
             if (i < total) {
-                const int r = i / chunks, j = i - r * chunks;
+                const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
                 float4 h, l;
                 tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                 const uint32_t off = umma_off(r, 4 * j, sbo);
@@ -289,6 +290,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
 }
 
+// 4x4 transpose across an aligned group of 4 lanes: lane r holds row r (x..w = columns 0..3); returns column r.
+__device__ __forceinline__ float4 quad_transpose(float4 a, int lane)
+{
+    const int r = lane & 3, base = lane & ~3;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int sidx = (r - i) & 3;                          // what the lane at distance i wants from this lane
+        const float send = sidx == 0 ? a.x : sidx == 1 ? a.y : sidx == 2 ? a.z : a.w;
+        const int src = (r + i) & 3;
+        const float got = __shfl_sync(0xffffffffu, send, base | src);
+        if (src == 0) c0 = got; else if (src == 1) c1 = got; else if (src == 2) c2 = got; else c3 = got;
+    }
+    return make_float4(c0, c1, c2, c3);
+}
+
+// Transposed operand build of the weight-gradient kernel: out element (row = 4*jc + e, col = sample) from source rows
+// [sample][4*n_chunks floats].  Source = rows[] pointers (A) or base + sample*stride with n_valid rows (B).  U = warp
+// items per warp (all loads in flight).  See the call site for the lane mapping.
+template <int U>
+__device__ __forceinline__ void dw_build_transposed(const float *const *rows, const float *base, int stride, int n_valid, int n_chunks,
+                                                    int rows_real, unsigned char *hi_buf, unsigned char *lo_buf, uint32_t SBO, int warp,
+                                                    int lane)
+{
+    const int q = lane >> 3, jp = (lane >> 2) & 1, r = lane & 3;
+    const int items = ((n_chunks + 1) / 2) * (kDwChunk / 16);
+    for (int it0 = warp; it0 < items; it0 += (kTcThreads / 32) * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * (kTcThreads / 32);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < items) {
+                const int jc = 2 * (it / (kDwChunk / 16)) + jp, bl = 16 * (it % (kDwChunk / 16)) + 4 * q + r;
+                if (jc < n_chunks) {
+                    if (rows) { if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+                    else if (bl < n_valid) v[u] = *reinterpret_cast<const float4 *>(base + (size_t)bl * stride + 4 * jc);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * (kTcThreads / 32);
+            const float4 x = quad_transpose(v[u], lane);       // every lane takes part in the shuffles
+            if (it >= items) continue;
+            const int jc = 2 * (it / (kDwChunk / 16)) + jp, f = 4 * jc + r;
+            if (f >= rows_real) continue;
+            float4 h, l4;
+            tf32_split(x.x, h.x, l4.x); tf32_split(x.y, h.y, l4.y); tf32_split(x.z, h.z, l4.z); tf32_split(x.w, h.w, l4.w);
+            const uint32_t off = umma_off(f, 16 * (it % (kDwChunk / 16)) + 4 * q, SBO);
+            *reinterpret_cast<float4 *>(hi_buf + off) = h;
+            *reinterpret_cast<float4 *>(lo_buf + off) = l4;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ split-K weight gradients
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
 {
@@ -331,38 +388,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
 
-    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row; every
-    // load of a thread is in flight before the first is split / stored (one L2/HBM round trip per CTA)
+    // A = [act ; 1]^T : element (row f, col b); source rows are [sample][feature].  (MN-major tcgen05 operands would take
+    // the source as it is, but kind::tf32 reads zeros from an unswizzled MN-major layout -- tools/umma_layout_probe.cu --
+    // so the transposition is done here.)  A warp item = 16 samples x 2 feature chunks: lane = (sample quad q, chunk
+    // parity jp, r): each lane loads one float4 (4 features of its sample), the 4 lanes of a quad transpose their 4x4
+    // block with shuffles, and lane r stores features-row 4*jc + r for the quad's 4 samples as ONE 16-byte store.  A
+    // quarter-warp then covers 8 different rows (f & 7) of one core-matrix column: 128 contiguous bytes, no bank conflict
+    // (element-wise 4-byte stores were 8-way conflicted and made this phase the longest of the kernel).
     const int fch = (T.K_real + 3) / 4;
-    {
-        constexpr int U = 13;                                  // 128 * 25 / 256 = 12.5 float4 per thread for the 100-wide input
-        for (int i0 = tid; i0 < kDwChunk * fch; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= kDwChunk * fch) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int f = 4 * jc + e;
-                    if (f < T.K_real) {
-                        float hi, lo; tf32_split(vv[e], hi, lo);
-                        const uint32_t off = umma_off(f, bl, SBO);
-                        *reinterpret_cast<float *>(Ahi + off) = hi;
-                        *reinterpret_cast<float *>(Alo + off) = lo;
-                    }
-                }
-            }
-        }
-    }
+    dw_build_transposed<13>(rows, nullptr, 0, 0, fch, T.K_real, Ahi, Alo, SBO, warp, lane);
     DW_TRACE(2);
     for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
         const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
@@ -372,37 +406,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
     DW_TRACE(3);
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    // B = dZ^T : element (row o, col b)
-    const int och = T.N_pad / 4;
-    {
-        constexpr int U = 8;
-        for (int i0 = tid; i0 < kDwChunk * och; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < kDwChunk * och) {
-                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
-                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= kDwChunk * och) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float hi, lo; tf32_split(vv[e], hi, lo);
-                    const uint32_t off = umma_off(4 * jc + e, bl, SBO);
-                    *reinterpret_cast<float *>(Bhi + off) = hi;
-                    *reinterpret_cast<float *>(Blo + off) = lo;
-                }
-            }
-        }
-    }
+    // B = dZ^T : element (row o, col b), same transposing build (source rows: the dZ scratch, N_pad floats per sample)
+    dw_build_transposed<8>(nullptr, a.dz_buf + (size_t)b0 * tc.dz_stride + T.dz_off, tc.dz_stride, a.B - b0, T.N_pad / 4, T.N_pad, Bhi, Blo,
+                           SBO, warp, lane);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -411,153 +417,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (tid == 0) {
         issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO), umma_desc(smem_u32(Alo), SBO), umma_desc(smem_u32(Bhi), SBO),
                      umma_desc(smem_u32(Blo), SBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
-        umma_commit(&mbar);
-    }
-    DW_TRACE(5);
-    mbar_wait(&mbar, 0);
-    tc_fence_after();
-    DW_TRACE(6);
-    // epilogue: accumulator row f = input feature (or the ones row), column o = output unit
-    float *part = a.partials + (size_t)chunk * a.P;
-    const int f = quad * 32 + lane;
-    for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
-        if (quad * 32 >= rowsA) break;
-        float v[32];
-        tmem_ld32_sum(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, tc.concat ? (uint32_t)T.N_pad : 0u, v);
-        if (f < rowsA) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int o = c0 + j;
-                if (o < T.N_real) {
-                    const bool vrow = o >= T.out_main;                                   // dueling value head row
-                    if (f < T.K_real) part[vrow ? T.w2_off + (o - T.out_main) * T.K_real + f : T.w_off + o * T.K_real + f] = v[j];
-                    else part[vrow ? T.b2_off + (o - T.out_main) : T.b_off + o] = v[j];
-                }
-            }
-        }
-    }
-    DW_TRACE(7);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
-    DW_TRACE(8);
-}
-
-// ------------------------------------------------------------------ split-K weight gradients, MN-major operands
-// dW_l^T[f][o] = sum_b [act_l ; 1][b][f] * dZ_l[b][o]: both operands are read with the reduction index b as the slow
-// one -- exactly the MN-major canonical layout (umma.cuh): a float4 of 4 consecutive features (outputs) of sample b is
-// ONE 16-byte SMEM store, consecutive lanes take consecutive samples (conflict-free), and every global load of a thread
-// is issued before the first is consumed.
-constexpr uint32_t kDwKStride = 128;                             // 8 samples x 16 B: core matrices adjacent in K are contiguous
-constexpr uint32_t kDwMnStride = (kDwChunk / 8) * kDwKStride;    // 2048 B per group of 4 features / outputs
-__global__ void __launch_bounds__(kTcThreads, 1) tc_dw_mn_kernel(TcNet tc, TcDwArgs a)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int l = blockIdx.x % tc.n_layers, chunk = blockIdx.x / tc.n_layers;
-    const TcLayer T = tc.L[l];
-    const int rowsA = T.K_real + 1;                            // input features + the all-ones row (bias gradient)
-    const int gA = (rowsA + 3) / 4, gB = T.N_pad / 4;           // 16-byte groups along MN
-    unsigned char *Ahi = smem, *Alo = Ahi + gA * kDwMnStride, *Bhi = Alo + gA * kDwMnStride, *Blo = Bhi + gB * kDwMnStride;
-    __shared__ uint64_t mbar;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ const float *rows[kDwChunk];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    DW_TRACE(0);
-    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
-    if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
-    const int b0 = chunk * kDwChunk;
-    if (tid < kDwChunk) {
-        const int b = b0 + tid;
-        const float *p = nullptr;
-        if (b < a.B) {
-            if (l == 0) {
-                uint32_t pkey[4];
-                Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
-                p = resolve_transition(a.src, b, tc.in_dim, pkey).s;
-            } else {
-                p = a.act_buf + (size_t)b * tc.act_stride + T.act_off;
-            }
-        }
-        rows[tid] = p;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
-    // PDL: hidden activations and dZ come from the training chain (the predecessor); the layer-0 CTAs' A operand is
-    // built from replay rows (written >= 2 kernels back) and is gathered before the wait
-    if (l != 0) { pdl_wait(); pdl_trigger(); }
-    DW_TRACE(1);
-    {   // A: K_real/4 feature groups x 128 samples, thread -> (sample = i % 128, group = i / 128)
-        const int fch = T.K_real / 4, total = kDwChunk * fch;   // K_real is a multiple of 4 (checked by tc_train_init)
-        constexpr int U = 13;                                   // 128 * 25 / 256 = 12.5 loads per thread for the 100-wide input
-        for (int i0 = tid; i0 < total; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < total) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= total) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                float4 h, lo4;
-                tf32_split(v[u].x, h.x, lo4.x); tf32_split(v[u].y, h.y, lo4.y); tf32_split(v[u].z, h.z, lo4.z); tf32_split(v[u].w, h.w, lo4.w);
-                const uint32_t off = (uint32_t)jc * kDwMnStride + (uint32_t)bl * 16u;
-                *reinterpret_cast<float4 *>(Ahi + off) = h;
-                *reinterpret_cast<float4 *>(Alo + off) = lo4;
-            }
-        }
-        // the ones row (feature index K_real, first element of the next group) and the zero rows after it
-        if (tid < kDwChunk) {
-            const uint32_t off = (uint32_t)(T.K_real / 4) * kDwMnStride + (uint32_t)tid * 16u;
-            *reinterpret_cast<float4 *>(Ahi + off) = make_float4(rows[tid] ? 1.f : 0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(Alo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    DW_TRACE(3);
-    if (l == 0) { pdl_wait(); pdl_trigger(); }
-    {   // B: N_pad/4 output groups x 128 samples
-        const int och = T.N_pad / 4, total = kDwChunk * och;
-        constexpr int U = 8;
-        for (int i0 = tid; i0 < total; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < total) {
-                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
-                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= total) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                float4 h, lo4;
-                tf32_split(v[u].x, h.x, lo4.x); tf32_split(v[u].y, h.y, lo4.y); tf32_split(v[u].z, h.z, lo4.z); tf32_split(v[u].w, h.w, lo4.w);
-                const uint32_t off = (uint32_t)jc * kDwMnStride + (uint32_t)bl * 16u;
-                *reinterpret_cast<float4 *>(Bhi + off) = h;
-                *reinterpret_cast<float4 *>(Blo + off) = lo4;
-            }
-        }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    DW_TRACE(4);
-    if (tid == 0) {
-        const bool sw = a.swap_desc != 0;
-        issue_3xtf32(tmem, umma_desc_mn(smem_u32(Ahi), kDwKStride, kDwMnStride, sw), umma_desc_mn(smem_u32(Alo), kDwKStride, kDwMnStride, sw),
-                     umma_desc_mn(smem_u32(Bhi), kDwKStride, kDwMnStride, sw), umma_desc_mn(smem_u32(Blo), kDwKStride, kDwMnStride, sw),
-                     kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0, true, kDwKStride);
         umma_commit(&mbar);
     }
     DW_TRACE(5);
@@ -601,27 +460,12 @@ static size_t dw_smem_bytes(const TcNet &tc)
     return mx;
 }
 
-static size_t dw_mn_smem_bytes(const TcNet &tc)
-{
-    size_t mx = 0;
-    for (int l = 0; l < tc.n_layers; ++l) {
-        const size_t gA = (size_t)(tc.L[l].K_real + 1 + 3) / 4, gB = (size_t)tc.L[l].N_pad / 4;
-        // the M = 128 instruction reads 32 feature groups from each A buffer and 2*N_pad/4 groups from B_hi: everything it can
-        // touch must lie inside the CTA's allocation
-        size_t b = 2 * (gA + gB) * kDwMnStride;
-        const size_t reach = (gA + 32) * kDwMnStride;           // A_lo start + 32 groups
-        if (reach > b) b = reach;
-        if (b > mx) mx = b;
-    }
-    return mx;
-}
-
 int tc_train_init(uavrl_learner *l)
 {
     l->tc_train_ok = false;
     const TcNet &tc = l->tc;
     for (int i = 0; i < tc.n_layers; ++i)
-        if (tc.L[i].K_real + 1 > 128) return 0;                  // no room for the ones row
+        if (tc.L[i].K_real + 1 > 128 || tc.L[i].K_real % 4 != 0) return 0;   // no room for the ones row / float4 feature chunks
     // the M=128 MMA reads 16 row groups from each A buffer: with fewer real rows it runs into the next buffers,
     // which must still be inside the CTA's allocation
     if (train_smem_bytes(tc, 32) > 227 * 1024 || dw_smem_bytes(tc) > 227 * 1024) return 0;
@@ -629,10 +473,6 @@ int tc_train_init(uavrl_learner *l)
     UAVRL_CUDA(cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
     UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
-    // MN-major operand variant (tc_dw_mn_kernel): experimental, results not yet validated -> opt-in only
-    l->dw_mn = getenv("UAVRL_DW_MN") != nullptr && dw_mn_smem_bytes(tc) <= 227 * 1024;
-    for (int i = 0; i < tc.n_layers; ++i) if (tc.L[i].K_real % 4 != 0) l->dw_mn = false;
-    if (l->dw_mn) UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_mn_smem_bytes(tc)));
     const size_t cap = (size_t)l->cfg.batch_size;
     UAVRL_CUDA(cudaMalloc((void **)&l->act_buf, cap * (size_t)(tc.act_stride > 0 ? tc.act_stride : 4) * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, cap * (size_t)tc.dz_stride * 4));
@@ -665,14 +505,8 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }
-    static const bool swap_desc = getenv("UAVRL_DW_SWAP") != nullptr;
-    d.swap_desc = swap_desc ? 1 : 0;
-    if (l->dw_mn)
-        UAVRL_CUDA(launch_kernel(tc_dw_mn_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_mn_smem_bytes(tc), st,
-                                 chain && !after_chain, tc, d));
-    else
-        UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
-                                 chain && !after_chain, tc, d));
+    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
+                             chain && !after_chain, tc, d));
     l->pdl_prev = chain ? kPdlDw : kPdlNone;
     UAVRL_LAUNCHED();
     if (trace_on) {

@@ -41,25 +41,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- MN-major operands (transposed inputs: the reduction index K is the slow one in memory).  Canonical no-swizzle
-// layout (cute::UMMA make_umma_desc<Major::MN>, INTERLEAVE): 16-byte units hold 4 consecutive MN elements; a core
-// matrix is 8 K-rows x 16 B, contiguous (K-row stride 16 B); core matrices adjacent in K are `k_stride` bytes apart
-// (descriptor LBO field), adjacent in MN (next 4 elements) `mn_stride` bytes apart (descriptor SBO field):
-//   element (mn, k) lives at  (mn/4)*mn_stride + (k/8)*k_stride + (k%8)*16 + (mn%4)*4.
-// One kind::tf32 instruction consumes K = 8 = one core matrix; the next K step starts k_stride further.
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t k_stride, uint32_t mn_stride, bool swap_fields)
-{
-    const uint32_t lbo = swap_fields ? mn_stride : k_stride, sbo = swap_fields ? k_stride : mn_stride;
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-// instruction descriptor with both operands MN-major (bits 15 / 16)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) { return umma_idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
-
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)   // whole warp, ncols power of 2 >= 32
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "r"(ncols) : "memory");
@@ -147,14 +128,13 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
 //   -> 2 instructions per K step instead of 3; the epilogue adds D[:, c] + D[:, N + c] (tmem_ld32_sum).
 //   !concat: hi*hi + hi*lo + lo*hi accumulate into the same N columns (3 instructions per K step).
 __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int M, int N,
-                                             int ksteps, bool concat, bool mn_major = false, uint32_t mn_k_stride = 0)
+                                             int ksteps, bool concat)
 {
-    const uint64_t kStep = mn_major ? (uint64_t)(mn_k_stride >> 4) : (uint64_t)((2 * kUmmaLBO) >> 4);
-    const uint32_t major = mn_major ? ((1u << 15) | (1u << 16)) : 0u;
-    const uint32_t idesc = umma_idesc_tf32(M, N) | major;
+    constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
+    const uint32_t idesc = umma_idesc_tf32(M, N);
     uint64_t da = a_hi, db = b_hi;
     if (concat) {
-        const uint32_t wide = umma_idesc_tf32(M, 2 * N) | major;
+        const uint32_t wide = umma_idesc_tf32(M, 2 * N);
         umma_tf32(d, da, db, wide, 0u);
         for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, wide, 1u); }
     } else {

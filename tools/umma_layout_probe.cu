@@ -9,6 +9,10 @@
 #include "../dqn-based-uav-3d_path_planer_b200/csrc/tma.cuh"
 #include "../dqn-based-uav-3d_path_planer_b200/csrc/umma.cuh"
 using namespace uavrl;
+// RESULT on B200 (gpurun_out/probe.txt, round 1): the K-major sanity mode reads element (mn, k) at float index
+// mn*4 + (k%4) + (k/4)*32 (LBO 128 B), as umma.cuh assumes; with a_major / b_major = 1 and layout_type 0 (no swizzle) the
+// instruction returns ZEROS for every (mn, k) and both LBO/SBO assignments: kind::tf32 does not read an unswizzled
+// MN-major operand.  The weight-gradient kernel therefore transposes in registers (tc_train.cu dw_build_transposed).
 
 constexpr int kFloats = 72 * 1024 / 4;          // probed region: 72 KB (M = 128 reads 32 groups x 2 KB = 64 KB)
 
