@@ -290,62 +290,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
 }
 
-// 4x4 transpose across an aligned group of 4 lanes: lane r holds row r (x..w = columns 0..3); returns column r.
-__device__ __forceinline__ float4 quad_transpose(float4 a, int lane)
-{
-    const int r = lane & 3, base = lane & ~3;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int sidx = (r - i) & 3;                          // what the lane at distance i wants from this lane
-        const float send = sidx == 0 ? a.x : sidx == 1 ? a.y : sidx == 2 ? a.z : a.w;
-        const int src = (r + i) & 3;
-        const float got = __shfl_sync(0xffffffffu, send, base | src);
-        if (src == 0) c0 = got; else if (src == 1) c1 = got; else if (src == 2) c2 = got; else c3 = got;
-    }
-    return make_float4(c0, c1, c2, c3);
-}
-
-// Transposed operand build of the weight-gradient kernel: out element (row = 4*jc + e, col = sample) from source rows
-// [sample][4*n_chunks floats].  Source = rows[] pointers (A) or base + sample*stride with n_valid rows (B).  U = warp
-// items per warp (all loads in flight).  See the call site for the lane mapping.
-template <int U>
-__device__ __forceinline__ void dw_build_transposed(const float *const *rows, const float *base, int stride, int n_valid, int n_chunks,
-                                                    int rows_real, unsigned char *hi_buf, unsigned char *lo_buf, uint32_t SBO, int warp,
-                                                    int lane)
-{
-    const int q = lane >> 3, jp = (lane >> 2) & 1, r = lane & 3;
-    const int items = ((n_chunks + 1) / 2) * (kDwChunk / 16);
-    for (int it0 = warp; it0 < items; it0 += (kTcThreads / 32) * U) {
-        float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u * (kTcThreads / 32);
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it < items) {
-                const int jc = 2 * (it / (kDwChunk / 16)) + jp, bl = 16 * (it % (kDwChunk / 16)) + 4 * q + r;
-                if (jc < n_chunks) {
-                    if (rows) { if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-                    else if (bl < n_valid) v[u] = *reinterpret_cast<const float4 *>(base + (size_t)bl * stride + 4 * jc);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u * (kTcThreads / 32);
-            const float4 x = quad_transpose(v[u], lane);       // every lane takes part in the shuffles
-            if (it >= items) continue;
-            const int jc = 2 * (it / (kDwChunk / 16)) + jp, f = 4 * jc + r;
-            if (f >= rows_real) continue;
-            float4 h, l4;
-            tf32_split(x.x, h.x, l4.x); tf32_split(x.y, h.y, l4.y); tf32_split(x.z, h.z, l4.z); tf32_split(x.w, h.w, l4.w);
-            const uint32_t off = umma_off(f, 16 * (it % (kDwChunk / 16)) + 4 * q, SBO);
-            *reinterpret_cast<float4 *>(hi_buf + off) = h;
-            *reinterpret_cast<float4 *>(lo_buf + off) = l4;
-        }
-    }
-}
-
 // ------------------------------------------------------------------ split-K weight gradients
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
 {
@@ -388,15 +332,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
 
-    // A = [act ; 1]^T : element (row f, col b); source rows are [sample][feature].  (MN-major tcgen05 operands would take
-    // the source as it is, but kind::tf32 reads zeros from an unswizzled MN-major layout -- tools/umma_layout_probe.cu --
-    // so the transposition is done here.)  A warp item = 16 samples x 2 feature chunks: lane = (sample quad q, chunk
-    // parity jp, r): each lane loads one float4 (4 features of its sample), the 4 lanes of a quad transpose their 4x4
-    // block with shuffles, and lane r stores features-row 4*jc + r for the quad's 4 samples as ONE 16-byte store.  A
-    // quarter-warp then covers 8 different rows (f & 7) of one core-matrix column: 128 contiguous bytes, no bank conflict
-    // (element-wise 4-byte stores were 8-way conflicted and made this phase the longest of the kernel).
+    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row; every
+    // load of a thread is in flight before the first is split / stored (one L2/HBM round trip per CTA).  The 4-byte
+    // transposing stores are 8-way bank conflicted and dominate this kernel (profiles/r01_tc_stage_trace.txt); tried and
+    // measured slower: a conflict-free scalar walk, a 4-lane shuffle transpose with 16-byte stores, and MN-major
+    // tcgen05 operands (kind::tf32 reads zeros from an unswizzled MN-major layout, tools/umma_layout_probe.cu).
     const int fch = (T.K_real + 3) / 4;
-    dw_build_transposed<13>(rows, nullptr, 0, 0, fch, T.K_real, Ahi, Alo, SBO, warp, lane);
+    {
+        constexpr int U = 13;                                  // 128 * 25 / 256 = 12.5 float4 per thread for the 100-wide input
+        for (int i0 = tid; i0 < kDwChunk * fch; i0 += U * kTcThreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= kDwChunk * fch) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int f = 4 * jc + e;
+                    if (f < T.K_real) {
+                        float hi, lo; tf32_split(vv[e], hi, lo);
+                        const uint32_t off = umma_off(f, bl, SBO);
+                        *reinterpret_cast<float *>(Ahi + off) = hi;
+                        *reinterpret_cast<float *>(Alo + off) = lo;
+                    }
+                }
+            }
+        }
+    }
     DW_TRACE(2);
     for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
         const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
@@ -406,9 +376,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
     DW_TRACE(3);
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    // B = dZ^T : element (row o, col b), same transposing build (source rows: the dZ scratch, N_pad floats per sample)
-    dw_build_transposed<8>(nullptr, a.dz_buf + (size_t)b0 * tc.dz_stride + T.dz_off, tc.dz_stride, a.B - b0, T.N_pad / 4, T.N_pad, Bhi, Blo,
-                           SBO, warp, lane);
+    // B = dZ^T : element (row o, col b)
+    const int och = T.N_pad / 4;
+    {
+        constexpr int U = 8;
+        for (int i0 = tid; i0 < kDwChunk * och; i0 += U * kTcThreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < kDwChunk * och) {
+                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
+                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kTcThreads;
+                if (i >= kDwChunk * och) continue;
+                const int bl = i % kDwChunk, jc = i / kDwChunk;
+                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float hi, lo; tf32_split(vv[e], hi, lo);
+                    const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+                    *reinterpret_cast<float *>(Bhi + off) = hi;
+                    *reinterpret_cast<float *>(Blo + off) = lo;
+                }
+            }
+        }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
