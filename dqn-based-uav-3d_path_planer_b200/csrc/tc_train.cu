@@ -39,6 +39,7 @@ struct TcDwArgs {
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_chunks][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
+    int32_t packed;                    // 1: LBO = 128 (core matrices packed, UAVRL_DW_PACKED), 0: skewed LBO = 144
 };
 #define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
@@ -298,7 +299,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     const TcLayer T = tc.L[l];
     const int rowsA = T.K_real + 1;                           // input features + the all-ones row (bias gradient)
     const int gA = (rowsA + 7) / 8, gB = T.N_pad / 8;
-    constexpr uint32_t SBO = umma_sbo(kDwChunk);               // K extent = 128 samples -> 4096 B per 8 rows
+    // K extent = 128 samples.  K-adjacent core matrices are spaced LBO = 144 B (128 + 16) instead of packed: the
+    // transposing 4-byte stores below walk the samples (K) for a fixed feature row, and with the 16-byte skew 32 consecutive
+    // samples land in 32 different banks (packed, they collide 8-way and the operand build dominates the kernel)
+    const uint32_t LBO = a.packed ? 128u : 144u;
+    const uint32_t SBO = (kDwChunk / 4) * LBO;                 // 4096 / 4608 B per 8 rows
     unsigned char *Ahi = smem, *Alo = Ahi + gA * SBO, *Bhi = Alo + gA * SBO, *Blo = Bhi + gB * SBO;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
                     const int f = 4 * jc + e;
                     if (f < T.K_real) {
                         float hi, lo; tf32_split(vv[e], hi, lo);
-                        const uint32_t off = umma_off(f, bl, SBO);
+                        const uint32_t off = umma_off(f, bl, SBO, LBO);
                         *reinterpret_cast<float *>(Ahi + off) = hi;
                         *reinterpret_cast<float *>(Alo + off) = lo;
                     }
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     DW_TRACE(2);
     for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
         const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
-        const uint32_t off = umma_off(f, bl, SBO);
+        const uint32_t off = umma_off(f, bl, SBO, LBO);
         *reinterpret_cast<float *>(Ahi + off) = (f == T.K_real && rows[bl]) ? 1.f : 0.f;
         *reinterpret_cast<float *>(Alo + off) = 0.f;
     }
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float hi, lo; tf32_split(vv[e], hi, lo);
-                    const uint32_t off = umma_off(4 * jc + e, bl, SBO);
+                    const uint32_t off = umma_off(4 * jc + e, bl, SBO, LBO);
                     *reinterpret_cast<float *>(Bhi + off) = hi;
                     *reinterpret_cast<float *>(Blo + off) = lo;
                 }
@@ -413,8 +418,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     tc_fence_after();
     DW_TRACE(4);
     if (tid == 0) {
-        issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO), umma_desc(smem_u32(Alo), SBO), umma_desc(smem_u32(Bhi), SBO),
-                     umma_desc(smem_u32(Blo), SBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
+        issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO, LBO), umma_desc(smem_u32(Alo), SBO, LBO), umma_desc(smem_u32(Bhi), SBO, LBO),
+                     umma_desc(smem_u32(Blo), SBO, LBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0, LBO);
         umma_commit(&mbar);
     }
     DW_TRACE(5);
@@ -452,7 +457,7 @@ static size_t dw_smem_bytes(const TcNet &tc)
 {
     size_t mx = 0;
     for (int l = 0; l < tc.n_layers; ++l) {
-        const size_t b = (size_t)2 * ((tc.L[l].K_real + 1 + 7) / 8 + tc.L[l].N_pad / 8) * umma_sbo(kDwChunk);
+        const size_t b = (size_t)2 * ((tc.L[l].K_real + 1 + 7) / 8 + tc.L[l].N_pad / 8) * (size_t)(kDwChunk / 4) * 144;
         if (b > mx) mx = b;
     }
     return mx;
@@ -500,6 +505,8 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
     d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
+    static const bool packed = getenv("UAVRL_DW_PACKED") != nullptr;
+    d.packed = packed ? 1 : 0;
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }

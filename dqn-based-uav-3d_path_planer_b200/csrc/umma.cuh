@@ -17,18 +17,18 @@ __host__ __device__ constexpr uint32_t umma_sbo(int k_pad) { return (uint32_t)(k
 __host__ __device__ constexpr uint32_t umma_tile_bytes(int rows, int k_pad) { return (uint32_t)(rows / 8) * umma_sbo(k_pad); }
 
 // byte offset of element (r, c) inside an operand tile
-__device__ __forceinline__ uint32_t umma_off(int r, int c, uint32_t sbo)
+__device__ __forceinline__ uint32_t umma_off(int r, int c, uint32_t sbo, uint32_t lbo = kUmmaLBO)
 {
-    return (uint32_t)(r >> 3) * sbo + (uint32_t)(c >> 2) * kUmmaLBO + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 3) * 4u;
+    return (uint32_t)(r >> 3) * sbo + (uint32_t)(c >> 2) * lbo + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 3) * 4u;
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 (no swizzle) [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo, uint32_t lbo = kUmmaLBO)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((kUmmaLBO >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
     return d;
@@ -128,9 +128,9 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
 //   -> 2 instructions per K step instead of 3; the epilogue adds D[:, c] + D[:, N + c] (tmem_ld32_sum).
 //   !concat: hi*hi + hi*lo + lo*hi accumulate into the same N columns (3 instructions per K step).
 __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int M, int N,
-                                             int ksteps, bool concat)
+                                             int ksteps, bool concat, uint32_t lbo = kUmmaLBO)
 {
-    constexpr uint64_t kStep = (2 * kUmmaLBO) >> 4;
+    const uint64_t kStep = (uint64_t)((2 * lbo) >> 4);
     const uint32_t idesc = umma_idesc_tf32(M, N);
     uint64_t da = a_hi, db = b_hi;
     if (concat) {
