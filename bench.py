@@ -347,6 +347,16 @@ def run_ours(a):
             ach = kernels[dom]["GBps"]
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": None}
+        # dram bytes per launch of the same kernel from the committed `ncu --set full` capture of this exact command
+        # (profiles/r01_ncu_traffic.json; only valid for the default workload it was captured on)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("envs") == N and tr.get("batch") == B and tr.get("net") == a.net and tr.get("algo") == a.algo and bool(tr.get("tc")) == bool(tc_on):
+                roof["traffic"] = tr["dram_bytes_per_launch"].get(dom)
+                roof["traffic_source"] = tr.get("source")
+        except (OSError, ValueError, KeyError):
+            pass
         roof["peak_source"] = pk["src"]
         roof["algorithmic_bytes_per_launch"] = alg_bytes[dom]
         out["roofline"] = roof

@@ -350,6 +350,8 @@ reduce_publish_kernel(int P, int nparts, int n_loss_parts, float inv_b, const fl
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
+    pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
+    pdl_trigger();
     float g = 0.f;
     if (i < P) {
         float acc[8];
@@ -410,6 +412,8 @@ allreduce_adam_kernel(AdamArgs a, float *const *peer_grads, int buf_off, const u
                       const int32_t *__restrict__ tc_hi, const int32_t *__restrict__ tc_lo, const int32_t *__restrict__ tc_hi2,
                       const int32_t *__restrict__ tc_lo2, float *__restrict__ loss_out)
 {
+    pdl_wait();                 // PDL: nothing may still read the weight images this kernel rewrites
+    pdl_trigger();
     if (threadIdx.x < a.world) {                                  // one thread per peer spins on that peer's flag
         while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) { }
     }
@@ -588,8 +592,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
     l->last_nparts = nparts;
     l->last_n_loss_parts = n_loss_parts;
     l->last_global_batch = global_batch;
-    if (partials_only) {
-        l->pdl_prev = kPdlNone;
+    if (partials_only) {                                        // the data-parallel pair follows (launch_update_dp)
         if (per_batch) return per_set(l, B, l->per.idx, nullptr, l->per.abs_err, 1, st);
         return 0;
     }     // the data-parallel pair that follows is launched plainly
@@ -655,19 +658,21 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
     l->flag_epoch += 1;
     const int P = l->net.P;
     const int buf_off = (int)((l->flag_epoch & 1u) * (unsigned)(P + 1));
-    reduce_publish_kernel<<<(P + 63) / 64, 256, 0, st>>>(P, l->last_nparts, l->last_n_loss_parts, 1.0f / (float)global_batch,
-                                                       l->partials, l->loss_partials, l->comm_grad + buf_off, l->comm_counter,
-                                                       l->peer_flag_dev, l->rank, l->world, l->flag_epoch);
+    const bool chain = l->pdl_chain && g_pdl.load();
+    UAVRL_CUDA(launch_kernel(reduce_publish_kernel, dim3((P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, P, l->last_nparts,
+                             l->last_n_loss_parts, 1.0f / (float)global_batch, l->partials, l->loss_partials, l->comm_grad + buf_off,
+                             l->comm_counter, l->peer_flag_dev, l->rank, l->world, l->flag_epoch));
     UAVRL_LAUNCHED();
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = P; a.apply = 1; a.world = l->world;
     fill_adam_args(l, a);
-    allreduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a, l->peer_grad_dev, buf_off, l->comm_flags, l->flag_epoch, l->grad,
-                                                         l->local, l->m, l->v, l->target, l->img_local, l->img_target, l->img_map,
-                                                         (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map,
-                                                         l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev);
+    UAVRL_CUDA(launch_kernel(allreduce_adam_kernel, dim3((P + 255) / 256), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a, l->peer_grad_dev,
+                             buf_off, l->comm_flags, l->flag_epoch, l->grad, l->local, l->m, l->v, l->target, l->img_local, l->img_target,
+                             l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map,
+                             l->tc_lo2_map, loss_out ? loss_out : l->loss_dev));
     UAVRL_LAUNCHED();
+    l->pdl_prev = chain ? kPdlAdam : kPdlNone;
     return 0;
 }
 
