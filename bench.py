@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
+    ap.add_argument("--fuse", type=int, default=1, help="1 = get_action + env step as one kernel on the tensor-core path (default), 0 = two kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -234,6 +235,7 @@ def run_ours(a):
             os.close(saved)
 
     _lib.lib().uavrl_set_pdl(int(a.pdl))
+    _lib.lib().uavrl_set_fuse_act_env(int(a.fuse))
     dims, b, p = load_city()
     city = engine.City(dims[0], dims[1], dims[2], b)
     params = engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
@@ -308,14 +310,16 @@ def run_ours(a):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64 env state / f32 obs+learner", "data": "synthetic",
                "config": dict(config_dict(a, world), qnet_path=("tcgen05 3xTF32 (fp32-grade)" if tc_on else "fp32 CUDA cores"),
-                              launch="programmatic dependent launch" if a.pdl else "serialised"),
+                              launch=("programmatic dependent launch" if a.pdl else "serialised")
+                              + (", get_action+step fused" if (a.fuse and tc_on) else "")),
                "clocks": clocks, "gpu_launches": int(launches),
                "host_wall_ms_per_step": 1e3 * t_wall / a.steps}
 
     # ---- roofline pass: per-kernel CUDA-event time (rank 0's GPU; same workload, events between kernels)
     if rank == 0:
         kp = engine.train_profile(env, L, min(a.steps, 200), a.eps) / float(min(a.steps, 200))   # ms per launch
-        names = ("act_eps_greedy", "env_step", "td_target", "fwd_bwd", "weight_grad", "reduce_adam")
+        fused = bool(a.fuse) and tc_on
+        names = ("act+env_step_fused" if fused else "act_eps_greedy", "env_step", "td_target", "fwd_bwd", "weight_grad", "reduce_adam")
         fwd = FWD_FLOPS[a.net]
         n_tgt = 1 if a.algo == "dqn" else 2          # target fwd (+ local fwd on s' for double DQN)
         # per sampled transition 4x fwd (DQN) / 5x fwd (DDQN) = target pass(es) + fwd on s + backward (2 fwd)
@@ -329,6 +333,9 @@ def run_ours(a):
                          "weight_grad": 0, "reduce_adam": 0}
             alg_bytes = {"act_eps_greedy": ACT_BYTES * N, "env_step": ENV_STEP_BYTES * N, "td_target": 0,
                          "fwd_bwd": TRANSITION_BYTES * B, "weight_grad": 0, "reduce_adam": 28 * L.P}
+        if fused:
+            for dct in (alg_flops, alg_bytes):
+                dct["act+env_step_fused"] = dct["act_eps_greedy"] + dct["env_step"]
         kernels = {}
         for n_, t_ in zip(names, kp):
             if t_ <= 0:

@@ -1,0 +1,187 @@
+// env_block.cuh -- the per-CTA body of the env step / observation kernel, callable from env_kernel (env.cu) and from
+// the fused act+step kernel (tc_forward.cu): EPB envs starting at e0, NT threads, shared-memory scratch passed in.
+// Phases and references: see env.cu.
+#pragma once
+#include "env.cuh"
+
+namespace uavrl {
+
+template <int EPB>
+struct EnvSmem {
+    Cyl cyl[kMaxCyl];
+    __align__(16) float obs[EPB][kObsDim];
+    double pos[3][EPB];
+    unsigned long long mask[EPB];
+};
+
+__device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
+{
+    const double *st = d.pool_start + (size_t)scen * 3;
+    const double *gl = d.pool_goal + (size_t)scen * 3;
+    const double *v0 = d.pool_v0 + (size_t)scen * 3;
+    s.px = st[0]; s.py = st[1]; s.pz = st[2];
+    s.gx = gl[0]; s.gy = gl[1]; s.gz = gl[2];
+    s.vx = v0[0]; s.vy = v0[1]; s.V = v0[2];
+    s.theta = angle_xy(s.vx, s.vy);
+    s.score = 0.0; s.total = 0.0; s.path_len = 0.0;
+    s.step = 0; s.cursor = 0; s.done = 0;
+    s.n_sub = d.pool_nsub[scen];
+    s.alias = d.pool_alias[scen];
+}
+
+__device__ __forceinline__ unsigned long long cull_mask(const EnvDev &d, const Cyl *cyl, double px, double py)
+{
+    unsigned long long m = 0ull;
+    for (int c = 0; c < d.k.n_cyl; ++c) {
+        const double reach = cyl[c].R + d.cull_w;
+        const bool near_x = fabs(px - cyl[c].cx) <= reach;
+        const bool near_y = fabs(py - cyl[c].cy) <= reach;
+        if (near_x && near_y) m |= (1ull << c);
+    }
+    return m;
+}
+
+__device__ __forceinline__ int threat_masked(const EnvConst &k, const Cyl *cyl, unsigned long long m,
+                                             double x, double y, double z)
+{
+    if (out_of_bounds(k, x, y, z)) return 1;
+    while (m) {
+        const int c = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (cyl_hit(cyl[c], x, y, z)) return 1;
+    }
+    return 0;
+}
+
+// USE_PDL: execute griddepcontrol.wait right before the actions are read (stand-alone kernel inside a PDL chain);
+// the fused kernel has already waited.
+template <bool DO_STEP, int EPB, int NT, bool USE_PDL>
+__device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int e0, int tid, int action_kind,
+                                          const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
+                                          uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
+                                          uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
+{
+    Cyl *s_cyl = sm.cyl;
+    float (*s_obs)[kObsDim] = sm.obs;
+    double (*s_pos)[EPB] = sm.pos;
+    unsigned long long *s_mask = sm.mask;
+    for (int i = tid; i < d.k.n_cyl * 6; i += NT)
+        reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
+    __syncthreads();
+    // PDL: the predecessor in the lockstep loops is the act kernel, which only writes `actions`; per-env state and
+    // the pool were last written by the previous env step.  Warp 0 loads its state first and waits just before it
+    // reads the action; the other warps have nothing to do until phase 2.
+    if (USE_PDL && tid >= 32) { pdl_wait(); pdl_trigger(); }
+
+    if (tid < 32) {
+        const int e = e0 + tid;
+        const bool valid = (tid < EPB) && (e < d.n);
+        unsigned long long mask = 0ull;
+        double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
+        int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
+        if (valid) {
+            EnvRegs s;
+            s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
+            s.vx = d.vx[e]; s.vy = d.vy[e]; s.V = d.V[e];
+            s.score = d.score[e]; s.total = d.total[e]; s.path_len = d.path_len[e];
+            s.gx = d.gx[e]; s.gy = d.gy[e]; s.gz = d.gz[e];
+            s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
+            s.done = d.done[e]; s.alias = d.alias[e];
+            s.theta = d.theta[e];
+            int scen = d.scen[e];
+            mask = cull_mask(d, s_cyl, s.px, s.py);
+            if (DO_STEP) {
+                if (USE_PDL) { pdl_wait(); pdl_trigger(); }
+                double act;
+                if (action_kind == UAVRL_ACT_CONT_F32) act = (double)static_cast<const float *>(actions)[e];
+                else if (action_kind == UAVRL_ACT_CONT_F64) act = static_cast<const double *>(actions)[e];
+                else if (action_kind == UAVRL_ACT_CONT_F32X2) act = (double)static_cast<const float *>(actions)[2 * e];
+                else act = (double)static_cast<const int32_t *>(actions)[e];
+                const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
+                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
+                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                const Cyl *cyl = s_cyl;
+                const EnvConst kk = d.k;
+                auto threat = [&kk, cyl, mask](double x, double y, double z) {
+                    return threat_masked(kk, cyl, mask, x, y, z);
+                };
+                StepOut o;
+                step_core(d.k, s, mode, act, sub, threat, o);
+                rew = o.reward;
+                n_stepped = 1; n_coll = o.coll; n_ended = s.done;
+                n_succ = (o.info == 1); n_lose = (o.info == 2);
+                if (reward) reward[e] = (float)o.reward;
+                d.rew64[e] = o.reward;
+                if (done_out) done_out[e] = (uint8_t)o.done_ret;
+                if (info_out) info_out[e] = (uint8_t)o.info;
+                if (coll_out) coll_out[e] = (uint8_t)o.coll;
+                if (ended_out) ended_out[e] = (uint8_t)s.done;
+                if (d.auto_reset && s.done) {                      // UAV.reset() at the episode boundary
+                    scen = (int)(((long long)scen + d.n) % d.P);
+                    load_scenario(d, scen, s);
+                    mask = cull_mask(d, s_cyl, s.px, s.py);
+                    d.scen[e] = scen;
+                    d.gx[e] = s.gx; d.gy[e] = s.gy; d.gz[e] = s.gz;
+                    d.n_sub[e] = s.n_sub;
+                }
+                d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
+                d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V; d.theta[e] = s.theta;
+                d.score[e] = s.score; d.total[e] = s.total; d.path_len[e] = s.path_len;
+                d.step[e] = s.step; d.cursor[e] = s.cursor;
+                d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
+            }
+            if (obs) {
+                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
+                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                obs_scalars(s, sub, &s_obs[tid][0]);
+            }
+            px = s.px; py = s.py; pz = s.pz;
+        }
+        if (tid < EPB) {
+            s_pos[0][tid] = px; s_pos[1][tid] = py; s_pos[2][tid] = pz;
+            s_mask[tid] = mask;
+        }
+        if (DO_STEP) {
+            const unsigned full = 0xffffffffu;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                n_stepped += __shfl_xor_sync(full, n_stepped, off);
+                n_ended += __shfl_xor_sync(full, n_ended, off);
+                n_coll += __shfl_xor_sync(full, n_coll, off);
+                n_succ += __shfl_xor_sync(full, n_succ, off);
+                n_lose += __shfl_xor_sync(full, n_lose, off);
+                rew += __shfl_xor_sync(full, rew, off);
+            }
+            if (tid == 0 && n_stepped) {
+                atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
+                if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
+                if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);
+                if (n_succ) atomicAdd(&d.stat_counts[3], (unsigned long long)n_succ);
+                if (n_lose) atomicAdd(&d.stat_counts[4], (unsigned long long)n_lose);
+                atomicAdd(d.stat_reward, rew);
+            }
+        }
+    }
+    __syncthreads();
+    if (!obs) return;
+
+    // phase 2: occupancy probes
+    for (int idx = tid; idx < EPB * 80; idx += NT) {
+        const int le = idx / 80, p = idx - 80 * le;
+        if (e0 + le >= d.n) break;
+        double x, y, z;
+        int slot;
+        probe_point(p, s_pos[0][le], s_pos[1][le], s_pos[2][le], x, y, z, slot);
+        s_obs[le][slot] = threat_masked(d.k, s_cyl, s_mask[le], x, y, z) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+
+    // phase 3: coalesced 16-byte stores of the contiguous [nvalid][100] tile
+    const int nvalid = min(EPB, d.n - e0);
+    const int nvec = nvalid * (kObsDim / 4);
+    float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)e0 * kObsDim);
+    const float4 *src = reinterpret_cast<const float4 *>(&s_obs[0][0]);
+    for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+}
+
+}  // namespace uavrl

@@ -507,6 +507,24 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
     return 0;
 }
 
+// Trainer.get_action + BaseEnv.Move_Agent for the lockstep loops in ONE kernel (tc_forward.cu, FUSE_ENV): each CTA steps
+// the envs whose actions it has just computed.  Returns 1 when the fused path is not available (tensor-core path off /
+// switched off): the caller then launches the two kernels.
+std::atomic<int> g_fuse_act_env{1};
+int launch_act_env(uavrl_learner *l, const EnvDev &d, const float *obs, float eps, int32_t *actions, float *obs_next, float *rew,
+                   uint8_t *done, cudaStream_t st)
+{
+    if (!(l->tc_ok && l->use_tc) || !g_fuse_act_env.load()) return 1;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.img = l->tc_img_local; a.obs = obs; a.n = d.n; a.n_tiles = (d.n + kTcTile - 1) / kTcTile; a.mode = kTcAct;
+    a.eps = eps; a.is_train = 1;
+    a.key = l->cfg.seed ^ 0xAC7ull; a.call = l->act_calls++; a.actions = actions;
+    EnvFuse ef;
+    ef.d = d; ef.obs_next = obs_next; ef.reward = rew; ef.done = done;
+    return launch_tc_forward(l, a, st, &ef);
+}
+
 static int launch_update_impl(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out, bool apply,
                               cudaStream_t st, cudaEvent_t *mid, bool partials_only = false);
 
@@ -877,6 +895,8 @@ int uavrl_replay_push(uavrl_learner *l, int32_t n, const float *obs, const int32
 
 int64_t uavrl_replay_size(const uavrl_learner *l) { return l ? l->count : 0; }
 
+int uavrl_set_fuse_act_env(int32_t on) { g_fuse_act_env.store(on ? 1 : 0); return 0; }
+
 int uavrl_replay_gather(uavrl_learner *l, int32_t n, const int64_t *idx, float *s, int32_t *a, float *r, float *s2,
                         uint8_t *d)
 {
@@ -907,7 +927,13 @@ int uavrl_replay_gather(uavrl_learner *l, int32_t n, const int64_t *idx, float *
 static int do_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_dev, bool apply, void *stream)
 {
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
-    return launch_update(l, src, B, global_batch, loss_dev, apply, (cudaStream_t)stream);
+    // one Trainer.update call = TD pass(es) -> training chain -> weight gradients -> optimiser: chain them with PDL
+    // (the first kernel is launched plainly: whatever precedes it on the stream is not ours)
+    const bool outer = l->pdl_chain;
+    if (!outer) { l->pdl_chain = true; l->pdl_prev = kPdlNone; }
+    const int rc = launch_update(l, src, B, global_batch, loss_dev, apply, (cudaStream_t)stream);
+    if (!outer) { l->pdl_chain = false; l->pdl_prev = kPdlNone; }
+    return rc;
 }
 
 int uavrl_learner_update(uavrl_learner *l, const int32_t *idx_tape_dev, float *loss_dev, void *stream)

@@ -222,6 +222,10 @@ __global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partial
 
 // generic MLP description: trunk widths + head = `head_main` rows (+ `head_extra` rows from a second parameter block)
 int build_mlp(int in_dim, int n_hidden, const int32_t *hidden, int head_main, int head_extra, NetDev &n);
+struct EnvDev;
+extern std::atomic<int> g_fuse_act_env;
+int launch_act_env(uavrl_learner *l, const EnvDev &d, const float *obs, float eps, int32_t *actions, float *obs_next, float *rew,
+                   uint8_t *done, cudaStream_t st);
 int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_train, const float *u_tape,
                const int32_t *rand_tape, int32_t *actions, float *q_out, cudaStream_t st);
 int launch_update(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, float *loss_out,

@@ -12,6 +12,7 @@
 // the next layer's A operand straight back into SMEM -- activations never touch HBM.  The head's epilogue
 // forms Q (dueling combine), then eps-greedy / argmax / max / gather depending on the mode.
 #include "tc_forward.cuh"
+#include "env_block.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -112,7 +113,10 @@ size_t tc_smem_bytes(const TcNet &tc) { return (size_t)2 * tc.a_bytes + (size_t)
 
 #define TC_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcArgs a)
+// FUSE_ENV: after a tile's actions are written, the same CTA steps those R envs (env_block.cuh) -- the act -> step
+// dependency is per env, so no grid-wide boundary is needed between Trainer.get_action and BaseEnv.Move_Agent.
+template <bool FUSE_ENV>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, TcArgs a, EnvFuse ef)
 {
     TC_TRACE(0);
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -314,6 +318,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
                 tc_fence_after();
             }
         }
+        if (FUSE_ENV) {
+            // the tile's actions are in global memory (written by this CTA before the barrier above)
+            __shared__ EnvSmem<32> env_sm;
+            for (int sb = 0; sb < R; sb += 32)
+                env_block<true, 32, kTcThreads, false>(ef.d, env_sm, base + sb, tid, UAVRL_ACT_DISCRETE27, a.actions, ef.obs_next,
+                                                       ef.reward, ef.done, nullptr, nullptr, nullptr);
+            __syncthreads();
+        }
     }
     TC_TRACE(20);
     tc_fence_before();
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(TcNet tc, TcA
     TC_TRACE(21);
 }
 
-int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
+int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st, const EnvFuse *fuse)
 {
     TcArgs a = a_in;
     a.rows_per_tile = (a.n >= 128 * 148) ? 128 : (a.n >= 64 * 148) ? 64 : 32;
@@ -343,8 +355,16 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st)
             a.pdl |= kPdlEarlyWeights;                             // neither the env step nor a TD pass writes weight images
         }
     }
-    UAVRL_CUDA(launch_kernel(tc_forward_kernel, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a));
-    l->pdl_prev = l->pdl_chain ? (a.mode == kTcAct ? kPdlAct : kPdlTd) : kPdlNone;
+    EnvFuse ef;
+    memset(&ef, 0, sizeof(ef));
+    if (fuse) {
+        ef = *fuse;
+        UAVRL_CUDA(launch_kernel(tc_forward_kernel_t<true>, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
+        l->pdl_prev = l->pdl_chain ? kPdlEnv : kPdlNone;
+    } else {
+        UAVRL_CUDA(launch_kernel(tc_forward_kernel_t<false>, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
+        l->pdl_prev = l->pdl_chain ? (a.mode == kTcAct ? kPdlAct : kPdlTd) : kPdlNone;
+    }
     UAVRL_LAUNCHED();
     if (trace_on) {
         long long h[32];
@@ -378,7 +398,8 @@ int tc_init(uavrl_learner *l)
     }
     UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)l->cfg.batch_size * 4));
-    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
     l->y_cap = l->cfg.batch_size;
     l->tc_ok = true;
     return tc_train_init(l);

@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 
+#include "env.cuh"
 #include "learner.cuh"
 
 namespace uavrl {
@@ -34,7 +35,9 @@ int tc_train_init(uavrl_learner *l);
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
                     int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain = nullptr);
 size_t tc_smem_bytes(const TcNet &tc);
-int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st);
+// the env step fused behind the act pass (tc_forward.cu): env batch + where the step writes
+struct EnvFuse { EnvDev d; float *obs_next; float *reward; uint8_t *done; };
+int launch_tc_forward(uavrl_learner *l, const TcArgs &a, cudaStream_t st, const EnvFuse *fuse = nullptr);
 int tc_init(uavrl_learner *l);        // builds the TC images/maps; leaves l->tc_ok = false when the net does not fit
 
 }  // namespace uavrl

@@ -41,12 +41,16 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
             if ((rc = launch_env_observe(env->d, obs_t, st))) return rc;
             l->frame0_valid = true;
         }
-        // Choose_Action2 -> Trainer.get_action (PathPlan_City.py:338-346)
-        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
-        // Move_Agent + replay add (PathPlan_City.py:371-382): reward/done land in the ring slots
-        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
-                                  l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
-        l->pdl_prev = kPdlEnv;
+        // Choose_Action2 -> Trainer.get_action (PathPlan_City.py:338-346), then Move_Agent + replay add (:371-382):
+        // reward/done land in the ring slots.  One fused kernel when the tensor-core path is on.
+        rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+            if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
+                                      l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
+            l->pdl_prev = kPdlEnv;
+        }
         lockstep_commit(l, st);
         if (do_update) {
             for (int u = 0; u < updates_per_iter; ++u) {  // PathPlan_City.update -> Trainer.update (:757-776)
@@ -95,10 +99,14 @@ extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_it
             if ((rc = launch_env_observe(env->d, obs_t, st))) return rc;
             l->frame0_valid = true;
         }
-        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
-        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
-                                  l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
-        l->pdl_prev = kPdlEnv;
+        rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+            if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
+                                      l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
+            l->pdl_prev = kPdlEnv;
+        }
         lockstep_commit(l, st);
         l->epoch += 1;
         // every rank must take part in every all-reduce: the caller warms the replay up first
@@ -125,9 +133,12 @@ extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_i
         lockstep_begin(l, &obs_t, &obs_next, &act, &rew, &done);
         cudaEvent_t *e = &ev[(size_t)it * NE];
         UAVRL_CUDA(cudaEventRecord(e[0], st));
-        if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+        rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);      // fused: slot 0 = act + step, slot 1 = 0
+        if (rc < 0) return rc;
+        const bool fused = (rc == 0);
+        if (!fused && (rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[1], st));
-        if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
+        if (!fused && (rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[2], st));
         lockstep_commit(l, st);
         l->epoch += 1;

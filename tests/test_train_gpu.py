@@ -76,15 +76,17 @@ def test_training_loop_learns_and_counts(env_golden, env27_golden):
 @pytest.mark.parametrize("algo", ["dqn", "ddqn"])
 def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo):
     """Programmatic dependent launch inside the loop (kernel k+1's prologue overlaps kernel k's tail,
-    uavrl_set_pdl) is a scheduling change only: 150 lockstep iterations with it on and off end in bit-identical
-    parameters, replay contents, env state and counters."""
+    uavrl_set_pdl) and the fused get_action + Move_Agent kernel (uavrl_set_fuse_act_env) are scheduling changes only:
+    150 lockstep iterations with every on/off combination end in bit-identical parameters, replay contents, env state
+    and counters."""
     from uavrl_b200 import _lib, engine
     city, params, _, _ = city_and_params(env_golden, env27_golden)
     N = 1024
     out = []
     try:
-        for pdl in (1, 0):
+        for pdl, fuse in ((1, 1), (0, 0), (1, 0), (0, 1)):          # the fused act+step kernel is the same kind of change
             _lib.lib().uavrl_set_pdl(pdl)
+            _lib.lib().uavrl_set_fuse_act_env(fuse)
             env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
             sc = env.make_scenarios(1024, seed=8)
             env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
@@ -103,8 +105,10 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
             env.close(); L.close()
     finally:
         _lib.lib().uavrl_set_pdl(1)
-    a, b = out
-    assert a["stats"][:6] == b["stats"][:6] and a["stats"][1] == 150 and a["stats"][7] == b["stats"][7]
-    assert abs(a["stats"][6] - b["stats"][6]) <= 1e-9 * abs(b["stats"][6])       # sum_reward: fp64 atomics, order-dependent
-    for k in ("p", "t", "s", "a", "r", "d", "px", "step"):
-        assert np.array_equal(a[k], b[k]), k
+        _lib.lib().uavrl_set_fuse_act_env(1)
+    a = out[0]
+    for b in out[1:]:
+        assert a["stats"][:6] == b["stats"][:6] and a["stats"][1] == 150 and a["stats"][7] == b["stats"][7]
+        assert abs(a["stats"][6] - b["stats"][6]) <= 1e-9 * abs(b["stats"][6])       # sum_reward: fp64 atomics, order-dependent
+        for k in ("p", "t", "s", "a", "r", "d", "px", "step"):
+            assert np.array_equal(a[k], b[k]), k
