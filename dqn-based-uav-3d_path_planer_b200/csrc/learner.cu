@@ -514,7 +514,7 @@ std::atomic<int> g_fuse_act_env{1};
 int launch_act_env(uavrl_learner *l, const EnvDev &d, const float *obs, float eps, int32_t *actions, float *obs_next, float *rew,
                    uint8_t *done, cudaStream_t st)
 {
-    if (!(l->tc_ok && l->use_tc) || !g_fuse_act_env.load()) return 1;
+    if (!(l->tc_ok && l->use_tc && l->fuse_ok) || !g_fuse_act_env.load()) return 1;
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.img = l->tc_img_local; a.obs = obs; a.n = d.n; a.n_tiles = (d.n + kTcTile - 1) / kTcTile; a.mode = kTcAct;

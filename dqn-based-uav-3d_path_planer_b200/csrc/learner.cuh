@@ -122,6 +122,7 @@ struct uavrl_learner {
     int64_t count = 0;                // valid transitions
     bool frame0_valid = false;
     // programmatic dependent launch chain of the lockstep loops (common.cuh)
+    bool fuse_ok = false;             // the fused get_action + step kernel fits (tc_forward.cu)
     bool pdl_chain = false;
     int pdl_prev = 0;
     // prioritised replay (per.cuh); off unless uavrl_per_enable was called

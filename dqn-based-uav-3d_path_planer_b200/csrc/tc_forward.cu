@@ -399,7 +399,13 @@ int tc_init(uavrl_learner *l)
     UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
-    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    {   // the fused act+step variant carries the env scratch as static shared memory on top: it must still fit one CTA
+        cudaFuncAttributes fa;
+        UAVRL_CUDA(cudaFuncGetAttributes(&fa, tc_forward_kernel_t<true>));
+        l->fuse_ok = fa.sharedSizeBytes + tc_smem_bytes(l->tc) <= (size_t)227 * 1024;
+        if (l->fuse_ok)
+            UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    }
     l->y_cap = l->cfg.batch_size;
     l->tc_ok = true;
     return tc_train_init(l);
