@@ -39,7 +39,7 @@ env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *_
            uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
 {
     __shared__ EnvSmem<EPB> sm;
-    env_block<DO_STEP, EPB, kEnvThreads, true>(d, sm, blockIdx.x * EPB, threadIdx.x, action_kind, actions, obs, reward, done_out,
+    env_block<DO_STEP, EPB, kEnvThreads, true, (EPB < 32 ? EPB : 32)>(d, sm, blockIdx.x * EPB, threadIdx.x, action_kind, actions, obs, reward, done_out,
                                                info_out, coll_out, ended_out);
 }
 

@@ -55,7 +55,9 @@ __device__ __forceinline__ int threat_masked(const EnvConst &k, const Cyl *cyl, 
 
 // USE_PDL: execute griddepcontrol.wait right before the actions are read (stand-alone kernel inside a PDL chain);
 // the fused kernel has already waited.
-template <bool DO_STEP, int EPB, int NT, bool USE_PDL>
+// LPW = envs per phase-1 warp: EPB / LPW warps run the fp64 chains of LPW envs each (one lane per env).  The chain is
+// latency bound, so few lanes on several warps (= several SM sub-partitions) finish sooner than 32 lanes on one warp.
+template <bool DO_STEP, int EPB, int NT, bool USE_PDL, int LPW>
 __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int e0, int tid, int action_kind,
                                           const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
                                           uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
@@ -71,11 +73,15 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     // PDL: the predecessor in the lockstep loops is the act kernel, which only writes `actions`; per-env state and
     // the pool were last written by the previous env step.  Warp 0 loads its state first and waits just before it
     // reads the action; the other warps have nothing to do until phase 2.
-    if (USE_PDL && tid >= 32) { pdl_wait(); pdl_trigger(); }
+    constexpr int NW1 = EPB / LPW;
+    static_assert(EPB % LPW == 0 && LPW <= 32 && NW1 * 32 <= NT, "phase-1 warp layout");
+    const int wp = tid >> 5, ln = tid & 31;
+    if (USE_PDL && wp >= NW1) { pdl_wait(); pdl_trigger(); }
 
-    if (tid < 32) {
-        const int e = e0 + tid;
-        const bool valid = (tid < EPB) && (e < d.n);
+    if (wp < NW1) {
+        const int le = wp * LPW + ln;                        // local env of this lane (valid lanes only)
+        const int e = e0 + le;
+        const bool valid = (ln < LPW) && (e < d.n);
         unsigned long long mask = 0ull;
         double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
         int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
@@ -133,13 +139,13 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             if (obs) {
                 const double *q = d.pool_sub + (size_t)scen * d.K * 3;
                 auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
-                obs_scalars(s, sub, &s_obs[tid][0]);
+                obs_scalars(s, sub, &s_obs[le][0]);
             }
             px = s.px; py = s.py; pz = s.pz;
         }
-        if (tid < EPB) {
-            s_pos[0][tid] = px; s_pos[1][tid] = py; s_pos[2][tid] = pz;
-            s_mask[tid] = mask;
+        if (ln < LPW) {
+            s_pos[0][le] = px; s_pos[1][le] = py; s_pos[2][le] = pz;
+            s_mask[le] = mask;
         }
         if (DO_STEP) {
             const unsigned full = 0xffffffffu;
@@ -152,7 +158,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 n_lose += __shfl_xor_sync(full, n_lose, off);
                 rew += __shfl_xor_sync(full, rew, off);
             }
-            if (tid == 0 && n_stepped) {
+            if (ln == 0 && n_stepped) {
                 atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
                 if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
                 if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             // the tile's actions are in global memory (written by this CTA before the barrier above)
             __shared__ EnvSmem<32> env_sm;
             for (int sb = 0; sb < R; sb += 32)
-                env_block<true, 32, kTcThreads, false>(ef.d, env_sm, base + sb, tid, UAVRL_ACT_DISCRETE27, a.actions, ef.obs_next,
+                env_block<true, 32, kTcThreads, false, 8>(ef.d, env_sm, base + sb, tid, UAVRL_ACT_DISCRETE27, a.actions, ef.obs_next,
                                                        ef.reward, ef.done, nullptr, nullptr, nullptr);
             __syncthreads();
         }
