@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
-    ap.add_argument("--fuse", type=int, default=1, help="1 = get_action + env step as one kernel on the tensor-core path (default), 0 = two kernels")
+    ap.add_argument("--fuse", type=int, default=0, help="1 = get_action + env step as one kernel on the tensor-core path, 0 = two PDL-chained kernels (default, faster)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -510,7 +510,9 @@ int launch_act(uavrl_learner *l, const float *obs, int n, float eps, int is_trai
 // Trainer.get_action + BaseEnv.Move_Agent for the lockstep loops in ONE kernel (tc_forward.cu, FUSE_ENV): each CTA steps
 // the envs whose actions it has just computed.  Returns 1 when the fused path is not available (tensor-core path off /
 // switched off): the caller then launches the two kernels.
-std::atomic<int> g_fuse_act_env{1};
+// Measured on B200 (profiles/r01_fused_act_env.txt): the fused kernel is ~4 % SLOWER than the two PDL-chained kernels at
+// 4096 envs and worse above (the stand-alone env kernel spreads its fp64 chains over 512 small CTAs) -> off by default.
+std::atomic<int> g_fuse_act_env{0};
 int launch_act_env(uavrl_learner *l, const EnvDev &d, const float *obs, float eps, int32_t *actions, float *obs_next, float *rew,
                    uint8_t *done, cudaStream_t st)
 {

@@ -320,7 +320,8 @@ int64_t uavrl_launch_count(void);
  * tail; results are unchanged).  Process-wide switch, default 1; 0 launches every kernel fully serialised. */
 int uavrl_set_pdl(int32_t on);
 /* Lockstep loops on the tensor-core path: get_action and Move_Agent as one kernel (each CTA steps the envs whose
- * actions it has just computed; results unchanged).  Process-wide switch, default 1. */
+ * actions it has just computed; results unchanged).  Process-wide switch, default 0: measured slower than the two
+ * kernels chained with programmatic dependent launch (profiles/r01_fused_act_env.txt). */
 int uavrl_set_fuse_act_env(int32_t on);
 
 #ifdef __cplusplus
