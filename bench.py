@@ -59,6 +59,7 @@ def parse():
                     help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
     ap.add_argument("--fuse", type=int, default=0, help="1 = get_action + env step as one kernel on the tensor-core path, 0 = two PDL-chained kernels (default, faster)")
+    ap.add_argument("--per", type=int, default=0, help="1 = prioritised replay (device SumTree equivalent) instead of uniform sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -132,7 +133,7 @@ def config_dict(a, world):
                         "1 update per lockstep step, replay %d transitions/GPU"
                         % (a.envs, world, a.algo.upper(), a.net, "-".join(map(str, NETS[a.net][0])), a.batch, a.replay),
             "envs_per_gpu": a.envs, "global_envs": a.envs * world, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
-            "net": a.net, "algo": a.algo, "replay_per_gpu": a.replay, "eps": a.eps, "scenario_pool": a.pool,
+            "net": a.net, "algo": a.algo, "replay_per_gpu": a.replay, "prioritised_replay": bool(getattr(a, "per", 0)), "eps": a.eps, "scenario_pool": a.pool,
             "parallelism": "dp%d (env shards + replay shards per GPU, %s)" % (world, "one-shot NVLink all-reduce fused into the Adam kernel" if a.dp == "fused" else "NCCL gradient all-reduce"),
             "l2": "replay ring %d MB/GPU > 126 MB L2, fully prefilled before timing; sampled rows come from all of it"
                   % (a.replay * 412 // 1000000)}
@@ -248,6 +249,8 @@ def run_ours(a):
     L = engine.Learner(OBS, hidden, 27, dueling, ALGOS[a.algo], lr=5e-4, gamma=0.99, batch_size=B, update_loop=3,
                        replay_capacity=a.replay, lockstep_envs=N, seed=1234 + rank, device=local)
     L.init_params(0)                       # same seed on every rank: replicas start identical
+    if a.per:
+        L.per_enable()
     tc_on = L.set_tensor_cores(bool(a.tc))
     stream = torch.cuda.current_stream(dev)
     if world > 1 and a.dp == "fused":
