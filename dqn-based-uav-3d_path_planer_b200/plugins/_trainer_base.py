@@ -43,7 +43,18 @@ class _ReplayFacade:
         self._t._add(states, actions, rewards, next_states, dones)
 
     def sample2(self, batch_size):
-        """random.sample(buffer, B) + stacking (replay_buffer.py:48-51); indices drawn on the host."""
+        """random.sample(buffer, B) + stacking (replay_buffer.py:48-51); indices drawn on the host.  With
+        IsPriority_Replay: ReplayTree.sample2 (:186-213) -- stratified draw on the device, returns the tree indices
+        (slot + capacity - 1) and the importance weights as the 6th / 7th element."""
+        if self._t.IsPriority_Replay:
+            t = self._t
+            slots, w = t._learner.per_sample(int(batch_size))
+            slots = slots.cpu().numpy().astype(np.int64)
+            n, cap = t._learner.replay_size(), t.replay_size
+            oldest = (t._head - n) % cap
+            s, a, r, s2, d = t._learner.gather((slots - oldest) % cap)
+            return (s, tuple(a.tolist()), tuple(r.tolist()), s2, tuple(bool(x) for x in d), (slots + cap - 1).tolist(),
+                    w.cpu().numpy().astype(np.float64))
         n = self._t._learner.replay_size()
         idx = np.random.default_rng(self._t._sample_calls).permutation(n)[:batch_size]
         self._t._sample_calls += 1
@@ -88,6 +99,12 @@ class TrainerB200:
         self._loss = torch.zeros(1, device=self._dev)
         self.loss = 0
         self._sample_calls = 0
+        self._head = 0                                   # next replay slot (SumTree.data_pointer)
+        self.IsPriority_Replay = int(None2Value(param.get('IsPriority_Replay'), 0))
+        if self.IsPriority_Replay:
+            if self.lockstep_envs == 0 and self.replay_size > 4 * 1024 * 1024:
+                raise ValueError("prioritised replay supports at most 4194304 slots")
+            self._learner.per_enable()                   # ReplayTree constants (replay_buffer.py:141-148)
         self.replay_memory = _ReplayFacade(self)
         self.model_dir = None2Value(param.get('model_path'), None)
         self.Load_Mod(self.model_dir)
@@ -120,11 +137,19 @@ class TrainerB200:
         r = torch.from_numpy(np.ascontiguousarray(rewards, np.float32).reshape(-1)).to(dev)
         d = torch.from_numpy(np.ascontiguousarray(dones).astype(np.uint8).reshape(-1)).to(dev)
         self._learner.push(s, a, r, s2, d)
+        slots = (self._head + np.arange(s.shape[0])) % self.replay_size
+        self._head = int((self._head + s.shape[0]) % self.replay_size)
+        return slots
 
     def Push_Replay(self, Experience, error=None):
         """(state, action, reward, next_state, done) tuple, tensors or arrays (PathPlan_City.py:374-379)."""
         s, a, r, s2, d = [x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in Experience]
-        self._add(s, a, r, s2, d)
+        slots = self._add(s, a, r, s2, d)
+        if self.IsPriority_Replay and error is not None:           # ReplayTree.push(sample, error) (:152-154)
+            e = error.detach().cpu().numpy() if isinstance(error, torch.Tensor) else np.asarray(error)
+            e = np.broadcast_to(np.abs(e.astype(np.float32)).reshape(-1), (len(slots),)) if e.size == 1 else np.abs(e.astype(np.float32)).reshape(-1)
+            self._learner.per_set_errors(torch.from_numpy(slots.astype(np.int32)).to(self._dev),
+                                         torch.from_numpy(np.ascontiguousarray(e)).to(self._dev), clip=False)
 
     # ---- learning
     def update(self, transition_dict):
@@ -141,7 +166,16 @@ class TrainerB200:
             a = torch.as_tensor(np.asarray(transition_dict['actions'], np.float32).astype(np.int32).reshape(-1)).to(dev)
             r = torch.as_tensor(np.asarray(transition_dict['rewards'], np.float32).reshape(-1)).to(dev)
             d = torch.as_tensor(np.asarray(transition_dict['dones'], np.float32).reshape(-1)).to(dev)
-            self._learner.update_batch(s, a, r, s2, d, self._loss)
+            idx, wts = transition_dict.get('idx'), transition_dict.get('weights')
+            if self.IsPriority_Replay and idx is not None and wts is not None:
+                # importance weights in the loss, then ReplayTree.batch_update(tree_idx, |TD error|) (SAC_Trainer.py:336-352)
+                w = torch.as_tensor(np.asarray(wts, np.float32).reshape(-1)).to(dev)
+                ae = torch.zeros(s.shape[0], dtype=torch.float32, device=dev)
+                self._learner.update_batch_per(s, a, r, s2, d, w, ae, self._loss)
+                slots = torch.as_tensor((np.asarray(idx, np.int64).reshape(-1) - (self.replay_size - 1)).astype(np.int32)).to(dev)
+                self._learner.per_set_errors(slots, ae, clip=True)
+            else:
+                self._learner.update_batch(s, a, r, s2, d, self._loss)
             self.loss = self._loss            # a 1-element tensor, like the reference's `self.loss = loss`
         self._maybe_save()
         return {'sum_epoch': self.epoch, 'loss': self.loss}

@@ -164,3 +164,36 @@ def test_sac_plugin_and_shipped_configuration(tmp_path):
     assert info["episodes"] >= 128 and info["env_steps"] == 128 * info["step"] and np.isfinite(info["loss"])
     ns, r, d, infos = env.Move_Agents(np.zeros(128, np.float32))
     assert ns.shape == (128, 100)
+
+
+def test_prioritised_replay_through_the_trainer_plugin():
+    """IsPriority_Replay = 1 (Trainer.xml:4): Push_Replay(exp, error), replay_memory.sample2 -> (..., idx, weights),
+    update(transition_dict) with them (loss weighted, priorities refreshed like ReplayTree.batch_update) and
+    learn_off_policy sampling through the tree."""
+    import importlib
+    from uavrl_b200.plugins import xmlconfig
+    tdict = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "Trainer_DDQN_B200.xml"))["Trainer"]
+    tdict.update(name="UAV_0", IsPriority_Replay="1", Batch_Size="64", replay_size="1000", save_loop="1000000", model_path="/nonexistent")
+    mod = importlib.import_module("uavrl_b200.plugins.DDQN_Trainer_B200")
+    tr = mod.DDQN_Trainer_B200(tdict)
+    rng = np.random.default_rng(0)
+    err = rng.gamma(1.5, 0.4, 300).astype(np.float32)
+    for i in range(300):
+        tr.Push_Replay((rng.standard_normal((1, 100)).astype(np.float32), [int(rng.integers(0, 27))], [[float(rng.standard_normal())]],
+                        rng.standard_normal((1, 100)).astype(np.float32), [[False]]), torch.tensor(err[i]))
+    leaves, total, beta = tr._learner.per_state(1000)
+    np.testing.assert_allclose(leaves[:300], (err + np.float32(0.01)) ** np.float32(0.6), rtol=3e-6)
+    assert (leaves[300:] == 0).all() and beta == 0.4
+    s, a, r, s2, d, idx, w = tr.replay_memory.sample2(64)
+    assert s.shape == (64, 100) and len(idx) == 64 and w.shape == (64,) and abs(w.max() - 1.0) < 1e-6 and (w > 0).all()
+    assert min(idx) >= 999 and max(idx) < 999 + 300                          # tree indices of filled leaves
+    res = tr.update({"states": s, "actions": a, "next_states": s2, "rewards": r, "dones": d, "idx": idx, "weights": w})
+    assert np.isfinite(float(res["loss"])) and res["sum_epoch"] == 1
+    after, _, beta2 = tr._learner.per_state(1000)
+    touched = np.unique(np.asarray(idx) - 999)
+    assert (after[touched] >= 0.01 ** 0.6 * (1 - 1e-5)).all() and (after[touched] <= 1 + 1e-6).all()
+    assert (after[touched] != leaves[touched]).any() and abs(beta2 - 0.401) < 1e-12
+    untouched = np.setdiff1d(np.arange(300), touched)
+    assert np.array_equal(after[untouched], leaves[untouched])
+    res = tr.learn_off_policy()
+    assert res["sum_epoch"] == 2 and np.isfinite(float(res["loss"]))
