@@ -147,7 +147,8 @@ class TrainerB200:
         slots = self._add(s, a, r, s2, d)
         if self.IsPriority_Replay and error is not None:           # ReplayTree.push(sample, error) (:152-154)
             e = error.detach().cpu().numpy() if isinstance(error, torch.Tensor) else np.asarray(error)
-            e = np.broadcast_to(np.abs(e.astype(np.float32)).reshape(-1), (len(slots),)) if e.size == 1 else np.abs(e.astype(np.float32)).reshape(-1)
+            e = np.abs(e.astype(np.float32)).reshape(-1)
+            e = np.full(len(slots), e[0], np.float32) if e.size == 1 else e
             self._learner.per_set_errors(torch.from_numpy(slots.astype(np.int32)).to(self._dev),
                                          torch.from_numpy(np.ascontiguousarray(e)).to(self._dev), clip=False)
 
