@@ -58,14 +58,31 @@ __global__ void __launch_bounds__(128) probe(const float *A, const float *B, flo
     long long t0 = 0;
     if (tid == 0) {
         const uint32_t idesc = umma_idesc_tf32(128, N);
+        // descriptors precomputed, K loop fully unrolled: the loop body is the bare instruction stream
+        uint64_t da[K / 8], db[K / 8]; uint32_t dta[K / 8];
+#pragma unroll
+        for (int k = 0; k < K / 8; ++k) {
+            da[k] = umma_desc(smem_u32(As) + k * 2 * kUmmaLBO, SBO); db[k] = umma_desc(smem_u32(Bs) + k * 2 * kUmmaLBO, SBO);
+            dta[k] = ta + (uint32_t)(8 * k);
+        }
         t0 = clock64();
-        for (int r = 0; r < reps; ++r)
-            for (int k = 0; k < K / 8; ++k) {
-                const uint64_t db = umma_desc(smem_u32(Bs) + k * 2 * kUmmaLBO, SBO);
-                const uint32_t acc = (r | k) ? 1u : 0u;
-                if (mode == 0) umma_tf32(tb, umma_desc(smem_u32(As) + k * 2 * kUmmaLBO, SBO), db, idesc, acc);
-                else umma_tf32_ta(tb, ta + (uint32_t)(8 * k), db, idesc, acc);
+        if (mode == 0) {
+            umma_tf32(tb, da[0], db[0], idesc, 0u);
+#pragma unroll
+            for (int k = 1; k < K / 8; ++k) umma_tf32(tb, da[k], db[k], idesc, 1u);
+            for (int r = 1; r < reps; ++r) {
+#pragma unroll
+                for (int k = 0; k < K / 8; ++k) umma_tf32(tb, da[k], db[k], idesc, 1u);
             }
+        } else {
+            umma_tf32_ta(tb, dta[0], db[0], idesc, 0u);
+#pragma unroll
+            for (int k = 1; k < K / 8; ++k) umma_tf32_ta(tb, dta[k], db[k], idesc, 1u);
+            for (int r = 1; r < reps; ++r) {
+#pragma unroll
+                for (int k = 0; k < K / 8; ++k) umma_tf32_ta(tb, dta[k], db[k], idesc, 1u);
+            }
+        }
         umma_commit(&bar);
     }
     mbar_wait(&bar, 0);
@@ -94,7 +111,7 @@ int main()
     const size_t smem = umma_tile_bytes(128, K) + umma_tile_bytes(N, K);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int mode = 0; mode < 2; ++mode) {
-        for (int reps : { 1, 16 }) {
+        for (int reps : { 1, 16, 64 }) {
             cudaMemset(dD, 0, D.size() * 4);
             probe<<<1, 128, smem>>>(dA, dB, dD, dC, mode, reps);
             cudaError_t e = cudaDeviceSynchronize();
