@@ -228,8 +228,7 @@ extern "C" int uavrl_env_generate_pool(uavrl_env *env, int32_t P, uint64_t seed,
     UAVRL_CUDA(cudaMalloc((void **)&failed, sizeof(int)));
     UAVRL_CUDA(cudaMemsetAsync(failed, 0, sizeof(int), st));
     const size_t smem = sizeof(WarpTree) * kRrtWarpsPerCta;          // 2 x 18 KB
-    static bool attr_set = false;
-    if (!attr_set) { UAVRL_CUDA(cudaFuncSetAttribute(rrt_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    UAVRL_CUDA(cudaFuncSetAttribute(rrt_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every call
     const int blocks = (P + kRrtWarpsPerCta - 1) / kRrtWarpsPerCta;
     rrt_pool_kernel<<<blocks, 32 * kRrtWarpsPerCta, smem, st>>>(c, seed, P, step, d.K, ps, pg, pv, pq, pn, pa, failed);
     UAVRL_LAUNCHED();
