@@ -84,6 +84,7 @@ SIGNATURES = {
     "uavrl_env_step": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP, VP]),
     "uavrl_env_step_host": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, VP, VP]),
     "uavrl_env_get_state": (C.c_int, [VP, C.POINTER(EnvStateHost)]),
+    "uavrl_env_set_state": (C.c_int, [VP, C.POINTER(EnvStateHost)]),
     "uavrl_env_threaten_rate": (C.c_int, [VP, C.c_int32, VP, VP]),
     "uavrl_learner_create": (C.c_int, [C.POINTER(LearnerConfig), C.POINTER(VP)]),
     "uavrl_learner_destroy": (C.c_int, [VP]),

@@ -59,6 +59,12 @@ __global__ void env_reset_kernel(EnvDev d, int first)
     d.done[e] = 0; d.alias[e] = (uint8_t)s.alias;
 }
 
+__global__ void env_theta_kernel(EnvDev d)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < d.n) d.theta[e] = angle_xy(d.vx[e], d.vy[e]);
+}
+
 __global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, uint8_t *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,6 +311,28 @@ int uavrl_env_get_state(uavrl_env *env, const uavrl_env_state_host *o)
         { o->cursor, d.cursor, 4 }, { o->scenario, d.scen, 4 }, { o->done, d.done, 1 } };
     for (auto &c : cp)
         if (c.dst) UAVRL_CUDA(cudaMemcpy(c.dst, c.src, n * c.sz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_env_set_state(uavrl_env *env, const uavrl_env_state_host *in)
+{
+    if (!env || !in) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_set_state before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    const EnvDev &d = env->d;
+    const size_t n = (size_t)d.n;
+    if (in->cursor || in->scenario)
+        return fail(UAVRL_ERR_INVALID, "cursor / scenario are owned by the scenario pool: set them through uavrl_env_set_pool + uavrl_env_reset");
+    struct { const void *src; void *dst; size_t sz; } cp[] = {
+        { in->px, d.px, 8 }, { in->py, d.py, 8 }, { in->pz, d.pz, 8 }, { in->vx, d.vx, 8 }, { in->vy, d.vy, 8 },
+        { in->V, d.V, 8 }, { in->score, d.score, 8 }, { in->total_score, d.total, 8 },
+        { in->path_len, d.path_len, 8 }, { in->step, d.step, 4 }, { in->done, d.done, 1 } };
+    for (auto &c : cp)
+        if (c.src) UAVRL_CUDA(cudaMemcpy(c.dst, c.src, n * c.sz, cudaMemcpyHostToDevice));
+    env_theta_kernel<<<(d.n + 127) / 128, 128>>>(d);            // the cached heading follows V_vector
+    UAVRL_LAUNCHED();
+    UAVRL_CUDA(cudaDeviceSynchronize());
     return 0;
 }
 

@@ -152,6 +152,24 @@ class EnvBatch:
         check(_lib.lib().uavrl_env_get_state(self.h, C.byref(st)))
         return out
 
+    def set_state(self, **arrays):
+        """Overwrite per-UAV state (px, py, pz, vx, vy, V, score, total_score, path_len: float64; step: int32; done: uint8)."""
+        st = _lib.EnvStateHost()
+        keep = []
+        for k, v in arrays.items():
+            if k in ("step",):
+                a, ct = np.ascontiguousarray(v, np.int32), C.c_int32
+            elif k == "done":
+                a, ct = np.ascontiguousarray(v, np.uint8), C.c_uint8
+            elif k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len"):
+                a, ct = np.ascontiguousarray(v, np.float64), C.c_double
+            else:
+                raise KeyError(k)
+            assert a.shape == (self.n,), (k, a.shape)
+            keep.append(a)
+            setattr(st, k, a.ctypes.data_as(C.POINTER(ct)))
+        check(_lib.lib().uavrl_env_set_state(self.h, C.byref(st)))
+
     def threaten_rate(self, pts):
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
         out = np.zeros(pts.shape[0], np.uint8)

@@ -122,6 +122,11 @@ typedef struct {
     uint8_t *done;
 } uavrl_env_state_host;
 int uavrl_env_get_state(uavrl_env *env, const uavrl_env_state_host *out);
+/* Overwrite per-UAV state from host arrays (NULL members are left alone): position, V_vector / V, Step, score,
+ * total_score, path_len, done -- the attributes UAV.reset / update_PathPlan maintain (Agents/UAV.py:335-366, 397-513);
+ * resume from a saved state, or start a step from a constructed one.  The sub-goal queue, goal and cursor belong to the
+ * scenario (uavrl_env_set_pool + uavrl_env_reset): cursor / scenario / reward64 must be NULL.  Synchronises the device. */
+int uavrl_env_set_state(uavrl_env *env, const uavrl_env_state_host *in);
 
 /* PathPlan_City.Threaten_rate (Envs/PathPlan_City.py:215-223) on arbitrary points (device kernel):
  * pts_host [n][3] -> out_host [n] u8. */

@@ -66,3 +66,17 @@ def test_env_core_matches_reference_goldens(shim, env_golden, env27_golden, whic
             assert np.array_equal(obs[0, 11:86], ep["obs"][t][11:86]) and np.array_equal(obs[0, 90:95], ep["obs"][t][90:95])
             steps += 1
     assert steps > 1000
+
+
+@pytest.mark.parametrize("prefix,mode", [("c_", 0), ("d_", 1)])
+def test_env_core_single_steps_next_to_every_decision_boundary(shim, env_golden, env27_golden, prefix, mode):
+    """The kernel's per-env source (host compile) on the constructed-state single steps of step_golden.npz."""
+    from conftest import check_step_outputs, step_batch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "step_golden.npz"))
+    d = env_golden["dims"]
+    city = O.OracleCity(d[0], d[1], d[2], env_golden["buildings"])
+    p = env_golden["uav_params"]
+    params = O.UavParams(p[0], p[1], p[2], float(env27_golden["climb_rate"]), int(p[3]))
+    b, n = step_batch(g, prefix, city, params)
+    rew, done, info, coll, obs = shim_step(shim, city, params, b, g[prefix + "action"].astype(np.float64), mode)
+    check_step_outputs(g, prefix, b, rew, done, info, coll, obs32=obs, exact=False)

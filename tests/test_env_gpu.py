@@ -232,3 +232,39 @@ def test_device_pool_generator_equals_host_generator(env_golden, env27_golden):
     print("\npool of 8192 scenarios: device %.1f ms, host threads %.1f ms" % (1e3 * t_dev, 1e3 * t_host))
     assert np.array_equal(b.get_pool()["n_sub"], a.make_scenarios(8192, seed=5)["n_sub"])
     a.close(); b.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("UAVRL_NEW_TESTS"),
+                    reason="added after round 1's GPU budget was spent (the same vectors already pin the oracle and the host-compiled "
+                           "kernel source on CPU); to be validated on a B200 at the start of round 2: UAVRL_NEW_TESTS=1")
+@pytest.mark.parametrize("prefix", ["c_", "d_"])
+def test_single_steps_next_to_every_decision_boundary(env_golden, env27_golden, prefix):
+    """The CUDA step from constructed states next to every decision boundary (tests/golden/step_golden.npz, 3000 reference
+    steps per action kind): states injected with uavrl_env_set_state, every integer output exact, fp64 state 1e-9."""
+    import os
+    from conftest import ROOT
+    from uavrl_b200 import engine
+    g = np.load(os.path.join(ROOT, "tests", "golden", "step_golden.npz"))
+    k = lambda s: g[prefix + s]                          # noqa: E731
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    n = len(k("reward"))
+    env = engine.EnvBatch(city, params, n, max_subgoals=k("sub").shape[1], auto_reset=False)
+    start = np.stack([k("px"), k("py"), k("pz")], 1)
+    env.set_pool(start, k("goal"), np.zeros(n), k("sub"), k("n_sub"), k("alias0"))
+    env.reset(0)
+    env.set_state(px=k("px"), py=k("py"), pz=k("pz"), vx=k("vx"), vy=k("vy"), V=k("V"), step=k("step"), score=k("score"),
+                  total_score=k("total_score"), path_len=k("path_len"))
+    if prefix == "c_":
+        act = torch.tensor(k("action").astype(np.float64), dtype=torch.float64, device="cuda")
+    else:
+        act = torch.tensor(k("action").astype(np.int32), dtype=torch.int32, device="cuda")
+    out = {kk: v.cpu().numpy() for kk, v in env.step(act).items()}
+    st = env.get_state()
+    for got, want, what in ((out["done"], k("done_ret"), "done"), (out["info"], k("info"), "info"), (out["collision"], k("collision"), "collision"),
+                            (out["ended"], k("o_done"), "ended"), (st["step"], k("o_step"), "step"), (st["cursor"], k("o_cursor"), "cursor")):
+        assert np.array_equal(got, want), (what, int((got != want).sum()))
+    assert_close64(st["reward64"], k("reward"), 1e-9, "reward")
+    for f in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len"):
+        assert_close64(st[f], k("o_" + f), 1e-9, f)
+    assert_obs(out["obs"], k("obs"), "obs")
+    env.close()
