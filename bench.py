@@ -9,12 +9,17 @@ followed by ONE DQN update (sample B transitions, TD target, MSE, backward, Adam
 target update) -- PathPlan_City.run_thread_OffPolicy + update (Envs/PathPlan_City.py:364-385,757-776).
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference ...                     (the CPU arm: the oracle port on all host threads)
+  python bench.py --impl reference ...                     (the CPU arm: the oracle port on the host threads)
 
-Prints ONE JSON line (rank 0).  value = whole-job env steps/s with inputs resident in HBM;
-e2e = the same iteration driven through host buffers at every plug-in boundary (H2D/D2H inside the
-timed region); roofline = dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json;
-cpu_baseline = the oracle port on the host cores (bounded sample).
+Prints ONE JSON line (rank 0).
+  value      whole-job env steps/s, inputs resident in HBM.  The K-step block (barrier + synchronize on both sides, CUDA
+             events, max over ranks) is REPEATED until the timed region is >= --min-seconds; value comes from the median block
+             (`repeats`, `block_ms_*` are printed), so the region is long enough for the clock sampler and the driver to see.
+  e2e        the same iteration through the reference-facing plug-in classes (PathPlan_City_B200 / DQN_Trainer_B200 built
+             from the XML configs) with HOST arrays at every boundary, H2D/D2H inside the timed region.
+  roofline   dominant kernel: algorithmic bytes|flops / CUDA-event time vs MEASURED_PEAKS.json.
+  cpu_baseline  the oracle port on the host cores (bounded sample) + the Python reference's own measured figure as context.
+  configs    sub-results for the other BASELINE configs that fit this launch (N=1: 16 384-env DuelingDQN and SAC; N=8: 65 536-env DDQN).
 """
 import argparse
 import json
@@ -26,25 +31,30 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import numpy as np  # noqa: E402
 
 OBS = 100
 NETS = {"qvalue3": ([64, 64], 0), "qnet2": ([64], 0), "vanet2": ([64], 1), "vanet3": ([128, 64], 1)}
+NET_XML = {"qvalue3": "QValueNet_SAC", "qnet2": "Qnet2", "vanet2": "VAnet2", "vanet3": "VAnet3"}
 ALGOS = {"dqn": 0, "ddqn": 1, "dueling": 2}
+TRAINER_XML = {"dqn": "DQN_Trainer_B200", "ddqn": "DDQN_Trainer_B200", "dueling": "DuelingDQN_Trainer_B200"}
 # algorithmic bytes / flops per unit
 ENV_STEP_BYTES = 563            # per env step (discrete action): obs 400 + reward 4 + flags 3 + action 4 + state r/w 128 + sub-goals 24
 ACT_BYTES = 404                 # per env: obs read 400 + action write 4
 TRANSITION_BYTES = 812          # per sampled transition
 FWD_FLOPS = {"qvalue3": 24448, "qnet2": 2 * (100 * 64 + 64 * 27), "vanet2": 2 * (100 * 64 + 64 * 28),
              "vanet3": 2 * (100 * 128 + 128 * 64 + 64 * 28)}
+PYTHON_REFERENCE = {"value": 100.0, "unit": "env_steps/s", "cores": 1, "kind": "python_reference",
+                    "sample": "the unmodified Python reference (simulator.StartAndTrain, shipped SAC config, render stubbed), measured at "
+                              "survey time on one core of an 8-vCPU Xeon 2.1 GHz container (BASELINE.md / SURVEY.md section 6): ~100 env steps/s "
+                              "with training, ~450 env-only; it is GIL-bound, cannot travel to the GPU box and is quoted as context only"}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1])")
@@ -60,9 +70,13 @@ def parse():
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
     ap.add_argument("--fuse", type=int, default=0, help="1 = get_action + env step as one kernel on the tensor-core path, 0 = two PDL-chained kernels (default, faster)")
     ap.add_argument("--per", type=int, default=0, help="1 = prioritised replay (device SumTree equivalent) instead of uniform sampling")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="the K-step block is repeated until the timed region is at least this long")
+    ap.add_argument("--max-repeats", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-results for the other BASELINE configs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--threads", type=int, default=0, help="CPU arm: host threads (0 = every CPU this process may run on)")
     return ap.parse_args()
 
 
@@ -80,9 +94,10 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of ONE GPU every 20 ms, started before the timed region's first barrier."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.idx, self.p, self.path = gpu_index, None, "/tmp/uavrl_clocks_%d.csv" % os.getpid()
@@ -96,7 +111,15 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        """number of lines written so far (the sampler starts before the region; samples from here on are 'under load')"""
+        try:
+            self.f.flush()
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
+
+    def stop(self, first_line=0):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.p:
             return out
@@ -106,8 +129,10 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
+        sm, mx, util, reasons = [], [], [], set()
+        for i, line in enumerate(open(self.path)):
+            if i < first_line:
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -118,8 +143,13 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+            try:
+                util.append(float(f[8]))
+            except (ValueError, IndexError):
+                pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       gpu_util_median=(statistics.median(util) if util else None))
         try:
             os.remove(self.path)
         except OSError:
@@ -139,26 +169,44 @@ def config_dict(a, world):
                   % (a.replay * 412 // 1000000)}
 
 
-# ============================================================================ CPU arm (oracle port)
+# ============================================================================ CPU arm (oracle port; never maps the product library)
+def usable_cpus():
+    """CPUs this process may actually run on: the affinity mask, capped by a cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
+def cpu_env(threads):
+    """Must run before liboracle.so (libgomp) is loaded: torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm is."""
+    n = threads if threads > 0 else usable_cpus()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "threads")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
+    return n
+
+
 def make_oracle_loop(a, n_envs, threads):
-    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    import uavrl_b200  # noqa: F401  (host-side scenario generator lives in the product library; no GPU needed)
-    from uavrl_b200 import _lib
-    dims, b, p = load_city()
-    nthreads = O.set_threads(threads)
-    cfg = _lib.EnvConfig()
-    cfg.n_envs, cfg.max_subgoals = 1, 64
-    cfg.len, cfg.width, cfg.h = dims
-    cfg.max_v, cfg.min_v, cfg.steering_angle, cfg.max_step, cfg.climb_rate = p[0], p[1], p[2], int(p[3]), 1.0
-    cfg.n_buildings, cfg.buildings_host = b.shape[0], b.ctypes.data_as(C.POINTER(C.c_double))
-    P = min(a.pool, 512)
-    sc = dict(start=np.zeros((P, 3)), goal=np.zeros((P, 3)), heading=np.zeros(P), sub=np.zeros((P, 64, 3)),
-              n_sub=np.zeros(P, np.int32))
-    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
-    rc = _lib.lib().uavrl_make_scenarios(C.byref(cfg), 42, P, 30, vp(sc["start"]), vp(sc["goal"]), vp(sc["heading"]),
-                                         vp(sc["sub"]), vp(sc["n_sub"]))
-    assert rc == 0
+    nthreads = O.set_threads(cpu_env(threads))
+    pool = np.load(os.path.join(ROOT, "oracle", "pool_512.npz"))        # committed scenarios (oracle/make_pool.py)
+    dims, b, p = pool["dims"], np.ascontiguousarray(pool["buildings"]), pool["uav_params"]
+    P = len(pool["n_sub"])
+    sub = np.zeros((P, 64, 3)); sub[:, :pool["sub"].shape[1]] = pool["sub"]
+    sc = dict(start=pool["start"], goal=pool["goal"], heading=pool["heading"], sub=sub, n_sub=pool["n_sub"])
     hidden, dueling = NETS[a.net]
     net = O.make_net(OBS, hidden, 27, dueling)
     rng = np.random.default_rng(0)
@@ -171,43 +219,233 @@ def make_oracle_loop(a, n_envs, threads):
 
 def cpu_baseline(a, seconds):
     """The oracle port timed on the host cores: bounded sample of the same workload."""
-    loop, nthreads = make_oracle_loop(a, a.envs, 0)
+    loop, nthreads = make_oracle_loop(a, a.envs, a.threads)
     loop.iteration(a.eps); loop.iteration(a.eps)                   # warm-up (fills the replay past Batch_Size)
     t0 = time.perf_counter(); it = 0
     while it < 3 or time.perf_counter() - t0 < seconds:
         loop.iteration(a.eps); it += 1
     dt = time.perf_counter() - t0
     return {"value": a.envs * it / dt, "unit": "env_steps/s", "updates_per_s": it / dt, "cores": nthreads,
-            "kind": "port",
+            "kind": "port", "usable_cpus": usable_cpus(), "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
             "sample": "%d lockstep iterations (%d envs each + 1 %s update, batch %d) of the C oracle port "
-                      "(oracle/*.c, OpenMP) in %.1f s" % (it, a.envs, a.algo.upper(), a.batch, dt)}
+                      "(oracle/*.c, OpenMP, %d threads) in %.1f s" % (it, a.envs, a.algo.upper(), a.batch, nthreads, dt),
+            "python_reference": PYTHON_REFERENCE}
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    loop, nthreads = make_oracle_loop(a, a.envs, 0)
+    loop, nthreads = make_oracle_loop(a, a.envs, a.threads)
     for _ in range(max(a.warmup, 2)):
         loop.iteration(a.eps)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        loop.iteration(a.eps)
-    dt = time.perf_counter() - t0
+    # the K-step block repeated like the GPU arm (median block), bounded to about --cpu-seconds x 3 of work
+    blocks, t_all0 = [], time.perf_counter()
+    while len(blocks) < 3 or (time.perf_counter() - t_all0 < 3 * a.cpu_seconds and len(blocks) < 9):
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            loop.iteration(a.eps)
+        blocks.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all0 > 6 * a.cpu_seconds:
+            break
+    dt = statistics.median(blocks)
     v = a.envs * a.steps / dt
-    sample = ("each step = one lockstep iteration of %d envs + 1 %s update (batch %d) on the oracle port "
-              "(C restatement of the Python reference; the Python reference itself cannot travel to the GPU box)"
-              % (a.envs, a.algo.upper(), a.batch))
+    sample = ("each step = one lockstep iteration of %d envs + 1 %s update (batch %d) on the oracle port, %d OpenMP threads "
+              "(C restatement of the Python reference; the Python reference itself cannot travel to the GPU box); "
+              "median of %d blocks of %d steps" % (a.envs, a.algo.upper(), a.batch, nthreads, len(blocks), a.steps))
     out = {"impl": "reference", "metric": "env steps/sec (+ DQN updates/sec), 500x500x100 city", "value": v,
            "unit": "env_steps/s", "updates_per_s": a.steps / dt, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "repeats": len(blocks), "block_s": blocks,
            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64 env / f32 learner", "data": "synthetic", "config": config_dict(a, 1),
-           "cpu_baseline": {"value": v, "unit": "env_steps/s", "cores": nthreads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": "env_steps/s", "cores": nthreads, "kind": "port", "sample": sample,
+                            "usable_cpus": usable_cpus(), "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
+                            "python_reference": PYTHON_REFERENCE},
            "e2e": {"value": v, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out, default=float), flush=True)
 
 
 # ============================================================================ GPU arm
+class Workload:
+    """env batch + learner of one BASELINE config on this rank's GPU, replay ring prefilled."""
+
+    def __init__(self, a, rank, world, local, dist):
+        import torch
+        import uavrl_b200  # noqa: F401
+        from uavrl_b200 import engine
+        self.a, self.rank, self.world, self.dist, self.engine, self.torch = a, rank, world, dist, engine, torch
+        dims, b, p = load_city()
+        city = engine.City(dims[0], dims[1], dims[2], b)
+        params = engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
+        N, B = a.envs, a.batch
+        self.env = engine.EnvBatch(city, params, N, max_subgoals=64, device=local, auto_reset=True)
+        sc = self.env.make_scenarios(a.pool, seed=42 + rank)
+        self.env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+        self.env.reset(0)
+        hidden, dueling = NETS[a.net]
+        self.L = engine.Learner(OBS, hidden, 27, dueling, ALGOS[a.algo], lr=5e-4, gamma=0.99, batch_size=B, update_loop=3,
+                                replay_capacity=a.replay, lockstep_envs=N, seed=1234 + rank, device=local)
+        self.L.init_params(0)                       # same seed on every rank: replicas start identical
+        if a.per:
+            self.L.per_enable()
+        self.tc_on = self.L.set_tensor_cores(bool(a.tc))
+        if world > 1 and a.dp == "fused":
+            self.L.connect_peers(dist, rank, world)
+        ring_frames = (a.replay + N - 1) // N + 1
+        engine.train_run(self.env, self.L, ring_frames, 1.0, 1, False, want_stats=False)     # prefill: sampling spans > L2 worth of rows
+
+    def iterate(self, k):
+        """k lockstep iterations.  1 GPU: the fused C loop.  N GPUs: env/act/ring per rank, local gradient, then the fused
+        one-shot NVLink all-reduce + Adam (or NCCL all-reduce + Adam with --dp nccl), identical step on every rank."""
+        a, engine = self.a, self.engine
+        if self.world == 1:
+            engine.train_run(self.env, self.L, k, a.eps, 1, True, want_stats=False)
+        elif a.dp == "fused":
+            engine.train_run_dp(self.env, self.L, k, a.eps, a.batch * self.world)
+        else:
+            gt = self.L.grad_tensor()
+            for _ in range(k):
+                engine.train_run(self.env, self.L, 1, a.eps, 1, False, want_stats=False)
+                self.L.compute_grads(a.batch * self.world)
+                self.dist.all_reduce(gt, op=self.dist.ReduceOp.SUM)
+                self.L.apply_grads()
+
+    def close(self):
+        self.L.close(); self.env.close()
+
+
+def timed_blocks(wl, a, dev, local, stream, barrier, sampler=None):
+    """Repeat the K-step block (barrier + synchronize on both sides, CUDA events on the launching stream) until the timed
+    region is >= --min-seconds.  Returns per-block ms (max over ranks), wall seconds of the region, sampler mark."""
+    import torch
+    world, dist = wl.world, wl.dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # pilot block: decides the repeat count (same on every rank)
+    barrier()
+    e0.record(stream); wl.iterate(a.steps); e1.record(stream)
+    barrier()
+    pilot = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+    repeats = int(min(a.max_repeats, max(3, np.ceil(a.min_seconds * 1e3 / max(float(pilot.item()), 1e-3)))))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
+    mark = sampler.mark() if sampler else 0
+    barrier()
+    t0 = time.perf_counter()
+    for s, e in evs:
+        s.record(stream)
+        wl.iterate(a.steps)
+        e.record(stream)
+        barrier()                                   # barrier + synchronize: the block is bracketed on both sides
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([s.elapsed_time(e) for s, e in evs], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # every block: max over ranks
+    return ms.cpu().numpy(), wall, mark
+
+
+def measure_config(a_sub, rank, world, local, dist, dev, stream, barrier, label):
+    """One sub-result (another BASELINE config) with the same timing discipline; returns a small dict (rank 0) or None."""
+    wl = Workload(a_sub, rank, world, local, dist)
+    wl.iterate(max(a_sub.warmup, 3))
+    ms, wall, _ = timed_blocks(wl, a_sub, dev, local, stream, barrier)
+    med = float(np.median(ms))
+    out = {"label": label, "value": a_sub.envs * world * a_sub.steps / (med * 1e-3), "unit": "env_steps/s",
+           "updates_per_s": a_sub.steps / (med * 1e-3), "ms_per_step": med / a_sub.steps, "repeats": int(len(ms)),
+           "timed_region_s": wall, "n_gpus": world, "config": config_dict(a_sub, world), "tensor_cores": bool(wl.tc_on)}
+    wl.close()
+    return out if rank == 0 else None
+
+
+def measure_sac(a, local, dev, stream, label):
+    """BASELINE configs[4]: SAC continuous, 16 384 envs, 1 GPU."""
+    import torch
+    from uavrl_b200 import engine
+    dims, b, p = load_city()
+    city = engine.City(dims[0], dims[1], dims[2], b)
+    params = engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
+    N = 16384
+    env = engine.EnvBatch(city, params, N, max_subgoals=64, device=local, auto_reset=True)
+    sc = env.make_scenarios(a.pool, seed=42)
+    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    env.reset(0)
+    L = engine.SacLearner(100, 64, 2, 1.0, 1e-4, 1e-3, 1e-4, 1.0, 0.99, 0.05, batch_size=N, replay_capacity=a.replay,
+                          lockstep_envs=N, seed=7, device=local)
+    L.init_params(0)
+    engine.sac_train_run(env, L, (a.replay + N - 1) // N + 1, False, want_stats=False)
+    engine.sac_train_run(env, L, 5, True, want_stats=False)
+    torch.cuda.synchronize(dev)
+    K = max(5, min(a.steps, 50))
+    times = []
+    t0 = time.perf_counter()
+    while len(times) < 3 or time.perf_counter() - t0 < 0.5:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        engine.sac_train_run(env, L, K, True, want_stats=False)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+    med = statistics.median(times)
+    out = {"label": label, "value": N * K / (med * 1e-3), "unit": "env_steps/s", "updates_per_s": K / (med * 1e-3), "ms_per_step": med / K,
+           "repeats": len(times), "n_gpus": 1,
+           "config": {"workload": "%d envs, continuous update_PathPlan, SAC actor 100-64-(2,2) + 2 critics 102-64-64-2, batch %d, replay %d (> L2), "
+                                  "1 update / lockstep iteration" % (N, N, a.replay)}}
+    L.close(); env.close()
+    return out
+
+
+class PluginE2E:
+    """The e2e loop: the reference-facing plug-in classes built from the XML configs the way EnvFactory / TrainerFactory
+    build them, driven per step with HOST arrays at every boundary (PathPlan_City_B200.run_step_OffPolicy =
+    run_thread_OffPolicy + update for all UAVs)."""
+
+    def __init__(self, a, rank, world, local, dist):
+        import importlib
+        from uavrl_b200.plugins import xmlconfig
+        cwd = os.getcwd()
+        os.chdir(ROOT)
+        try:
+            cfg = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "PathPlan_City_B200.xml"))["simulator"]
+            ed = cfg["env"]
+            ed["num_UAV"], ed["scenario_pool"], ed["device"], ed["host_driven"], ed["seed"] = str(a.envs), str(a.pool), str(local), "1", str(42 + rank)
+            ed["Agent"]["Trainer"]["Trainer_path"] = os.path.join(ROOT, "configs", "Trainer_%s_B200.xml" % {"dqn": "DQN", "ddqn": "DDQN", "dueling": "DuelingDQN"}[a.algo])
+            mod = importlib.import_module("uavrl_b200.plugins." + ed["Env_Type"])
+            # trainer hyper-parameters of this workload (the XML ships the reference's Batch_Size 64 / replay 10 000)
+            self._patch = dict(Batch_Size=str(a.batch), replay_size=str(64 * a.envs), NetWork=NET_XML[a.net], save_loop="1000000000", model_path="/tmp/uavrl_bench_mod_%d" % os.getpid())
+            orig = xmlconfig.XML2Dict
+
+            def patched(path):
+                d = orig(path)
+                if "Trainer" in d and isinstance(d["Trainer"], dict):
+                    d["Trainer"].update(self._patch)
+                return d
+            mod.XML2Dict = patched
+            try:
+                self.env = getattr(mod, ed["Env_Type"])(ed)
+            finally:
+                mod.XML2Dict = orig
+        finally:
+            os.chdir(cwd)
+        self.tr = self.env.Trainer
+        assert type(self.tr).__name__ == TRAINER_XML[a.algo]
+        if world > 1:
+            self.tr.attach_dist(dist, rank, world)
+        N = a.envs
+        ob = N * OBS * 4
+        # per step: get_action (obs in, actions out) + Move_Agent (actions in; obs, reward, done, info out) + replay add (s, a, r, s2, d in) + update (loss out)
+        self.h2d_bytes = ob + N * 4 + (2 * ob + N * 4 + N * 4 + N)
+        self.d2h_bytes = N * 4 + (ob + N * 4 + N + N) + 4
+        self.state = self.env.states()
+        self.loss = 0.0
+
+    def run(self, iters, eps):
+        for _ in range(iters):
+            self.state, r, d, info, res = self.env.run_step_OffPolicy(eps, self.state)
+            lt = res["loss"]
+            self.loss = float(lt) if not hasattr(lt, "item") else float(lt.item())      # device -> host read of the step's result
+        return self.loss
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -221,6 +459,8 @@ def run_ours(a):
         a.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    sampler.start()                                   # every rank samples its own GPU; the fork is far from any timed region
     if world > 1:
         # NCCL prints its version banner on fd 1 at communicator creation: park stdout on stderr meanwhile so that
         # this process's stdout carries the ONE JSON line only
@@ -237,72 +477,29 @@ def run_ours(a):
 
     _lib.lib().uavrl_set_pdl(int(a.pdl))
     _lib.lib().uavrl_set_fuse_act_env(int(a.fuse))
-    dims, b, p = load_city()
-    city = engine.City(dims[0], dims[1], dims[2], b)
-    params = engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
     N, B = a.envs, a.batch
-    env = engine.EnvBatch(city, params, N, max_subgoals=64, device=local, auto_reset=True)
-    sc = env.make_scenarios(a.pool, seed=42 + rank)
-    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
-    env.reset(0)
-    hidden, dueling = NETS[a.net]
-    L = engine.Learner(OBS, hidden, 27, dueling, ALGOS[a.algo], lr=5e-4, gamma=0.99, batch_size=B, update_loop=3,
-                       replay_capacity=a.replay, lockstep_envs=N, seed=1234 + rank, device=local)
-    L.init_params(0)                       # same seed on every rank: replicas start identical
-    if a.per:
-        L.per_enable()
-    tc_on = L.set_tensor_cores(bool(a.tc))
     stream = torch.cuda.current_stream(dev)
-    if world > 1 and a.dp == "fused":
-        L.connect_peers(dist, rank, world)
-
-    def iterate(k):
-        """k lockstep iterations.  1 GPU: the fused C loop.  N GPUs: env/act/ring per rank, local gradient,
-        NCCL all-reduce of the gradient vector, identical Adam step on every rank."""
-        if world == 1:
-            engine.train_run(env, L, k, a.eps, 1, True, want_stats=False)
-            return
-        if a.dp == "fused":
-            engine.train_run_dp(env, L, k, a.eps, B * world)
-            return
-        gt = L.grad_tensor()
-        for _ in range(k):
-            engine.train_run(env, L, 1, a.eps, 1, False, want_stats=False)
-            L.compute_grads(B * world)
-            dist.all_reduce(gt, op=dist.ReduceOp.SUM)
-            L.apply_grads()
-
-    # prefill the replay ring so that sampling spans > L2 worth of rows
-    ring_frames = (a.replay + N - 1) // N + 1
-    engine.train_run(env, L, ring_frames, 1.0, 1, False, want_stats=False)
-    iterate(max(a.warmup, 3))
-    torch.cuda.synchronize(dev)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local)
+    wl = Workload(a, rank, world, local, dist if world > 1 else None)
+    env, L, tc_on = wl.env, wl.L, wl.tc_on
+    wl.iterate(max(a.warmup, 3))
+    torch.cuda.synchronize(dev)
+
     launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t_wall0 = time.perf_counter()
-    e0.record(stream)
-    iterate(a.steps)
-    e1.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms_blocks, t_wall, mark = timed_blocks(wl, a, dev, local, stream, barrier, sampler)
+    clocks = sampler.stop(mark)
+    launches_per_block = (_lib.launch_count() - launches0) / float(len(ms_blocks) + 1)       # pilot + repeats, all identical
+    ms = float(np.median(ms_blocks))
     value = N * world * a.steps / (ms * 1e-3)
+    if world > 1:       # every rank's clock record, gathered
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        clocks = dict(allc[0], per_rank=[{k: c.get(k) for k in ("sm_mhz", "sm_min_mhz", "reasons", "samples")} for c in allc])
 
     out = None
     if rank == 0:
@@ -310,17 +507,23 @@ def run_ours(a):
         out = {"metric": "env steps/sec (+ DQN updates/sec), 500x500x100 city", "value": value, "unit": "env_steps/s",
                "updates_per_s": a.steps / (ms * 1e-3), "samples_per_s": a.steps * B * world / (ms * 1e-3),
                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
+               "repeats": int(len(ms_blocks)), "block_ms_median": ms, "block_ms_min": float(ms_blocks.min()), "block_ms_max": float(ms_blocks.max()),
+               "timed_region_s": t_wall,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64 env state / f32 obs+learner", "data": "synthetic",
                "config": dict(config_dict(a, world), qnet_path=("tcgen05 3xTF32 (fp32-grade)" if tc_on else "fp32 CUDA cores"),
                               launch=("programmatic dependent launch" if a.pdl else "serialised")
-                              + (", get_action+step fused" if (a.fuse and tc_on) else "")),
-               "clocks": clocks, "gpu_launches": int(launches),
-               "host_wall_ms_per_step": 1e3 * t_wall / a.steps}
+                              + (", get_action+step fused" if (a.fuse and tc_on) else ""),
+                              timing="the %d-step block (barrier + synchronize both sides, CUDA events, max over ranks) repeated %d times; "
+                                     "value = median block" % (a.steps, len(ms_blocks))),
+               "clocks": clocks, "gpu_launches": int(round(launches_per_block)),
+               "gpu_launches_timed_region": int(round(launches_per_block * len(ms_blocks))),
+               "host_wall_ms_per_step": 1e3 * t_wall / (a.steps * len(ms_blocks))}
 
     # ---- roofline pass: per-kernel CUDA-event time (rank 0's GPU; same workload, events between kernels)
     if rank == 0:
-        kp = engine.train_profile(env, L, min(a.steps, 200), a.eps) / float(min(a.steps, 200))   # ms per launch
+        n_prof = max(50, min(a.steps, 200))
+        kp = engine.train_profile(env, L, n_prof, a.eps) / float(n_prof)   # ms per launch
         fused = bool(a.fuse) and tc_on
         names = ("act+env_step_fused" if fused else "act_eps_greedy", "env_step", "td_target", "fwd_bwd", "weight_grad", "reduce_adam")
         fwd = FWD_FLOPS[a.net]
@@ -358,11 +561,13 @@ def run_ours(a):
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": None}
         # dram bytes per launch of the same kernel from the committed `ncu --set full` capture of this exact command
-        # (profiles/r01_ncu_traffic.json; only valid for the default workload it was captured on)
+        # (profiles/r02_ncu_traffic.json; only valid for the workload it was captured on, replay size included)
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
                 tr = json.load(f)
-            if tr.get("envs") == N and tr.get("batch") == B and tr.get("net") == a.net and tr.get("algo") == a.algo and bool(tr.get("tc")) == bool(tc_on):
+            same = (tr.get("envs") == N and tr.get("batch") == B and tr.get("net") == a.net and tr.get("algo") == a.algo
+                    and bool(tr.get("tc")) == bool(tc_on) and tr.get("replay") == a.replay)
+            if same:
                 roof["traffic"] = tr["dram_bytes_per_launch"].get(dom)
                 roof["traffic_source"] = tr.get("source")
         except (OSError, ValueError, KeyError):
@@ -371,29 +576,56 @@ def run_ours(a):
         roof["algorithmic_bytes_per_launch"] = alg_bytes[dom]
         out["roofline"] = roof
         out["kernels"] = kernels
+        # the whole iteration against HBM: algorithmic bytes of all six kernels / the timed iteration
+        tot_bytes = sum(alg_bytes[k] for k in kernels)
+        out["iteration_hbm"] = {"algorithmic_bytes": tot_bytes, "GBps": tot_bytes / (ms / a.steps * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": tot_bytes / (ms / a.steps * 1e-3) / 1e9 / pk["hbm"]}
 
-    # ---- e2e: the same iteration driven through host buffers at every plug-in boundary
+    # ---- e2e: the same iteration through the plug-in classes, host arrays at every boundary
     if not a.no_e2e:
-        from uavrl_b200.plugin_loop import HostDrivenLoop
-        hl = HostDrivenLoop(env, L, world, dist if world > 1 else None)
-        ke = max(10, min(a.steps, 100))
-        hl.run(3, a.eps)
+        pe = PluginE2E(a, rank, world, local, dist if world > 1 else None)
+        pe.run(5, a.eps)                     # fills the replay past Batch_Size, warms the pinned rings
         barrier()
-        e0.record(stream)
-        t0 = time.perf_counter()
-        hl.run(ke, a.eps)
-        e1.record(stream)
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        ke = max(20, min(a.steps, 100))
+        blocks = []
+        t_all = time.perf_counter()
+        while len(blocks) < 3 or time.perf_counter() - t_all < 0.5:
+            barrier()
+            t0 = time.perf_counter()
+            pe.run(ke, a.eps)
+            torch.cuda.synchronize(dev)
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            blocks.append(float(dt.item()))
+            if world > 1:       # same number of blocks on every rank
+                go = torch.tensor([1.0 if (len(blocks) < 3 or time.perf_counter() - t_all < 0.5) else 0.0], device=dev)
+                dist.broadcast(go, 0)
+                if go.item() == 0.0:
+                    break
+        dt = statistics.median(blocks)
         if rank == 0:
-            out["e2e"] = {"value": N * world * ke / dt, "unit": "env_steps/s", "h2d_bytes_per_step": hl.h2d_bytes,
-                          "d2h_bytes_per_step": hl.d2h_bytes, "steps": ke, "ms_per_step": 1e3 * dt / ke,
-                          "what": "per step: get_action(host obs)->host actions, Move_Agent(host actions)->host obs/reward/done, "
-                                  "replay add from host arrays, update()->host loss; pinned host memory, copies inside the timed region"}
+            out["e2e"] = {"value": N * world * ke / dt, "unit": "env_steps/s", "h2d_bytes_per_step": pe.h2d_bytes,
+                          "d2h_bytes_per_step": pe.d2h_bytes, "steps": ke, "repeats": len(blocks), "ms_per_step": 1e3 * dt / ke,
+                          "what": "per step through PathPlan_City_B200.run_step_OffPolicy + %s (plug-in classes built from configs/*.xml): "
+                                  "get_action(host obs)->host actions, Move_Agent(host actions)->host obs/reward/done/info, replay add from host "
+                                  "arrays, update()->host loss; pinned host memory, copies inside the timed region%s"
+                                  % (TRAINER_XML[a.algo], "; gradient exchange = the fused NVLink all-reduce + Adam" if world > 1 else "")}
+
+    # ---- the other BASELINE configs that fit this launch
+    if not a.no_configs:
+        subs = {}
+        if world == 1:
+            a2 = argparse.Namespace(**vars(a)); a2.envs = a2.batch = 16384; a2.net, a2.algo = "vanet2", "dueling"; a2.min_seconds = 0.5
+            subs["configs[2]"] = measure_config(a2, rank, world, local, None, dev, stream, barrier,
+                                                "16384 envs, DuelingDQN (VAnet2), buildings.xml obstacle set, 1xB200")
+            subs["configs[4]"] = measure_sac(a, local, dev, stream, "16384 envs, SAC_Trainer continuous-action UAV (actor+2 critics), 1xB200")
+        if world == 8:
+            a3 = argparse.Namespace(**vars(a)); a3.envs = a3.batch = 8192; a3.net, a3.algo = "qvalue3", "ddqn"; a3.min_seconds = 0.5
+            subs["configs[3]"] = measure_config(a3, rank, world, local, dist, dev, stream, barrier,
+                                                "65536 envs (8192/GPU), DDQN, replay buffer 1M/GPU, grad allreduce across 8xB200")
+        if rank == 0 and subs:
+            out["configs"] = subs
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
@@ -402,8 +634,7 @@ def run_ours(a):
     sys.stdout.flush()
     if world > 1:
         dist.barrier(device_ids=[local])
-    L.close()
-    env.close()
+    wl.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -412,6 +643,7 @@ if __name__ == "__main__":
     args = parse()
     if args.batch <= 0:
         args.batch = args.envs
+    cpu_env(args.threads)                   # before anything loads an OpenMP runtime (the oracle legs read it)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -104,6 +104,7 @@ SIGNATURES = {
     "uavrl_learner_apply_grads": (C.c_int, [VP, VP]),
     "uavrl_learner_hard_update": (C.c_int, [VP, VP]),
     "uavrl_learner_lockstep_restart": (C.c_int, [VP]),
+    "uavrl_learner_set_is_train": (C.c_int, [VP, C.c_int32]),
     "uavrl_learner_set_tensor_cores": (C.c_int, [VP, C.c_int32]),
     "uavrl_learner_comm_init": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
     "uavrl_learner_comm_connect": (C.c_int, [VP, VP, VP]),

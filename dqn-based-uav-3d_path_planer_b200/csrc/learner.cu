@@ -520,7 +520,7 @@ int launch_act_env(uavrl_learner *l, const EnvDev &d, const float *obs, float ep
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.img = l->tc_img_local; a.obs = obs; a.n = d.n; a.n_tiles = (d.n + kTcTile - 1) / kTcTile; a.mode = kTcAct;
-    a.eps = eps; a.is_train = 1;
+    a.eps = eps; a.is_train = l->is_train;
     a.key = l->cfg.seed ^ 0xAC7ull; a.call = l->act_calls++; a.actions = actions;
     EnvFuse ef;
     ef.d = d; ef.obs_next = obs_next; ef.reward = rew; ef.done = done;
@@ -1028,6 +1028,13 @@ int uavrl_learner_set_tensor_cores(uavrl_learner *l, int32_t enable)
     if (!l) return 0;
     l->use_tc = enable != 0;
     return (l->tc_ok && l->use_tc) ? 1 : 0;
+}
+
+int uavrl_learner_set_is_train(uavrl_learner *l, int32_t is_train)
+{
+    if (!l) return fail(UAVRL_ERR_INVALID, "null learner");
+    l->is_train = is_train ? 1 : 0;
+    return 0;
 }
 
 int uavrl_learner_lockstep_restart(uavrl_learner *l)

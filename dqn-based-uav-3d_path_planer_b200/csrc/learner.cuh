@@ -95,6 +95,7 @@ struct uavrl_learner {
     uavrl::TcNet tc;
     bool tc_ok = false;
     bool use_tc = true;               // runtime switch (uavrl_learner_set_tensor_cores): false = fp32 CUDA-core path
+    int32_t is_train = 1;             // Trainer.Is_Train for the lockstep loops (uavrl_learner_set_is_train): 0 = always greedy
     unsigned char *tc_img_local = nullptr, *tc_img_target = nullptr;
     int32_t *tc_hi_map = nullptr, *tc_lo_map = nullptr;   // flat param index -> float index in the TC image (-1: none)
     float *y_buf = nullptr;           // [batch_size] TD targets produced by the tensor-core pass

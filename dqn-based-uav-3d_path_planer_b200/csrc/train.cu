@@ -46,7 +46,7 @@ extern "C" int uavrl_train_run(uavrl_env *env, uavrl_learner *l, int32_t n_iters
         rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);
         if (rc < 0) return rc;
         if (rc == 1) {
-            if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+            if ((rc = launch_act(l, obs_t, env->d.n, eps, l->is_train, nullptr, nullptr, act, nullptr, st))) return rc;
             if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
                                       l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
             l->pdl_prev = kPdlEnv;
@@ -102,7 +102,7 @@ extern "C" int uavrl_train_run_dp(uavrl_env *env, uavrl_learner *l, int32_t n_it
         rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);
         if (rc < 0) return rc;
         if (rc == 1) {
-            if ((rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+            if ((rc = launch_act(l, obs_t, env->d.n, eps, l->is_train, nullptr, nullptr, act, nullptr, st))) return rc;
             if ((rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st,
                                       l->pdl_prev == kPdlAct && g_pdl.load()))) return rc;
             l->pdl_prev = kPdlEnv;
@@ -136,7 +136,7 @@ extern "C" int uavrl_train_profile(uavrl_env *env, uavrl_learner *l, int32_t n_i
         rc = launch_act_env(l, env->d, obs_t, eps, act, obs_next, rew, done, st);      // fused: slot 0 = act + step, slot 1 = 0
         if (rc < 0) return rc;
         const bool fused = (rc == 0);
-        if (!fused && (rc = launch_act(l, obs_t, env->d.n, eps, 1, nullptr, nullptr, act, nullptr, st))) return rc;
+        if (!fused && (rc = launch_act(l, obs_t, env->d.n, eps, l->is_train, nullptr, nullptr, act, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[1], st));
         if (!fused && (rc = launch_env_step(env->d, UAVRL_ACT_DISCRETE27, act, obs_next, rew, done, nullptr, nullptr, nullptr, st))) return rc;
         UAVRL_CUDA(cudaEventRecord(e[2], st));

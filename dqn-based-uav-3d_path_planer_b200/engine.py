@@ -355,6 +355,10 @@ class Learner:
     def lockstep_restart(self):
         check(_lib.lib().uavrl_learner_lockstep_restart(self.h))
 
+    def set_is_train(self, is_train):
+        """Trainer.Is_Train for the lockstep loops: False = get_action is always greedy (DuelingDQN_Trainer.py:90)."""
+        check(_lib.lib().uavrl_learner_set_is_train(self.h, int(bool(is_train))))
+
 
 class _DevView:
     """Expose a raw device pointer as a torch tensor through __cuda_array_interface__."""

@@ -104,7 +104,11 @@ class PathPlan_City_B200:
         tpath = os.path.normpath(agents_params['Trainer']['Trainer_path'])
         tdict = XML2Dict(tpath).get('Trainer')
         tdict['name'] = 'UAV_0'
-        tdict['lockstep_envs'] = str(self.num_UAV)
+        # host_driven = 1: the per-step methods (states / Move_Agents / Trainer.get_action / replay_memory.add / update) carry
+        # HOST arrays across every boundary like the reference's own objects, and the trainer keeps the generic replay store;
+        # 0 (default): run_eposide drives the device-resident lockstep loop (observations go straight into the replay ring)
+        self.host_driven = int(None2Value(param.get('host_driven'), 0))
+        tdict['lockstep_envs'] = '0' if self.host_driven else str(self.num_UAV)
         tdict['device'] = str(self.device_index)
         ttype = tdict.get('Trainer_Type')
         try:
@@ -132,20 +136,57 @@ class PathPlan_City_B200:
         self._next_first = (self._next_first + self.num_UAV) % self.pool_size
         self.Trainer._learner_reset_lockstep()
 
-    def states(self):
-        return self.batch.observe().cpu().numpy()
+    def _host_out(self):
+        """Pinned host staging for the step outputs, a ring of 4 sets (see TrainerB200._pinned): the arrays returned by
+        states() / Move_Agents() are numpy views of these buffers and stay valid for the next 3 calls."""
+        if not hasattr(self, "_hbuf"):
+            N = self.num_UAV
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)  # noqa: E731
+            self._hbuf = [dict(obs=mk((N, engine.OBS_DIM), torch.float32), reward=mk((N,), torch.float32), done=mk((N,), torch.uint8),
+                               info=mk((N,), torch.uint8)) for _ in range(4)]
+            dev = self.batch.device
+            self._dbuf = dict(obs=torch.empty((N, engine.OBS_DIM), dtype=torch.float32, device=dev),
+                              reward=torch.empty(N, dtype=torch.float32, device=dev), done=torch.empty(N, dtype=torch.uint8, device=dev),
+                              info=torch.empty(N, dtype=torch.uint8, device=dev))
+            self._hturn = 0
+        self._hturn = (self._hturn + 1) % 4
+        return self._hbuf[self._hturn]
 
-    def Move_Agents(self, actions):
+    def states(self):
+        h = self._host_out()
+        self.batch.observe(self._dbuf["obs"])
+        h["obs"].copy_(self._dbuf["obs"], non_blocking=True)
+        torch.cuda.current_stream(self.batch.device).synchronize()
+        return h["obs"].numpy()
+
+    def Move_Agents(self, actions, want_info_names=True):
         """BaseEnv.Move_Agent for every UAV: actions [N] (int32 indices or float32 steering) ->
         (next_states [N,100], rewards [N], dones [N], infos [N])."""
         a = np.asarray(actions)
-        if self.discrete:
-            t = torch.from_numpy(a.astype(np.int32)).cuda(self.device_index)
-        else:
-            t = torch.from_numpy(a.astype(np.float32)).cuda(self.device_index)
-        out = self.batch.step(t)
-        infos = [engine.INFO_NAMES[i] for i in out["info"].cpu().numpy()]
-        return out["obs"].cpu().numpy(), out["reward"].cpu().numpy(), out["done"].cpu().numpy().astype(bool), infos
+        a = np.ascontiguousarray(a, np.int32 if self.discrete else np.float32)
+        t = torch.from_numpy(a).to(self.batch.device, non_blocking=True)
+        h = self._host_out()
+        self.batch.step(t, out=self._dbuf)
+        for k in ("obs", "reward", "done", "info"):
+            h[k].copy_(self._dbuf[k], non_blocking=True)
+        torch.cuda.current_stream(self.batch.device).synchronize()
+        infos = h["info"].numpy()
+        if want_info_names:
+            infos = [engine.INFO_NAMES[i] for i in infos]
+        return h["obs"].numpy(), h["reward"].numpy(), h["done"].numpy().view(np.bool_), infos
+
+    # ---- one lockstep step with HOST arrays at every boundary (PathPlan_City.run_thread_OffPolicy :364-385 + update :757-776,
+    #      for all UAVs at once): state -> Trainer.get_action -> Move_Agent -> replay add -> sample -> Trainer.update
+    def run_step_OffPolicy(self, eps_rate, state=None):
+        if not self.host_driven:
+            raise ValueError("run_step_OffPolicy needs <host_driven>1</host_driven> (the lockstep ring belongs to run_eposide)")
+        tr = self.Trainer
+        s = self.states() if state is None else state                          # uav.state()
+        a = tr.get_action(s, eps_rate)                                          # Choose_Action2 -> Trainer.get_action
+        s2, r, d, info = self.Move_Agents(a, want_info_names=False)             # Move_Agent -> update + state
+        tr.replay_memory.add_batch(s, a, r, s2, d)                              # replay_memory.add (:380-382)
+        res = tr.learn_off_policy()                                             # sample + Trainer.update (:383-385, :757-776)
+        return s2, r, d, info, res
 
     def Check_uav_Done(self):
         return bool(self.batch.get_state()["done"].all())
@@ -164,15 +205,28 @@ class PathPlan_City_B200:
         is_sac = isinstance(learner, engine.SacLearner)
         if is_sac == self.discrete:
             raise ValueError("SAC needs update_function_name = update_PathPlan (continuous); the DQN family needs update_PathPlan27")
+        if self.host_driven:
+            raise ValueError("run_eposide drives the device-resident lockstep loop: construct without host_driven")
         t0 = time.time()
+        save_loop = int(getattr(self.Trainer, "save_loop", 0) or 0)
         ended = steps = updates = coll = n_s = n_l = 0
         reward_sum, loss, chunk, iters = 0.0, 0.0, 16, 0
         max_iters = 64 * self.uav_params.max_step
         while ended < self.num_UAV and iters < max_iters:
+            e_before = self.Trainer.epoch
             if is_sac:
                 st = engine.sac_train_run(self.batch, learner, chunk, bool(self.Trainer.Is_Train))
             else:
+                # Is_Train = 0: get_action is greedy whatever eps is (uavrl_learner_set_is_train, set by the trainer plug-in)
                 st = engine.train_run(self.batch, learner, chunk, eps_rate, 1, bool(self.Trainer.Is_Train))
+            if not self.Trainer.Is_Train and not is_sac:
+                # Trainer.update counts epochs whether or not it trains (DuelingDQN_Trainer.py:152)
+                e, t = learner.counters()
+                learner.set_counters(e_before + chunk, t)
+            # the reference saves inside Trainer.update every save_loop epochs (DuelingDQN_Trainer.py:187-188, SAC_Trainer.py:436-437);
+            # the device loop advances `chunk` epochs per call: save whenever a multiple of save_loop was crossed
+            if save_loop > 0 and self.Trainer.epoch // save_loop != e_before // save_loop:
+                self.Trainer.save()
             ended += st.episodes_ended; steps += st.env_steps; updates += st.updates; coll += st.collisions
             n_s += st.n_success; n_l += st.n_lose; reward_sum += st.sum_reward; loss = st.last_loss
             iters += chunk

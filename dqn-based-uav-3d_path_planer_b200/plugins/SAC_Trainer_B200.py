@@ -121,24 +121,36 @@ class SAC_Trainer_B200:
         if not all(os.path.exists(p) for p in paths):
             return
         try:
-            epoch, step = 0, 0
+            # parse all three checkpoints into host arrays first; only a fully parsed set touches the live learner
+            epoch, step, staged = 0, 0, []
             for role, p in enumerate(paths):
-                ck = torch.load(p, weights_only=False)
+                ck = torch.load(p, weights_only=False, map_location='cpu')
                 flat = np.concatenate([v.detach().cpu().numpy().ravel() for v in ck['model'].values()]).astype(np.float32)
-                self._learner.set_params(role, flat)
-                if role > 0:
-                    self._learner.set_params(role + 2, flat)
+                if flat.size != self._learner.P[role]:
+                    raise ValueError("%s holds %d parameters, the network has %d" % (p, flat.size, self._learner.P[role]))
+                m = v = None
                 st = ck['optimizer'].get('state', {})
                 if st:
                     keys = sorted(st.keys())
-                    self._learner.set_params(5 + role, np.concatenate([st[k]['exp_avg'].numpy().ravel() for k in keys]).astype(np.float32))
-                    self._learner.set_params(8 + role, np.concatenate([st[k]['exp_avg_sq'].numpy().ravel() for k in keys]).astype(np.float32))
+                    m = np.concatenate([st[k]['exp_avg'].detach().cpu().numpy().ravel() for k in keys]).astype(np.float32)
+                    v = np.concatenate([st[k]['exp_avg_sq'].detach().cpu().numpy().ravel() for k in keys]).astype(np.float32)
+                    if m.size != flat.size or v.size != flat.size:
+                        raise ValueError("%s: optimizer state does not match the model" % p)
                     step = int(float(st[keys[0]]['step']))
                 epoch = int(ck['epoch'])
-            sc = self._learner.scalars()
-            self._learner.set_scalars(sc["log_alpha"], sc["la_m"], sc["la_v"], epoch, step)
-        except Exception as e:              # the reference prints and carries on
+                staged.append((role, flat, m, v))
+        except Exception as e:              # the reference prints and carries on (SAC_Trainer.py:105-106); nothing was applied
             print(e.args)
+            return
+        for role, flat, m, v in staged:
+            self._learner.set_params(role, flat)
+            if role > 0:
+                self._learner.set_params(role + 2, flat)
+            if m is not None:
+                self._learner.set_params(5 + role, m)
+                self._learner.set_params(8 + role, v)
+        sc = self._learner.scalars()
+        self._learner.set_scalars(sc["log_alpha"], sc["la_m"], sc["la_v"], epoch, step)
 
     def hard_update(self):
         pass

@@ -56,8 +56,7 @@ class _ReplayFacade:
             return (s, tuple(a.tolist()), tuple(r.tolist()), s2, tuple(bool(x) for x in d), (slots + cap - 1).tolist(),
                     w.cpu().numpy().astype(np.float64))
         n = self._t._learner.replay_size()
-        idx = np.random.default_rng(self._t._sample_calls).permutation(n)[:batch_size]
-        self._t._sample_calls += 1
+        idx = self._t._rng.choice(n, int(batch_size), replace=False)       # random.sample: distinct, uniform
         s, a, r, s2, d = self._t._learner.gather(idx)
         return s, tuple(a.tolist()), tuple(r.tolist()), s2, tuple(bool(x) for x in d), None, None
 
@@ -98,7 +97,11 @@ class TrainerB200:
         self._dev = self._learner.device
         self._loss = torch.zeros(1, device=self._dev)
         self.loss = 0
-        self._sample_calls = 0
+        self._rng = np.random.default_rng([int(None2Value(param.get('seed'), 42)), sum(map(ord, str(self.name)))])
+        self._learner.set_is_train(self.Is_Train)        # the lockstep loops read it (get_action greedy when 0)
+        self._pin = {}                                   # pinned host staging, by (tag, slot)
+        self._pin_turn = 0
+        self._dist, self._rank, self._world = None, 0, 1
         self._head = 0                                   # next replay slot (SumTree.data_pointer)
         self.IsPriority_Replay = int(None2Value(param.get('IsPriority_Replay'), 0))
         if self.IsPriority_Replay:
@@ -114,15 +117,40 @@ class TrainerB200:
     def epoch(self):
         return self._learner.counters()[0]
 
+    # ---- host <-> device staging.  Arrays this plug-in hands out (actions; the env plug-in's observations) are numpy views
+    # of PINNED buffers taken round-robin from a ring of 4, so when the caller passes them back (state -> get_action ->
+    # replay add, as PathPlan_City.run_thread_OffPolicy does) the upload is a direct DMA.  A returned array stays valid for
+    # the next 3 calls that return the same kind of array.
+    def _pinned(self, tag, shape, dtype):
+        self._pin_turn = (self._pin_turn + 1) % 4
+        key = (tag, self._pin_turn, tuple(shape), dtype)
+        buf = self._pin.get(key)
+        if buf is None:
+            buf = self._pin[key] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        return buf
+
+    def _h2d(self, arr):
+        """numpy array (pinned or pageable) -> device tensor on the current stream, without a host synchronisation."""
+        return torch.from_numpy(arr).to(self._dev, non_blocking=True)
+
+    def attach_dist(self, dist, rank, world):
+        """Data-parallel training, one process per GPU: learn_off_policy() then runs the fused one-shot NVLink all-reduce +
+        Adam (uavrl_learner_update_dp) on this rank's replay shard; replicas stay bit-identical."""
+        self._dist, self._rank, self._world = dist, int(rank), int(world)
+        if self._world > 1:
+            self._learner.connect_peers(dist, self._rank, self._world)
+
     # ---- acting
     def get_action(self, state, eps):
         """DuelingDQN_Trainer.get_action (:86-97).  state: [w] -> python int, or [N, w] -> int32 array."""
         s = np.ascontiguousarray(state, np.float32)
         single = s.ndim == 1
         s = s.reshape(-1, self.w)
-        a = self._learner.act(torch.from_numpy(s).to(self._dev), float(eps), is_train=bool(self.Is_Train))
-        a = a.cpu().numpy()
-        return int(a[0]) if single else a
+        a = self._learner.act(self._h2d(s), float(eps), is_train=bool(self.Is_Train))
+        out = self._pinned("act", (s.shape[0],), torch.int32)
+        out.copy_(a, non_blocking=True)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return int(out[0]) if single else out.numpy()
 
     def get_q(self, state):
         s = torch.from_numpy(np.ascontiguousarray(state, np.float32).reshape(-1, self.w)).to(self._dev)
@@ -130,12 +158,11 @@ class TrainerB200:
 
     # ---- replay
     def _add(self, states, actions, rewards, next_states, dones):
-        dev = self._dev
-        s = torch.from_numpy(np.ascontiguousarray(states, np.float32).reshape(-1, self.w)).to(dev)
-        s2 = torch.from_numpy(np.ascontiguousarray(next_states, np.float32).reshape(-1, self.w)).to(dev)
-        a = torch.from_numpy(np.ascontiguousarray(actions, np.int32).reshape(-1)).to(dev)
-        r = torch.from_numpy(np.ascontiguousarray(rewards, np.float32).reshape(-1)).to(dev)
-        d = torch.from_numpy(np.ascontiguousarray(dones).astype(np.uint8).reshape(-1)).to(dev)
+        s = self._h2d(np.ascontiguousarray(states, np.float32).reshape(-1, self.w))
+        s2 = self._h2d(np.ascontiguousarray(next_states, np.float32).reshape(-1, self.w))
+        a = self._h2d(np.ascontiguousarray(actions, np.int32).reshape(-1))
+        r = self._h2d(np.ascontiguousarray(rewards, np.float32).reshape(-1))
+        d = self._h2d(np.ascontiguousarray(dones).astype(np.uint8, copy=False).reshape(-1))
         self._learner.push(s, a, r, s2, d)
         slots = (self._head + np.arange(s.shape[0])) % self.replay_size
         self._head = int((self._head + s.shape[0]) % self.replay_size)
@@ -162,11 +189,11 @@ class TrainerB200:
             return {'sum_epoch': self.epoch, 'loss': self.loss}
         if self.Is_Train:
             dev = self._dev
-            s = torch.as_tensor(np.asarray(states, np.float32)).to(dev)
-            s2 = torch.as_tensor(np.asarray(transition_dict['next_states'], np.float32)).to(dev)
-            a = torch.as_tensor(np.asarray(transition_dict['actions'], np.float32).astype(np.int32).reshape(-1)).to(dev)
-            r = torch.as_tensor(np.asarray(transition_dict['rewards'], np.float32).reshape(-1)).to(dev)
-            d = torch.as_tensor(np.asarray(transition_dict['dones'], np.float32).reshape(-1)).to(dev)
+            s = self._h2d(np.ascontiguousarray(states, np.float32))
+            s2 = self._h2d(np.ascontiguousarray(transition_dict['next_states'], np.float32))
+            a = self._h2d(np.asarray(transition_dict['actions'], np.float32).astype(np.int32).reshape(-1))
+            r = self._h2d(np.ascontiguousarray(transition_dict['rewards'], np.float32).reshape(-1))
+            d = self._h2d(np.ascontiguousarray(transition_dict['dones'], np.float32).reshape(-1))
             idx, wts = transition_dict.get('idx'), transition_dict.get('weights')
             if self.IsPriority_Replay and idx is not None and wts is not None:
                 # importance weights in the loss, then ReplayTree.batch_update(tree_idx, |TD error|) (SAC_Trainer.py:336-352)
@@ -178,13 +205,21 @@ class TrainerB200:
             else:
                 self._learner.update_batch(s, a, r, s2, d, self._loss)
             self.loss = self._loss            # a 1-element tensor, like the reference's `self.loss = loss`
+        else:                                 # self.epoch += 1 is unconditional (:152); the C update did it when training
+            e, t = self._learner.counters()
+            self._learner.set_counters(e + 1, t)
+            if self.Update_loop > 0 and (e + 1) % self.Update_loop == 0:
+                self._learner.hard_update()   # :183-184 runs whether or not Is_Train
         self._maybe_save()
         return {'sum_epoch': self.epoch, 'loss': self.loss}
 
     def learn_off_policy(self):
         """DQN_Trainer/DDQN_Trainer.learn_off_policy (:85-136 / :72-117): sample from the replay, update."""
         if self._learner.replay_size() > self.Batch_Size and self.Is_Train:
-            self._learner.update(loss=self._loss)
+            if self._world > 1:
+                self._learner.update_dp(self.Batch_Size * self._world, loss=self._loss)
+            else:
+                self._learner.update(loss=self._loss)
             self.loss = self._loss
         else:
             e, t = self._learner.counters()
@@ -269,11 +304,16 @@ class TrainerB200:
         torch.save({'model': self.state_dict(0), 'optimizer': osd, 'epoch': self.epoch}, pl)
 
     def Load_Mod(self, Mod_path=None):
+        """DuelingDQN_Trainer.Load_Mod (:40-69): <root>/Mod by default; a given Mod_path is tried as written and, like the
+        reference's `root + Mod_path`, relative to the working directory."""
         directory = Mod_path or os.path.join(os.getcwd(), 'Mod')
+        if Mod_path and not os.path.isdir(directory) and os.path.isdir(os.path.join(os.getcwd(), Mod_path.lstrip('/'))):
+            directory = os.path.join(os.getcwd(), Mod_path.lstrip('/'))
         pt, pl = self._paths(directory)
         if os.path.exists(pt) and os.path.exists(pl):
             try:
-                mt, ml = torch.load(pt, weights_only=False), torch.load(pl, weights_only=False)
+                mt = torch.load(pt, weights_only=False, map_location='cpu')
+                ml = torch.load(pl, weights_only=False, map_location='cpu')
                 self.load_state_dict(mt['model'], 1)
                 self.load_state_dict(ml['model'], 0)
                 self.load_optimizer_state_dict(ml['optimizer'])

@@ -207,6 +207,9 @@ int uavrl_learner_apply_grads(uavrl_learner *l, void *stream);
  * cores with the 3xTF32 split (default when the network fits), 0 = fp32 CUDA cores.  Returns the path in use. */
 int uavrl_learner_set_tensor_cores(uavrl_learner *l, int32_t enable);
 int uavrl_learner_hard_update(uavrl_learner *l, void *stream);   /* DuelingDQN_Trainer.py:199-202 */
+/* Trainer.Is_Train (BaseTrainer.py:47) for the lockstep loops below: with 0, get_action is greedy whatever eps is
+ * (`sample > eps or not self.Is_Train`, DuelingDQN_Trainer.py:90).  Default 1. */
+int uavrl_learner_set_is_train(uavrl_learner *l, int32_t is_train);
 /* After an explicit uavrl_env_reset the lockstep ring's current frame no longer matches the env
  * state: call this; the next uavrl_train_run re-observes into a fresh frame and the lockstep replay
  * restarts empty (envs that end episodes restart by themselves with auto_reset and need no call). */

@@ -78,3 +78,66 @@ def test_tc_td_targets_keep_update_parity(dqn_golden, name):
     np.testing.assert_allclose(out[True][1], g[name + "_local"][-1], atol=2e-5)
     np.testing.assert_allclose(out[True][1], out[False][1], atol=5e-6)
     np.testing.assert_allclose(out[True][2], out[False][2], atol=5e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The tile variants the large BASELINE configs select (launch_tc_forward: R = 64 rows per M=128 tile from n >= 64 x 148,
+# R = 128 from n >= 128 x 148; tc_train: R = 64 from B >= 64 x 148) compared with the oracle by VALUE, ragged last tiles.
+def big_inputs(g, n, rng):
+    base = np.concatenate([g["batch_s"].reshape(-1, 100), g["batch_s2"].reshape(-1, 100)])
+    x = np.tile(base, (n // base.shape[0] + 1, 1))[:n]
+    return (x + rng.normal(0, 0.02, x.shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [12000, 20011])
+@pytest.mark.parametrize("hidden,dueling", [([64, 64], 0), ([64], 1)])
+def test_tc_act_large_tiles_vs_oracle(dqn_golden, n, hidden, dueling):
+    from uavrl_b200 import engine
+    rng = np.random.default_rng(n)
+    net = O.make_net(100, hidden, 27, dueling)
+    params = rng.normal(0, 0.15, O.net_param_count(net)).astype(np.float32)
+    x = big_inputs(dqn_golden, n, rng)
+    u = rng.uniform(size=n).astype(np.float32); ra = rng.integers(0, 27, n).astype(np.int32)
+    L = engine.Learner(100, hidden, 27, dueling, 1)
+    L.set_params(params, 0)
+    assert L.set_tensor_cores(True)
+    a_tc, q_tc = L.act(dev(x), 0.25, u_tape=dev(u), rand_tape=dev(ra), want_q=True)
+    a_or, q_or = O.act(net, params, x, 0.25, u, ra)
+    np.testing.assert_allclose(q_tc.cpu().numpy(), q_or, rtol=2e-5, atol=2e-5)
+    top2 = np.sort(q_or, 1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4
+    assert clear.mean() > 0.99
+    assert np.array_equal(a_tc.cpu().numpy()[clear], a_or[clear])
+    L.close()
+
+
+@pytest.mark.parametrize("B", [12000, 20011])
+@pytest.mark.parametrize("name", ["dqn_qvalue3", "ddqn_qvalue3", "dueling_vanet2"])
+def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
+    """Trainer.update on an explicit batch of 12 000 / 20 011 transitions (TD-target passes with R = 64 / 128 rows per tile,
+    training chain R = 64, 94 / 157 weight-gradient chunks) against the oracle learner: loss 2e-5 relative, gradient 2e-4,
+    parameters 2e-5 after every one of 4 updates (incl. the hard update at epoch 3)."""
+    from uavrl_b200 import engine
+    g = dqn_golden
+    hidden, dueling, algo = CASES[name]
+    rng = np.random.default_rng(B + algo)
+    net = O.make_net(100, hidden, 27, dueling)
+    L = engine.Learner(100, hidden, 27, dueling, algo, lr=5e-4, gamma=0.99, batch_size=64, update_loop=3, replay_capacity=1000)
+    assert L.set_tensor_cores(True)
+    L.set_params(g[name + "_local0"], 0); L.set_params(g[name + "_target0"], 1)
+    OL = O.OracleLearner(net, algo, g[name + "_local0"], update_loop=3)
+    OL.target[:] = g[name + "_target0"]
+    loss = torch.zeros(1, device="cuda")
+    for step in range(4):
+        s = big_inputs(g, B, rng); s2 = big_inputs(g, B, rng)
+        a = rng.integers(0, 27, B).astype(np.int32)
+        r = rng.normal(0, 1.0, B).astype(np.float32)
+        d = (rng.uniform(size=B) < 0.1).astype(np.float32)
+        L.update_batch(dev(s), dev(a), dev(r), dev(s2), dev(d), loss)
+        lo, grads = OL.update(s, a, r, s2, d)
+        torch.cuda.synchronize()
+        assert np.isclose(float(loss), lo, rtol=2e-5), (step, float(loss), lo)
+        np.testing.assert_allclose(L.get_params(4), grads, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(L.get_params(0), OL.local, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(L.get_params(1), OL.target, rtol=0, atol=2e-5)
+    L.close()
