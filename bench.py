@@ -170,8 +170,16 @@ def config_dict(a, world):
 
 
 # ============================================================================ CPU arm (oracle port; never maps the product library)
+_USABLE = None
+
+
 def usable_cpus():
-    """CPUs this process may actually run on: the affinity mask, capped by a cgroup CPU quota if there is one."""
+    """CPUs this process may actually run on: the affinity mask at start-up (an OpenMP runtime with OMP_PROC_BIND later pins
+    the calling thread, which would shrink the mask seen from it), capped by a cgroup CPU quota if there is one
+    (the GPU boxes show 128 logical CPUs under a 16-CPU cpu.max quota)."""
+    global _USABLE
+    if _USABLE is not None:
+        return _USABLE
     n = len(os.sched_getaffinity(0))
     try:
         q, p = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -185,23 +193,27 @@ def usable_cpus():
                 n = min(n, max(1, q // p))
         except (OSError, ValueError):
             pass
+    _USABLE = n
     return n
 
 
-def cpu_env(threads):
-    """Must run before liboracle.so (libgomp) is loaded: torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm is."""
+def cpu_env(threads, bind):
+    """Must run before liboracle.so (libgomp) is loaded: torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm is.
+    bind: pin the oracle's threads (OMP_PROC_BIND) -- only in the CPU-arm process, where the oracle's libgomp is the only
+    OpenMP runtime; in the GPU process torch's own runtime would pin the main thread to one CPU and starve the oracle."""
     n = threads if threads > 0 else usable_cpus()
     os.environ["OMP_NUM_THREADS"] = str(n)
-    os.environ.setdefault("OMP_PROC_BIND", "spread")
-    os.environ.setdefault("OMP_PLACES", "threads")
     os.environ.setdefault("OMP_DYNAMIC", "false")
+    if bind:
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "threads")
     return n
 
 
 def make_oracle_loop(a, n_envs, threads):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    nthreads = O.set_threads(cpu_env(threads))
+    nthreads = O.set_threads(threads if threads > 0 else usable_cpus())
     pool = np.load(os.path.join(ROOT, "oracle", "pool_512.npz"))        # committed scenarios (oracle/make_pool.py)
     dims, b, p = pool["dims"], np.ascontiguousarray(pool["buildings"]), pool["uav_params"]
     P = len(pool["n_sub"])
@@ -643,7 +655,8 @@ if __name__ == "__main__":
     args = parse()
     if args.batch <= 0:
         args.batch = args.envs
-    cpu_env(args.threads)                   # before anything loads an OpenMP runtime (the oracle legs read it)
+    usable_cpus()                           # read the affinity mask before any OpenMP runtime can pin this thread
+    cpu_env(args.threads, bind=(args.impl == "reference"))
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -32,15 +32,15 @@ thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_pdl{1};
 
-template <bool DO_STEP, int EPB>
+template <bool DO_STEP, int EPB, bool EXTRAS = false>
 __global__ void __launch_bounds__(kEnvThreads)
 env_kernel(EnvDev d, int action_kind, const void *__restrict__ actions, float *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
            uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
 {
     __shared__ EnvSmem<EPB> sm;
-    env_block<DO_STEP, EPB, kEnvThreads, true, (EPB < 32 ? EPB : 32)>(d, sm, blockIdx.x * EPB, threadIdx.x, action_kind, actions, obs, reward, done_out,
-                                               info_out, coll_out, ended_out);
+    env_block<DO_STEP, EPB, kEnvThreads, true, (EPB < 32 ? EPB : 32), EXTRAS>(d, sm, blockIdx.x * EPB, threadIdx.x, action_kind, actions, obs,
+                                                                              reward, done_out, info_out, coll_out, ended_out);
 }
 
 __global__ void env_reset_kernel(EnvDev d, int first)
@@ -57,6 +57,13 @@ __global__ void env_reset_kernel(EnvDev d, int first)
     d.score[e] = 0.0; d.total[e] = 0.0; d.path_len[e] = 0.0; d.rew64[e] = 0.0;
     d.step[e] = 0; d.cursor[e] = 0; d.n_sub[e] = s.n_sub;
     d.done[e] = 0; d.alias[e] = (uint8_t)s.alias;
+    if (d.extras & kExtraEnergy) d.energy[e] = 0.0;
+    if ((d.extras & kExtraTrack) && e < d.track_n) { d.path_cur[e] = 0; d.path_n[e] = 0; d.path_n[d.track_n + e] = 0; }
+    if (d.extras & kExtraApf) {                                  // the env's own copy of the scenario's sub-goal queue
+        const double *src = d.pool_sub + (size_t)scen * d.K * 3;
+        double *dst = d.sub_env + (size_t)e * d.K * 3;
+        for (int i = 0; i < d.K * 3; ++i) dst[i] = src[i];
+    }
 }
 
 __global__ void env_theta_kernel(EnvDev d)
@@ -78,7 +85,11 @@ __global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, u
 int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st, bool pdl)
 {
-    if (d.n <= kSmallBatchEnvs) {
+    if (d.extras) {                                              // optional models: the EXTRAS instantiation (never inside a PDL chain)
+        const int blocks = (d.n + kEnvsPerBlockSmall - 1) / kEnvsPerBlockSmall;
+        UAVRL_CUDA(launch_kernel(env_kernel<true, kEnvsPerBlockSmall, true>, dim3(blocks), dim3(kEnvThreads), 0, st, pdl, d, action_kind, actions, obs,
+                                 reward, done, info, coll, ended));
+    } else if (d.n <= kSmallBatchEnvs) {
         const int blocks = (d.n + kEnvsPerBlockSmall - 1) / kEnvsPerBlockSmall;
         UAVRL_CUDA(launch_kernel(env_kernel<true, kEnvsPerBlockSmall>, dim3(blocks), dim3(kEnvThreads), 0, st, pdl, d, action_kind, actions, obs,
                                  reward, done, info, coll, ended));
@@ -94,7 +105,8 @@ int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float
 int launch_env_observe(const EnvDev &d, float *obs, cudaStream_t st)
 {
     const int blocks = (d.n + kEnvsPerBlockLarge - 1) / kEnvsPerBlockLarge;
-    env_kernel<false, kEnvsPerBlockLarge><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (d.extras) env_kernel<false, kEnvsPerBlockLarge, true><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else env_kernel<false, kEnvsPerBlockLarge><<<blocks, kEnvThreads, 0, st>>>(d, 0, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
     UAVRL_LAUNCHED();
     return 0;
 }
@@ -150,6 +162,7 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
         const double *b = cfg->buildings_host + 5 * i;
         Cyl c;
         c.cx = b[0]; c.cy = b[1]; c.R = b[3]; c.H = b[4];      // b[2] = base z: only ever subtracted from itself
+        env->base_z.push_back(b[2]);                           // (the APF distance is 3-D: it does see it)
         const double r2 = c.R * c.R;
         c.r2lo = r2 * (1.0 - 1e-12); c.r2hi = r2 * (1.0 + 1e-12);
         cyl[i] = c;
@@ -184,6 +197,7 @@ int uavrl_env_destroy(uavrl_env *env)
                      d.gz, d.rew64, d.theta, d.step, d.cursor, d.n_sub, d.scen, d.done, d.alias, d.stat_counts,
                      d.stat_reward, env->h_act_dev, env->h_obs_dev, env->h_rew_dev, env->h_flags_dev };
     for (void *p : ptrs) cudaFree(p);
+    cudaFree(d.energy); cudaFree((void *)d.apf_obs); cudaFree(d.sub_env); cudaFree(d.path_buf); cudaFree(d.path_n); cudaFree(d.path_cur);
     free_pool(d);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
@@ -333,6 +347,107 @@ int uavrl_env_set_state(uavrl_env *env, const uavrl_env_state_host *in)
     env_theta_kernel<<<(d.n + 127) / 128, 128>>>(d);            // the cached heading follows V_vector
     UAVRL_LAUNCHED();
     UAVRL_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int uavrl_env_set_extras(uavrl_env *env, const uavrl_env_extras *x)
+{
+    if (!env || !x) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (x->apf_enabled && !x->obstacle_v_host && env->cfg.n_buildings > 0) return fail(UAVRL_ERR_INVALID, "apf_enabled needs obstacle_v_host");
+    if (x->track_envs < 0 || x->track_envs > env->d.n || (x->track_envs > 0 && x->track_capacity <= 0))
+        return fail(UAVRL_ERR_INVALID, "track_envs must be in [0, n_envs] with a positive track_capacity");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    EnvDev &d = env->d;
+    cudaFree(d.energy); cudaFree((void *)d.apf_obs); cudaFree(d.sub_env); cudaFree(d.path_buf); cudaFree(d.path_n); cudaFree(d.path_cur);
+    d.energy = nullptr; d.apf_obs = nullptr; d.sub_env = nullptr; d.path_buf = nullptr; d.path_n = nullptr; d.path_cur = nullptr;
+    d.extras = 0; d.track_n = 0; d.track_cap = 0;
+    const size_t n = (size_t)d.n;
+    if (x->energy_enabled) {
+        if (!(x->v_0 > 0) || !(x->F_b > 0)) return fail(UAVRL_ERR_INVALID, "energy model: v_0 and F_b must be > 0");
+        d.pw.P_i = x->P_i; d.pw.v_0 = x->v_0; d.pw.d_0 = x->d_0; d.pw.rho = x->rho; d.pw.s = x->s; d.pw.A = x->A;
+        d.pw.P_b = x->P_b; d.pw.F_b = x->F_b; d.pw.xi = x->xi;
+        int rc = dev_alloc(&d.energy, n); if (rc) return rc;
+        d.extras |= kExtraEnergy;
+    }
+    if (x->apf_enabled) {
+        // the obstacle table with velocities; |v| and the direction of v are per-obstacle constants (UAV.py:189,193):
+        // Eu_Loc_distance(0, v) and calculate_angle(0, v), evaluated here with libm like the reference does
+        std::vector<Cyl> cyl((size_t)(d.k.n_cyl > 0 ? d.k.n_cyl : 1));
+        UAVRL_CUDA(cudaMemcpy(cyl.data(), d.cyl, cyl.size() * sizeof(Cyl), cudaMemcpyDeviceToHost));
+        std::vector<ApfObs> ob(cyl.size());
+        for (int i = 0; i < d.k.n_cyl; ++i) {
+            ApfObs o;
+            o.x = cyl[i].cx; o.y = cyl[i].cy; o.z = env->base_z.empty() ? 0.0 : env->base_z[(size_t)i]; o.R = cyl[i].R;
+            o.vx = x->obstacle_v_host[3 * i]; o.vy = x->obstacle_v_host[3 * i + 1]; o.vz = x->obstacle_v_host[3 * i + 2];
+            o.vmag = sqrt(o.vx * o.vx + o.vy * o.vy + o.vz * o.vz);
+            const double a = angle_xy(o.vx, o.vy);
+            o.cav = cos(a); o.sav = sin(a);
+            ob[(size_t)i] = o;
+        }
+        ApfObs *dob = nullptr;
+        UAVRL_CUDA(cudaMalloc((void **)&dob, ob.size() * sizeof(ApfObs)));
+        UAVRL_CUDA(cudaMemcpy(dob, ob.data(), ob.size() * sizeof(ApfObs), cudaMemcpyHostToDevice));
+        d.apf_obs = dob;
+        int rc = dev_alloc(&d.sub_env, n * (size_t)d.K * 3); if (rc) return rc;
+        d.extras |= kExtraApf;
+    }
+    if (x->track_envs > 0) {
+        d.track_n = x->track_envs; d.track_cap = x->track_capacity;
+        int rc = dev_alloc(&d.path_buf, (size_t)2 * d.track_n * d.track_cap * 3); if (rc) return rc;
+        if ((rc = dev_alloc(&d.path_n, (size_t)2 * d.track_n))) return rc;
+        if ((rc = dev_alloc(&d.path_cur, (size_t)d.track_n))) return rc;
+        d.extras |= kExtraTrack;
+    }
+    env->extras_set = true;
+    env->reset_done = false;                                     // the new columns are initialised by uavrl_env_reset
+    return 0;
+}
+
+int uavrl_env_get_energy(uavrl_env *env, double *energy_host)
+{
+    if (!env || !energy_host) return fail(UAVRL_ERR_INVALID, "null argument");
+    if (!(env->d.extras & kExtraEnergy)) return fail(UAVRL_ERR_STATE, "the energy model is not enabled (uavrl_env_set_extras)");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    UAVRL_CUDA(cudaMemcpy(energy_host, env->d.energy, (size_t)env->d.n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_env_get_path(uavrl_env *env, int32_t e, int32_t which, int32_t capacity, double *xyz_host, int32_t *n_out)
+{
+    if (!env || !xyz_host || !n_out || capacity <= 0 || which < 0 || which > 1) return fail(UAVRL_ERR_INVALID, "bad argument");
+    const EnvDev &d = env->d;
+    if (!(d.extras & kExtraTrack) || e < 0 || e >= d.track_n) return fail(UAVRL_ERR_STATE, "this UAV is not tracked (uavrl_env_set_extras track_envs)");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    int32_t cur = 0, np = 0;
+    UAVRL_CUDA(cudaMemcpy(&cur, d.path_cur + e, 4, cudaMemcpyDeviceToHost));
+    const int buf = which == 0 ? cur : (cur ^ 1);
+    UAVRL_CUDA(cudaMemcpy(&np, d.path_n + (size_t)buf * d.track_n + e, 4, cudaMemcpyDeviceToHost));
+    *n_out = np;
+    int m = np < d.track_cap ? np : d.track_cap;
+    if (m > capacity) m = capacity;
+    if (m > 0) UAVRL_CUDA(cudaMemcpy(xyz_host, d.path_buf + ((size_t)buf * d.track_n + e) * d.track_cap * 3, (size_t)m * 24, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_env_get_subgoals(uavrl_env *env, double *sub_host)
+{
+    if (!env || !sub_host) return fail(UAVRL_ERR_INVALID, "null argument");
+    const EnvDev &d = env->d;
+    if (!env->reset_done) return fail(UAVRL_ERR_STATE, "uavrl_env_get_subgoals before uavrl_env_reset");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    const size_t row = (size_t)d.K * 3;
+    if (d.extras & kExtraApf) {
+        UAVRL_CUDA(cudaMemcpy(sub_host, d.sub_env, (size_t)d.n * row * 8, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    std::vector<int32_t> scen((size_t)d.n);
+    UAVRL_CUDA(cudaMemcpy(scen.data(), d.scen, (size_t)d.n * 4, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < d.n; ++e)
+        UAVRL_CUDA(cudaMemcpy(sub_host + (size_t)e * row, d.pool_sub + (size_t)scen[(size_t)e] * row, row * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

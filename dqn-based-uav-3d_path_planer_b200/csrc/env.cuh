@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "env_core.cuh"
 
+#include <vector>
+
 namespace uavrl {
 
 constexpr int kEnvThreads = 128;       // warp 0 steps the CTA's envs; all 4 warps share their probes
@@ -30,7 +32,18 @@ struct EnvDev {
     // running statistics: [0] env steps, [1] episodes ended, [2] collisions ; sum_reward separately
     unsigned long long *stat_counts;
     double *stat_reward;
+    // optional models (uavrl_env_set_extras); extras = bit mask kExtra*
+    int32_t extras;
+    PowerConst pw;                      // energy: Calc_Fly_Power constants
+    double *energy;                     // [n] accumulated over the episode in progress
+    const ApfObs *apf_obs;              // APF: every obstacle with its velocity (device)
+    double *sub_env;                    // APF: per-env sub-goal queues [n][K][3] (shifted every step)
+    double *path_buf;                   // track: [2][track_n][track_cap][3]
+    int32_t *path_n;                    // [2][track_n] points recorded (buffer 0/1)
+    int32_t *path_cur;                  // [track_n] buffer holding the episode in progress
+    int32_t track_n, track_cap;
 };
+constexpr int kExtraEnergy = 1, kExtraApf = 2, kExtraTrack = 4;
 
 }  // namespace uavrl
 
@@ -43,6 +56,8 @@ struct uavrl_env {
     float *h_obs_dev = nullptr, *h_rew_dev = nullptr;
     uint8_t *h_flags_dev = nullptr;      // done | info | collision | ended, each [n]
     cudaStream_t own_stream = nullptr;
+    bool extras_set = false;
+    std::vector<double> base_z;          // building base heights (position.z), used by the APF distance only
 };
 
 namespace uavrl {

@@ -12,6 +12,7 @@ struct EnvSmem {
     __align__(16) float obs[EPB][kObsDim];
     double pos[3][EPB];
     unsigned long long mask[EPB];
+    uint8_t flags[EPB];                 // EXTRAS/APF: 1 = shift this env's sub-goal queue, 2 = reload it from the pool
 };
 
 __device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
@@ -57,13 +58,24 @@ __device__ __forceinline__ int threat_masked(const EnvConst &k, const Cyl *cyl, 
 // the fused kernel has already waited.
 // LPW = envs per phase-1 warp: EPB / LPW warps run the fp64 chains of LPW envs each (one lane per env).  The chain is
 // latency bound, so few lanes on several warps (= several SM sub-partitions) finish sooner than 32 lanes on one warp.
-template <bool DO_STEP, int EPB, int NT, bool USE_PDL, int LPW>
+// device-side UAV.cal_force over the env's obstacle table
+struct ApfDev {
+    static constexpr bool enabled = true;
+    const ApfObs *ob; int n;
+    __device__ __forceinline__ P3 force(double x, double y, double z) const { return apf_force(ob, n, x, y, z); }
+};
+
+// EXTRAS: the optional models of uavrl_env_set_extras (energy accumulator, APF with per-env sub-goal queues, trajectory
+// recording); the default instantiation (false) is the hot path and carries none of it.
+template <bool DO_STEP, int EPB, int NT, bool USE_PDL, int LPW, bool EXTRAS = false>
 __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int e0, int tid, int action_kind,
                                           const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
                                           uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
                                           uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
 {
     Cyl *s_cyl = sm.cyl;
+    uint8_t *sm_flags = EXTRAS ? sm.flags : nullptr;
+    if (EXTRAS && tid < EPB) sm.flags[tid] = 0;
     float (*s_obs)[kObsDim] = sm.obs;
     double (*s_pos)[EPB] = sm.pos;
     unsigned long long *s_mask = sm.mask;
@@ -104,7 +116,8 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 else if (action_kind == UAVRL_ACT_CONT_F32X2) act = (double)static_cast<const float *>(actions)[2 * e];
                 else act = (double)static_cast<const int32_t *>(actions)[e];
                 const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
-                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
+                const bool apf_on = EXTRAS && (d.extras & kExtraApf);
+                const double *q = apf_on ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
                 auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
                 const Cyl *cyl = s_cyl;
                 const EnvConst kk = d.k;
@@ -112,7 +125,26 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                     return threat_masked(kk, cyl, mask, x, y, z);
                 };
                 StepOut o;
-                step_core(d.k, s, mode, act, sub, threat, o);
+                if (apf_on) {
+                    ApfDev apf; apf.ob = d.apf_obs; apf.n = d.k.n_cyl;
+                    step_core_apf(d.k, s, mode, act, sub, threat, apf, o);
+                } else {
+                    step_core(d.k, s, mode, act, sub, threat, o);
+                }
+                if (EXTRAS) {
+                    if (d.extras & kExtraEnergy) d.energy[e] = dadd(d.energy[e], fly_power(d.pw, s.V));
+                    if ((d.extras & kExtraTrack) && e < d.track_n) {           // UAV.path.append (UAV.py:432)
+                        const int cur = d.path_cur[e];
+                        const int np = d.path_n[cur * d.track_n + e];
+                        if (np < d.track_cap) {
+                            double *pp = d.path_buf + (((size_t)cur * d.track_n + e) * d.track_cap + np) * 3;
+                            pp[0] = s.px; pp[1] = s.py; pp[2] = s.pz;
+                        }
+                        d.path_n[cur * d.track_n + e] = np + 1;
+                        if (s.done) { d.path_cur[e] = cur ^ 1; d.path_n[(cur ^ 1) * d.track_n + e] = 0; }     // UAV.reset: path = []
+                    }
+                    if (sm_flags) sm_flags[le] = (uint8_t)((d.auto_reset && s.done) ? 2 : 1);   // 2: reload the queue, 1: shift it
+                }
                 rew = o.reward;
                 n_stepped = 1; n_coll = o.coll; n_ended = s.done;
                 n_succ = (o.info == 1); n_lose = (o.info == 2);
@@ -124,6 +156,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 if (ended_out) ended_out[e] = (uint8_t)s.done;
                 if (d.auto_reset && s.done) {                      // UAV.reset() at the episode boundary
                     scen = (int)(((long long)scen + d.n) % d.P);
+                    if (EXTRAS && (d.extras & kExtraEnergy)) d.energy[e] = 0.0;
                     load_scenario(d, scen, s);
                     mask = cull_mask(d, s_cyl, s.px, s.py);
                     d.scen[e] = scen;
@@ -137,8 +170,18 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
             }
             if (obs) {
-                const double *q = d.pool_sub + (size_t)scen * d.K * 3;
-                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                const bool apf_on = EXTRAS && (d.extras & kExtraApf);
+                // APF: an env that did not restart reads its own queue, whose entries phase 1b shifts right after this
+                // (same function, so the on-the-fly shift below equals what will be stored); a restarted env reads the pool
+                const bool own_q = apf_on && !(DO_STEP && d.auto_reset && n_ended);
+                const double *q = own_q ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
+                const bool shift = own_q && DO_STEP;
+                const ApfObs *aob = d.apf_obs; const int an = d.k.n_cyl;
+                auto sub = [q, shift, aob, an](int i) {
+                    P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2];
+                    if (EXTRAS && shift) { const P3 f = apf_force(aob, an, p.x, p.y, p.z); p.x = dadd(p.x, f.x); p.y = dadd(p.y, f.y); p.z = dadd(p.z, f.z); }
+                    return p;
+                };
                 obs_scalars(s, sub, &s_obs[le][0]);
             }
             px = s.px; py = s.py; pz = s.pz;
@@ -169,6 +212,22 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
         }
     }
     __syncthreads();
+    if (EXTRAS && DO_STEP && (d.extras & kExtraApf)) {
+        // phase 1b, all threads: UAV.Adjust_subgoal (UAV.py:156-166) for the stored queues -- every entry moves by the
+        // force at its (pre-step) position; an env that restarted takes its new scenario's queue instead
+        for (int idx = tid; idx < EPB * d.K; idx += NT) {
+            const int le = idx / d.K, i = idx - le * d.K, e = e0 + le;
+            if (e >= d.n || sm.flags[le] == 0) continue;
+            double *q = d.sub_env + ((size_t)e * d.K + i) * 3;
+            if (sm.flags[le] == 2) {
+                const double *src = d.pool_sub + ((size_t)d.scen[e] * d.K + i) * 3;
+                q[0] = src[0]; q[1] = src[1]; q[2] = src[2];
+            } else if (i < d.n_sub[e]) {
+                const P3 f = apf_force(d.apf_obs, d.k.n_cyl, q[0], q[1], q[2]);
+                q[0] = dadd(q[0], f.x); q[1] = dadd(q[1], f.y); q[2] = dadd(q[2], f.z);
+            }
+        }
+    }
     if (!obs) return;
 
     // phase 2: occupancy probes

@@ -121,11 +121,64 @@ UAVRL_HD double calc_v(const EnvConst &k, double &vx, double &vy)
     return V;
 }
 
+// UAV.py:239-245 Calc_Fly_Power with the constants of config/UAV.xml <Power_param><Fly_power>.
+struct PowerConst { double P_i, v_0, d_0, rho, s, A, P_b, F_b, xi; };
+UAVRL_HD double fly_power(const PowerConst &c, double V)
+{
+    const double V2 = dmul(V, V), v02 = dmul(c.v_0, c.v_0);
+    const double V4 = dmul(V2, V2), v04 = dmul(v02, v02);
+    const double induced = dmul(c.P_i, dsqrt(dsub(dsqrt(dadd(1.0, ddiv(V4, dmul(4.0, v04)))), ddiv(V2, dmul(2.0, v02)))));
+    const double parasite = dmul(dmul(dmul(dmul(dmul(0.5, c.d_0), c.rho), c.s), c.A), dmul(V2, V));
+    const double blade = dmul(dmul(c.xi, c.P_b), dadd(1.0, ddiv(dmul(3.0, V2), dmul(c.F_b, c.F_b))));
+    return dadd(dadd(induced, parasite), blade);
+}
+
+// Moving obstacle as the APF code sees it (UAV.py:174-210): position, radius, velocity `v`, and -- constant per obstacle --
+// |v| and cos/sin of calculate_angle(0, v), evaluated once on the host.
+struct ApfObs { double x, y, z, R, vx, vy, vz, vmag, cav, sav; };
+
+// UAV.cal_force (UAV.py:174-210): repulsion min(1, R/d_edge^2) (max(-d_edge, 2) inside the obstacle) along -(p -> centre)
+// plus the motion force min(1, |v| R / d_edge^2) along v, for obstacles with v != 0 whose edge is within 60 m.
+// When the accumulated magnitude exceeds 100 the reference calls Cal_SubTask_Dynamic() without its two arguments (a
+// TypeError): here the force accumulated so far is returned (documented deviation; needs > 50 obstacles in range).
+UAVRL_HD P3 apf_force(const ApfObs *ob, int n, double px, double py, double pz)
+{
+    P3 tot; tot.x = 0.0; tot.y = 0.0; tot.z = 0.0;
+    double cum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const ApfObs &o = ob[i];
+        if (o.vx == 0.0 && o.vy == 0.0 && o.vz == 0.0) continue;            // :180-182
+        const double dis = dist3(px, py, pz, o.x, o.y, o.z);                  // :183
+        const double d2e = dsub(dis, o.R);                                    // :185
+        if (d2e > 60.0) continue;                                             // :186-187
+        const double dd = dmul(d2e, d2e);
+        double f1 = ddiv(o.R, dd);                                            // :190  min(1, w R / d^2), w = 1
+        f1 = (1.0 < f1 || f1 != f1) ? 1.0 : f1;
+        const double a1 = angle_xy(dsub(o.x, px), dsub(o.y, py));             // :191
+        if (d2e < 0.0) f1 = (-d2e > 2.0) ? -d2e : 2.0;                        // :196-197
+        const double f1x = dmul(-f1, cos(a1)), f1y = dmul(-f1, sin(a1));      // :198
+        double f2 = ddiv(dmul(o.vmag, o.R), dd);                              // :200
+        f2 = (1.0 < f2 || f2 != f2) ? 1.0 : f2;
+        const double f2x = dmul(f2, o.cav), f2y = dmul(f2, o.sav);            // :201
+        cum = dadd(cum, dadd(f1, f2));                                        // :202
+        tot.x = dadd(dadd(tot.x, f1x), f2x);                                  // :203
+        tot.y = dadd(dadd(tot.y, f1y), f2y);
+        if (cum > 100.0) return tot;                                          // :205-208 (see above)
+    }
+    return tot;
+}
+
+struct NoApf {
+    static constexpr bool enabled = false;
+    UAVRL_HD P3 force(double, double, double) const { P3 z; z.x = z.y = z.z = 0.0; return z; }
+};
+
 // UAV.py:397-513 update_PathPlan.  sub(i) returns entry i of this env's sub-goal queue;
 // threat(x,y,z) is PathPlan_City.Threaten_rate.  act_mode: 0 continuous (action = a0), 1 discrete-27.
-template <class SubFn, class ThreatFn>
-UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double action, SubFn sub,
-                        ThreatFn threat, StepOut &o)
+// apf: NoApf, or a functor with enabled = true and force(x, y, z) = UAV.cal_force at that point (APF_Enabled, UAV.py:448-453).
+template <class SubFn, class ThreatFn, class ApfFn>
+UAVRL_HD void step_core_apf(const EnvConst &k, EnvRegs &s, int act_mode, double action, SubFn sub,
+                            ThreatFn threat, const ApfFn &apf, StepOut &o)
 {
     double r = 0.0;
     o.coll = 0;
@@ -185,15 +238,27 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
     r = dsub(r, 0.1);                                                // :438
     r = dsub(r, dmul(0.01, fabs(dsub(s.pz, sg.z))));                 // :440
     s.path_len = dadd(s.path_len, s.V);                              // :443
-    // :448-453 APF: zero-velocity obstacles are skipped (UAV.py:180-182) -> the term is exactly 0.
+    // :448-453 APF.  With static obstacles (the shipped config) every force is exactly 0 (UAV.py:180-182) and this block is
+    // compiled out (NoApf).  Otherwise: Adjust_subgoal shifts every remaining sub-goal by the force at its position (the
+    // caller applies the same shift to the stored queue), then the force at the UAV adds 0.2 |F| cos|angle(F) - tri_V|.
+    double dis_t = dis_new;                                          // |p - sub_goals[0]| as the termination tests see it
+    if (ApfFn::enabled) {
+        const P3 f0 = apf.force(sg.x, sg.y, sg.z);                   // :449 (the aliased entry becomes a new Loc here)
+        sg.x = dadd(sg.x, f0.x); sg.y = dadd(sg.y, f0.y); sg.z = dadd(sg.z, f0.z);
+        const P3 F = apf.force(s.px, s.py, s.pz);                    // :450
+        const double force = dist3(0.0, 0.0, 0.0, F.x, F.y, F.z);    // :451
+        const double tri_force = angle_xy(F.x, F.y);                 // :452
+        r = dadd(r, dmul(dmul(0.2, force), cos(fabs(dsub(tri_force, tri_V)))));     // :453
+        dis_t = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);
+    }
 
     if (s.step >= k.max_step) {                                      // :456-465
         s.done = 1;
-        r = dadd(r, dsub(50.0, dis_new));
+        r = dadd(r, dsub(50.0, dis_t));
         s.score = dadd(s.score, r); s.total = dadd(s.total, r);
         o.reward = r; o.done_ret = 1; o.info = 2;
-    } else if (dis_new < 7.0 || dg_new < dist3(sg.x, sg.y, sg.z, s.gx, s.gy, s.gz)) {   // :466
-        r = dadd(r, dsub(50.0, dis_new));                            // :468
+    } else if (dis_t < 7.0 || dg_new < dist3(sg.x, sg.y, sg.z, s.gx, s.gy, s.gz)) {   // :466
+        r = dadd(r, dsub(50.0, dis_t));                              // :468
         s.cursor += 1;                                               // :469
         if (s.n_sub - s.cursor == 0) {                               // :470-483
             r = dadd(r, 50.0);
@@ -204,7 +269,11 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
         } else {                                                     // :484-495
             s.step = 0; s.score = 0.0;                               // local reset :329-332
             s.V = calc_v(k, s.vx, s.vy);
-            const P3 ng = sub(s.cursor);
+            P3 ng = sub(s.cursor);
+            if (ApfFn::enabled) {                                    // the stored queue is shifted after this call returns
+                const P3 fn = apf.force(ng.x, ng.y, ng.z);
+                ng.x = dadd(ng.x, fn.x); ng.y = dadd(ng.y, fn.y); ng.z = dadd(ng.z, fn.z);
+            }
             const double tg = angle_xy(dsub(ng.x, s.px), dsub(ng.y, s.py));   // :488
             const double tv = s.theta;                               // :489 (V_vector unchanged by the local reset)
             r = dadd(r, dmul(0.2, cos(fabs(dsub(tg, tv)))));         // :490
@@ -223,6 +292,13 @@ UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double acti
         o.reward = r; o.done_ret = 0; o.info = 0;
     }
     s.alias = 0;
+}
+
+template <class SubFn, class ThreatFn>
+UAVRL_HD void step_core(const EnvConst &k, EnvRegs &s, int act_mode, double action, SubFn sub,
+                        ThreatFn threat, StepOut &o)
+{
+    step_core_apf(k, s, act_mode, action, sub, threat, NoApf(), o);
 }
 
 // UAV.py:515-531,557-560: the 20 real-valued entries of the observation (probes are separate).

@@ -339,12 +339,18 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     }
 }
 
-// ---- data-parallel pair.  (1) reduce this rank's partials into its symmetric buffer and, once the whole grid is
-// done, raise this rank's flag on every peer (remote stores over NVLink).  (2) wait for every rank's flag, read
-// all gradient vectors through peer-mapped memory, sum in rank order, Adam.
+// ---- data-parallel pair (one-shot NVLink all-reduce fused with the optimiser).
+// Every rank owns a symmetric receive buffer recv[2][world][P+1] (double-buffered by update parity; slot q belongs to
+// rank q) and a flag word per peer.
+//   (1) reduce_publish_kernel: reduce this rank's gradient partials and PUSH the result -- fire-and-forget remote stores
+//       over NVLink -- into slot `rank` of every rank's receive buffer (its own included); once the whole grid is done
+//       (last-block detection), fence at system scope and raise this rank's flag on every peer.
+//   (2) allreduce_adam_kernel: wait for all `world` flags in LOCAL memory, read the `world` gradient vectors from the LOCAL
+//       receive buffer, sum them in rank order (bit-identical replicas) and apply Adam.  Nothing is pulled across NVLink on
+//       the critical path: the only remote traffic are the posted writes of (1).
 __global__ void __launch_bounds__(256)
 reduce_publish_kernel(int P, int nparts, int n_loss_parts, float inv_b, const float *__restrict__ partials,
-                      const float *__restrict__ loss_partials, float *__restrict__ my_grad, unsigned *counter,
+                      const float *__restrict__ loss_partials, float *const *peer_recv, size_t slot_off, unsigned *counter,
                       unsigned *const *peer_flags, int rank, int world, unsigned epoch)
 {
     __shared__ float red[4][64];
@@ -367,20 +373,26 @@ reduce_publish_kernel(int P, int nparts, int n_loss_parts, float inv_b, const fl
     }
     red[cg][ix] = g;
     __syncthreads();
-    if (cg == 0 && i < P) my_grad[i] = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
+    // thread (cg, ix) pushes element i to peers cg, cg+4, ...: 64 consecutive floats = 256 contiguous bytes per peer
+    if (i < P) {
+        const float gs = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
+        for (int q = cg; q < world; q += 4) peer_recv[q][slot_off + i] = gs;
+    }
     if (blockIdx.x == 0 && threadIdx.x >= 224) {                 // last warp of block 0: this rank's loss share
         const int lane = threadIdx.x & 31;
         float s = 0.f;
         for (int c = lane; c < n_loss_parts; c += 32) s += loss_partials[c];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) my_grad[P] = s * inv_b;
+        if (lane == 0)
+            for (int q = 0; q < world; ++q) peer_recv[q][slot_off + P] = s * inv_b;
     }
+    __threadfence_system();                                      // this thread's remote stores are performed system-wide
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned prev = atomicAdd(counter, 1u);
-        if (prev == gridDim.x - 1) {                             // the whole gradient vector is in place
+        if (prev == gridDim.x - 1) {                             // every block's slice has been pushed to every peer
             *counter = 0u;
             __threadfence_system();
             for (int q = 0; q < world; ++q) {
@@ -405,7 +417,7 @@ __device__ __forceinline__ float ld_relaxed_sys(const float *p)
 }
 
 __global__ void __launch_bounds__(256)
-allreduce_adam_kernel(AdamArgs a, float *const *peer_grads, int buf_off, const unsigned *my_flags, unsigned epoch,
+allreduce_adam_kernel(AdamArgs a, const float *recv, size_t stride, const unsigned *my_flags, unsigned epoch,
                       float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
                       float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,
                       const int32_t *__restrict__ img_map, float *__restrict__ tc_local, float *__restrict__ tc_target,
@@ -414,16 +426,27 @@ allreduce_adam_kernel(AdamArgs a, float *const *peer_grads, int buf_off, const u
 {
     pdl_wait();                 // PDL: nothing may still read the weight images this kernel rewrites
     pdl_trigger();
-    if (threadIdx.x < a.world) {                                  // one thread per peer spins on that peer's flag
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // Adam state of this parameter: independent of the peers, fetched while the flags are still in flight
+    float mi = 0.f, vi = 0.f, p = 0.f;
+    if (i < a.P) { mi = m[i]; vi = v[i]; p = local[i]; }
+    if (threadIdx.x < a.world) {                                  // one thread per peer spins on that peer's flag (local memory)
         while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) { }
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.P) {
+        // `world` vectors of the LOCAL receive buffer, summed in rank order; loads issued 8 at a time
         float g = 0.f;
-        for (int q = 0; q < a.world; ++q) g += ld_relaxed_sys(peer_grads[q] + buf_off + i);     // fixed rank order
+        int q = 0;
+        for (; q + 8 <= a.world; q += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = ld_relaxed_sys(recv + (size_t)(q + u) * stride + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g += t[u];
+        }
+        for (; q < a.world; ++q) g += ld_relaxed_sys(recv + (size_t)q * stride + i);
         grad[i] = g;
-        float mi = m[i], vi = v[i], p = local[i];
         mi = mi + (g - mi) * a.beta1_c;
         vi = vi * a.beta2 + a.beta2_c * g * g;
         const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
@@ -449,7 +472,7 @@ allreduce_adam_kernel(AdamArgs a, float *const *peer_grads, int buf_off, const u
     }
     if (i == 0 && loss_out) {
         float s = 0.f;
-        for (int q = 0; q < a.world; ++q) s += ld_relaxed_sys(peer_grads[q] + buf_off + a.P);
+        for (int q = 0; q < a.world; ++q) s += ld_relaxed_sys(recv + (size_t)q * stride + a.P);
         *loss_out = s;
     }
 }
@@ -677,20 +700,21 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
     if (rc) return rc;
     l->flag_epoch += 1;
     const int P = l->net.P;
-    const int buf_off = (int)((l->flag_epoch & 1u) * (unsigned)(P + 1));
+    const size_t stride = (size_t)P + 1;                                        // one rank's slot: gradient vector + loss share
+    const size_t parity_off = (size_t)(l->flag_epoch & 1u) * (size_t)l->world * stride;
     const bool chain = l->pdl_chain && g_pdl.load();
     UAVRL_CUDA(launch_kernel(reduce_publish_kernel, dim3((P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, P, l->last_nparts,
-                             l->last_n_loss_parts, 1.0f / (float)global_batch, l->partials, l->loss_partials, l->comm_grad + buf_off,
-                             l->comm_counter, l->peer_flag_dev, l->rank, l->world, l->flag_epoch));
+                             l->last_n_loss_parts, 1.0f / (float)global_batch, l->partials, l->loss_partials, l->peer_grad_dev,
+                             parity_off + (size_t)l->rank * stride, l->comm_counter, l->peer_flag_dev, l->rank, l->world, l->flag_epoch));
     UAVRL_LAUNCHED();
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = P; a.apply = 1; a.world = l->world;
     fill_adam_args(l, a);
-    UAVRL_CUDA(launch_kernel(allreduce_adam_kernel, dim3((P + 255) / 256), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a, l->peer_grad_dev,
-                             buf_off, l->comm_flags, l->flag_epoch, l->grad, l->local, l->m, l->v, l->target, l->img_local, l->img_target,
-                             l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map,
-                             l->tc_lo2_map, loss_out ? loss_out : l->loss_dev));
+    UAVRL_CUDA(launch_kernel(allreduce_adam_kernel, dim3((P + 255) / 256), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a,
+                             (const float *)(l->comm_grad + parity_off), stride, l->comm_flags, l->flag_epoch, l->grad, l->local, l->m, l->v,
+                             l->target, l->img_local, l->img_target, l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target,
+                             l->tc_hi_map, l->tc_lo_map, l->tc_hi2_map, l->tc_lo2_map, loss_out ? loss_out : l->loss_dev));
     UAVRL_LAUNCHED();
     l->pdl_prev = chain ? kPdlAdam : kPdlNone;
     return 0;
@@ -1060,8 +1084,14 @@ int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void 
         return fail(UAVRL_ERR_INVALID, "bad rank/world/handle pointer");
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
     l->rank = rank; l->world = world;
+    if (l->comm_grad && l->comm_world != world) {                // re-initialised with another world size
+        UAVRL_CUDA(cudaDeviceSynchronize());
+        cudaFree(l->comm_grad); cudaFree(l->comm_flags); cudaFree(l->comm_counter);
+        l->comm_grad = nullptr; l->comm_flags = nullptr; l->comm_counter = nullptr;
+    }
+    l->comm_world = world;
     if (!l->comm_grad) {
-        const size_t n = 2 * ((size_t)l->net.P + 1);
+        const size_t n = 2 * (size_t)world * ((size_t)l->net.P + 1);     // recv[2][world][P+1]
         UAVRL_CUDA(cudaMalloc((void **)&l->comm_grad, n * sizeof(float)));
         UAVRL_CUDA(cudaMemset(l->comm_grad, 0, n * sizeof(float)));
         UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, 64 * sizeof(unsigned)));

@@ -132,10 +132,11 @@ struct uavrl_learner {
     uint64_t act_calls = 0;
     // data-parallel: one-shot NVLink all-reduce fused with Adam (symmetric buffers exchanged through CUDA IPC)
     int32_t rank = 0, world = 1;
-    float *comm_grad = nullptr;       // own, [2][P+1]: double-buffered gradient vector (+ loss partial)
+    float *comm_grad = nullptr;       // own receive buffer recv[2][world][P+1]: slot q is written by rank q (remote stores)
+    int32_t comm_world = 0;
     unsigned *comm_flags = nullptr;   // own, [64]: slot q is raised by rank q
     unsigned *comm_counter = nullptr; // last-block detection of the publish kernel
-    float **peer_grad_dev = nullptr;  // device array [world]: every rank's comm_grad as mapped on THIS device
+    float **peer_grad_dev = nullptr;  // device array [world]: every rank's receive buffer as mapped on THIS device
     unsigned **peer_flag_dev = nullptr;
     void *peer_grad_host[64] = { nullptr }, *peer_flag_host[64] = { nullptr };
     bool comm_ready = false;

@@ -339,6 +339,13 @@ class Learner:
         check(_lib.lib().uavrl_learner_comm_connect(self.h, _ptr(g), _ptr(f)))
         dist.barrier(device_ids=[self.device.index])
 
+    def connect_self(self):
+        """world = 1: the data-parallel kernel pair (push into the local receive buffer, flag, all-reduce + Adam) on one GPU --
+        the self-test of the fused path that needs no second device."""
+        hg = (C.c_ubyte * 64)(); hf = (C.c_ubyte * 64)()
+        check(_lib.lib().uavrl_learner_comm_init(self.h, 0, 1, hg, hf))
+        check(_lib.lib().uavrl_learner_comm_connect(self.h, hg, hf))
+
     def update_dp(self, global_batch, idx_tape=None, loss=None):
         check(_lib.lib().uavrl_learner_update_dp(self.h, _ptr(idx_tape), int(global_batch), _ptr(loss), _stream(self.device)))
 

@@ -128,6 +128,32 @@ int uavrl_env_get_state(uavrl_env *env, const uavrl_env_state_host *out);
  * scenario (uavrl_env_set_pool + uavrl_env_reset): cursor / scenario / reward64 must be NULL.  Synchronises the device. */
 int uavrl_env_set_state(uavrl_env *env, const uavrl_env_state_host *in);
 
+/* Optional models of the UAV (off by default; set after uavrl_env_create, before uavrl_env_reset):
+ *   energy   UAV.Calc_Fly_Power (Agents/UAV.py:239-245) with the constants of config/UAV.xml <Power_param><Fly_power>
+ *            (xi = 0.8 + 0.02 j, UAV.py:58): P(V) = P_i sqrt(sqrt(1 + V^4/(4 v_0^4)) - V^2/(2 v_0^2)) + d_0 rho s A V^3 / 2
+ *            + xi P_b (1 + 3 V^2 / F_b^2), accumulated per step into a per-UAV energy column (the reference evaluates the
+ *            formula but never accumulates it, UAV.py:59,93 -- the accumulator is the north-star's "energy model" output).
+ *   apf      moving-obstacle artificial potential field (UAV.cal_force / Adjust_subgoal, UAV.py:156-210, and the reward
+ *            term :448-453): obstacle_v_host [n_buildings][3] = the `v` attribute of each obstacle; obstacles with v = 0
+ *            exert no force (UAV.py:180-182).  Every step shifts each remaining sub-goal by the force at its position,
+ *            so sub-goal queues become per-UAV state.
+ *   track    UAV.path (UAV.py:432) of the first track_envs UAVs, up to track_capacity points per episode, double
+ *            buffered: the episode in progress and the last finished one (what path.csv holds, UAV.py:461-464). */
+typedef struct {
+    int32_t energy_enabled;
+    double P_i, v_0, d_0, rho, s, A, P_b, F_b, xi;
+    int32_t apf_enabled;
+    const double *obstacle_v_host;
+    int32_t track_envs, track_capacity;
+} uavrl_env_extras;
+int uavrl_env_set_extras(uavrl_env *env, const uavrl_env_extras *extras);
+/* energy_host [n_envs]: sum of Calc_Fly_Power(V) over the steps of the episode in progress (joules per unit step time) */
+int uavrl_env_get_energy(uavrl_env *env, double *energy_host);
+/* which = 0: episode in progress, 1: last finished episode.  xyz_host [capacity][3]; *n_out = points recorded */
+int uavrl_env_get_path(uavrl_env *env, int32_t e, int32_t which, int32_t capacity, double *xyz_host, int32_t *n_out);
+/* the per-UAV sub-goal queues [n_envs][K][3] (the scenario's queue, shifted by APF when enabled) */
+int uavrl_env_get_subgoals(uavrl_env *env, double *sub_host);
+
 /* PathPlan_City.Threaten_rate (Envs/PathPlan_City.py:215-223) on arbitrary points (device kernel):
  * pts_host [n][3] -> out_host [n] u8. */
 int uavrl_env_threaten_rate(uavrl_env *env, int32_t n, const double *pts_host, uint8_t *out_host);
@@ -216,13 +242,15 @@ int uavrl_learner_set_is_train(uavrl_learner *l, int32_t is_train);
 int uavrl_learner_lockstep_restart(uavrl_learner *l);
 
 /* One-shot NVLink all-reduce fused with the optimiser (data-parallel training, one process per GPU):
- *   uavrl_learner_comm_init     allocate this rank's symmetric gradient buffer + flag words, return their
+ *   uavrl_learner_comm_init     allocate this rank's symmetric receive buffer recv[2][world][P+1] + flag words, return their
  *                               CUDA IPC handles (64 bytes each) for exchange (e.g. torch.distributed.all_gather)
  *   uavrl_learner_comm_connect  open every rank's handles (grad_handles / flag_handles: [world][64] bytes)
- *   uavrl_learner_update_dp     epoch += 1; local gradient (loss scaled by 1/global_batch) -> reduced into the
- *                               symmetric buffer -> flags raised on every peer over NVLink -> the optimiser kernel
- *                               waits for all ranks, reads all `world` gradient vectors through peer-mapped memory,
- *                               sums them in rank order (bit-identical replicas) and applies Adam.  No NCCL call.
+ *   uavrl_learner_update_dp     epoch += 1; local gradient (loss scaled by 1/global_batch) -> reduced and PUSHED with remote
+ *                               stores over NVLink into slot `rank` of every rank's receive buffer -> flags raised on every
+ *                               peer -> the optimiser kernel waits for all ranks' flags in local memory, sums the `world`
+ *                               vectors of its local receive buffer in rank order (bit-identical replicas) and applies Adam.
+ *                               No NCCL call, nothing pulled across NVLink on the critical path.  world = 1 runs the same two
+ *                               kernels on the local buffer (self-test on one GPU).
  * loss_dev (optional) receives the GLOBAL batch loss. */
 int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void *grad_handle_out, void *flag_handle_out);
 int uavrl_learner_comm_connect(uavrl_learner *l, const void *grad_handles, const void *flag_handles);

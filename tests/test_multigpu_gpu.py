@@ -86,3 +86,39 @@ def test_two_rank_nccl_data_parallel(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DP_OK" in r.stdout and "FUSED_OK" in r.stdout
+
+
+def test_fused_allreduce_pair_world1_equals_plain_update(dqn_golden):
+    """The data-parallel kernel pair on ONE GPU (world = 1): reduce + push into the local receive buffer + flag, then
+    flag wait + rank-ordered sum + Adam -- must equal the single-GPU update (same partials, same Adam arithmetic), through
+    hard updates and both parities of the double-buffered receive buffer; the loss is the batch loss."""
+    import numpy as np
+    from uavrl_b200 import engine
+    g = dqn_golden
+    s = g["batch_s"].reshape(-1, 100)[:300]; s2 = g["batch_s2"].reshape(-1, 100)[:300]
+    a = g["batch_a"].reshape(-1)[:300]; r = g["batch_r"].reshape(-1)[:300]; d = g["batch_d"].reshape(-1)[:300]
+
+    def dev(x, dt=None):
+        t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+        return t if dt is None else t.to(dt)
+    Ls = []
+    for _ in range(2):
+        L = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DDQN, batch_size=256, replay_capacity=300, update_loop=2)
+        L.set_params(g["ddqn_qvalue3_local0"], 0); L.set_params(g["ddqn_qvalue3_target0"], 1)
+        L.push(dev(s), dev(a, torch.int32), dev(r), dev(s2), dev(d, torch.uint8))
+        Ls.append(L)
+    Ls[1].connect_self()
+    rng = np.random.default_rng(4)
+    l0, l1 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    for it in range(5):
+        idx = dev(rng.permutation(300)[:256].astype(np.int32))
+        Ls[0].update(idx_tape=idx, loss=l0)
+        Ls[1].update_dp(256, idx_tape=idx, loss=l1)
+        torch.cuda.synchronize()
+        assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
+        np.testing.assert_allclose(Ls[1].get_params(4), Ls[0].get_params(4), rtol=0, atol=1e-9)       # the reduced gradient
+        np.testing.assert_allclose(Ls[1].get_params(0), Ls[0].get_params(0), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(Ls[1].get_params(1), Ls[0].get_params(1), rtol=0, atol=1e-7)
+    assert Ls[0].counters() == Ls[1].counters() == (5, 5)
+    for L in Ls:
+        L.close()

@@ -111,12 +111,70 @@ def test_tc_act_large_tiles_vs_oracle(dqn_golden, n, hidden, dueling):
     L.close()
 
 
+def f64_update(layers, algo, dueling, local, target, s, a, r, s2, d, gamma=0.99):
+    """The TD update's loss and gradient in float64 numpy (the arbiter between two fp32 implementations whose summation
+    orders differ): DQN_Trainer.py:107-124 / DDQN_Trainer.py:93-107 / DuelingDQN_Trainer.py:164-180."""
+    def unpack(flat):
+        out, off = [], 0
+        for (o, i) in layers:
+            W = flat[off:off + o * i].reshape(o, i).astype(np.float64); off += o * i
+            b = flat[off:off + o].astype(np.float64); off += o
+            out.append((W, b))
+        return out
+
+    def fwd(P, x):
+        acts, h = [x], x
+        nt = len(P) - (2 if dueling else 1)
+        for W, b in P[:nt]:
+            h = np.maximum(h @ W.T + b, 0.0); acts.append(h)
+        if dueling:
+            (WA, bA), (WV, bV) = P[nt], P[nt + 1]
+            A = h @ WA.T + bA; V = h @ WV.T + bV
+            return V + A - A.mean(1, keepdims=True), acts
+        W, b = P[nt]
+        return h @ W.T + b, acts
+    PL, PT = unpack(local), unpack(target)
+    s, s2 = s.astype(np.float64), s2.astype(np.float64)
+    B = s.shape[0]
+    qt, _ = fwd(PT, s2)
+    if algo == 0:
+        nq = qt.max(1)
+    else:
+        nq = qt[np.arange(B), fwd(PL, s2)[0].argmax(1)]
+    y = r.astype(np.float64) + gamma * nq * (1.0 - d.astype(np.float64))
+    q, acts = fwd(PL, s)
+    diff = q[np.arange(B), a] - y
+    loss = float((diff ** 2).mean())
+    gq = np.zeros_like(q); gq[np.arange(B), a] = 2.0 * diff / B
+    grads = []
+    nt = len(PL) - (2 if dueling else 1)
+    h = acts[-1]
+    if dueling:
+        gA = gq - gq.sum(1, keepdims=True) / q.shape[1]; gV = gq.sum(1, keepdims=True)
+        gh = gA @ PL[nt][0] + gV @ PL[nt + 1][0]
+        head = [gA.T @ h, gA.sum(0), gV.T @ h, gV.sum(0)]
+    else:
+        gh = gq @ PL[nt][0]
+        head = [gq.T @ h, gq.sum(0)]
+    trunk = []
+    for l in range(nt - 1, -1, -1):
+        gz = gh * (acts[l + 1] > 0)
+        trunk = [gz.T @ acts[l], gz.sum(0)] + trunk
+        gh = gz @ PL[l][0]
+    return loss, np.concatenate([g.ravel() for g in trunk + head])
+
+
 @pytest.mark.parametrize("B", [12000, 20011])
 @pytest.mark.parametrize("name", ["dqn_qvalue3", "ddqn_qvalue3", "dueling_vanet2"])
 def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
     """Trainer.update on an explicit batch of 12 000 / 20 011 transitions (TD-target passes with R = 64 / 128 rows per tile,
-    training chain R = 64, 94 / 157 weight-gradient chunks) against the oracle learner: loss 2e-5 relative, gradient 2e-4,
-    parameters 2e-5 after every one of 4 updates (incl. the hard update at epoch 3)."""
+    training chain R = 64, 94 / 157 weight-gradient chunks).  At this batch size two fp32 implementations differ by their
+    summation order alone (the oracle adds 20 000 per-sample terms one after the other per thread; the kernels add 128-sample
+    tensor-core partials), so a float64 numpy restatement arbitrates: the CUDA gradient must match float64 within 2e-4
+    relative / 2e-5 absolute on EVERY entry and be about as close to it as the fp32 oracle is, or closer; against the oracle itself
+    99.9 % of the entries meet the same bound and none is off by more than 2e-4.  Parameters after each of 4 updates (incl. the
+    hard update at epoch 3): within 2e-5 of the oracle's except where Adam divides a gradient that is itself inside the fp32
+    summation noise (|g| < 1e-5: the step is +-lr whichever way the noise points), and never further than 4 lr."""
     from uavrl_b200 import engine
     g = dqn_golden
     hidden, dueling, algo = CASES[name]
@@ -127,17 +185,32 @@ def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
     L.set_params(g[name + "_local0"], 0); L.set_params(g[name + "_target0"], 1)
     OL = O.OracleLearner(net, algo, g[name + "_local0"], update_loop=3)
     OL.target[:] = g[name + "_target0"]
+    dims = [100] + list(hidden)
+    layers = [(dims[i + 1], dims[i]) for i in range(len(hidden))] + ([(27, hidden[-1]), (1, hidden[-1])] if dueling else [(27, hidden[-1])])
     loss = torch.zeros(1, device="cuda")
+    noisy = np.zeros(L.P, bool)
     for step in range(4):
         s = big_inputs(g, B, rng); s2 = big_inputs(g, B, rng)
         a = rng.integers(0, 27, B).astype(np.int32)
         r = rng.normal(0, 1.0, B).astype(np.float32)
         d = (rng.uniform(size=B) < 0.1).astype(np.float32)
+        l64, g64 = f64_update(layers, algo, dueling, L.get_params(0), L.get_params(1), s, a, r, s2, d)
         L.update_batch(dev(s), dev(a), dev(r), dev(s2), dev(d), loss)
         lo, grads = OL.update(s, a, r, s2, d)
         torch.cuda.synchronize()
         assert np.isclose(float(loss), lo, rtol=2e-5), (step, float(loss), lo)
-        np.testing.assert_allclose(L.get_params(4), grads, rtol=2e-4, atol=2e-5)
-        np.testing.assert_allclose(L.get_params(0), OL.local, rtol=0, atol=2e-5)
-        np.testing.assert_allclose(L.get_params(1), OL.target, rtol=0, atol=2e-5)
+        assert np.isclose(float(loss), l64, rtol=2e-5), (step, float(loss), l64)
+        gg = L.get_params(4).astype(np.float64)
+        bound = 2e-4 * np.abs(g64) + 2e-5
+        err_gpu, err_or = np.abs(gg - g64), np.abs(grads - g64)
+        assert (err_gpu <= bound).all(), (step, float((err_gpu - bound).max()))
+        assert err_gpu.max() <= max(2 * err_or.max(), 5e-6) and err_gpu.mean() <= max(2 * err_or.mean(), 2e-7)
+        vs_or = np.abs(gg - grads)
+        assert (vs_or <= 2e-4 * np.abs(grads) + 2e-5).mean() >= 0.999 and vs_or.max() <= 2e-4
+        noisy |= np.abs(g64) < 1e-5
+        dp = np.abs(L.get_params(0) - OL.local)
+        assert (dp[~noisy] <= 2e-5).all() and dp.max() <= 4 * 5e-4, (step, float(dp[~noisy].max()), float(dp.max()))
+        dt = np.abs(L.get_params(1) - OL.target)
+        assert (dt[~noisy] <= 2e-5).all() and dt.max() <= 4 * 5e-4
+    assert noisy.mean() < 0.02
     L.close()
