@@ -39,6 +39,12 @@ class EnvStateHost(C.Structure):
                [("done", C.POINTER(C.c_uint8))]
 
 
+class EnvExtras(C.Structure):
+    _fields_ = [("energy_enabled", C.c_int32)] + [(k, C.c_double) for k in ("P_i", "v_0", "d_0", "rho", "s", "A", "P_b", "F_b", "xi")] + \
+               [("apf_enabled", C.c_int32), ("obstacle_v_host", C.POINTER(C.c_double)), ("track_envs", C.c_int32),
+                ("track_capacity", C.c_int32)]
+
+
 class LearnerConfig(C.Structure):
     _fields_ = [("in_dim", C.c_int32), ("n_hidden", C.c_int32), ("hidden", C.c_int32 * MAX_HIDDEN),
                 ("n_actions", C.c_int32), ("dueling", C.c_int32), ("algo", C.c_int32),
@@ -72,6 +78,11 @@ SIGNATURES = {
     "uavrl_make_scenarios": (C.c_int, [C.POINTER(EnvConfig), C.c_uint64, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
     "uavrl_set_pdl": (C.c_int, [C.c_int32]),
     "uavrl_set_fuse_act_env": (C.c_int, [C.c_int32]),
+    "uavrl_set_fuse_dw_adam": (C.c_int, [C.c_int32]),
+    "uavrl_env_set_extras": (C.c_int, [VP, VP]),
+    "uavrl_env_get_energy": (C.c_int, [VP, VP]),
+    "uavrl_env_get_path": (C.c_int, [VP, C.c_int32, C.c_int32, C.c_int32, VP, VP]),
+    "uavrl_env_get_subgoals": (C.c_int, [VP, VP]),
     "uavrl_per_enable": (C.c_int, [VP, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "uavrl_per_sample": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP]),
     "uavrl_per_set_errors": (C.c_int, [VP, C.c_int32, VP, VP, C.c_int32, VP]),

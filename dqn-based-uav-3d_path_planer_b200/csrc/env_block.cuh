@@ -6,6 +6,14 @@
 
 namespace uavrl {
 
+// The 80 probes of UAV.state_PathPlan (UAV.py:533-555,562-566; probe_point in env_core.cuh) as offsets from the UAV position
+// and observation slots: 3 grids of 5 x 5 at 1 / 5 / 10 m, then 5 points below.  x = px + dx is the same IEEE operation the
+// per-probe arithmetic performs (the offsets are small integers, exact in fp64).
+static __constant__ signed char kProbeDx[80] = { -2, -2, -2, -2, -2, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, -10, -10, -10, -10, -10, -5, -5, -5, -5, -5, 0, 0, 0, 0, 0, 5, 5, 5, 5, 5, 10, 10, 10, 10, 10, -20, -20, -20, -20, -20, -10, -10, -10, -10, -10, 0, 0, 0, 0, 0, 10, 10, 10, 10, 10, 20, 20, 20, 20, 20, 0, 0, 0, 0, 0 };
+static __constant__ signed char kProbeDy[80] = { -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, 0, 0, 0, 0, 0 };
+static __constant__ signed char kProbeDz[80] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, -2, -3, -4, -5 };
+static __constant__ unsigned char kProbeSlot[80] = { 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 90, 91, 92, 93, 94 };
+
 template <int EPB>
 struct EnvSmem {
     Cyl cyl[kMaxCyl];
@@ -13,6 +21,7 @@ struct EnvSmem {
     double pos[3][EPB];
     unsigned long long mask[EPB];
     uint8_t flags[EPB];                 // EXTRAS/APF: 1 = shift this env's sub-goal queue, 2 = reload it from the pool
+    uint8_t safe[EPB];                  // 1: none of this env's 75 planar probes can be out of bounds (phase 2 skips the test)
 };
 
 __device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
@@ -39,6 +48,27 @@ __device__ __forceinline__ unsigned long long cull_mask(const EnvDev &d, const C
         const bool near_y = fabs(py - cyl[c].cy) <= reach;
         if (near_x && near_y) m |= (1ull << c);
     }
+    return m;
+}
+
+// The same candidate set computed by G = 32 / LPW lanes per env: lane (part, env) tests cylinders part, part + G, ... and the
+// partial masks are OR-ed across the parts.  Every lane of the warp must call this (shuffles); lanes >= LPW take their env's
+// position from lane (lane % LPW).
+template <int LPW>
+__device__ __forceinline__ unsigned long long cull_mask_coop(const EnvDev &d, const Cyl *cyl, double px, double py, int lane)
+{
+    constexpr int G = 32 / LPW;
+    if (G == 1) return cull_mask(d, cyl, px, py);
+    const unsigned full = 0xffffffffu;
+    const int src = lane % LPW, part = lane / LPW;
+    const double x = __shfl_sync(full, px, src), y = __shfl_sync(full, py, src);
+    unsigned long long m = 0ull;
+    for (int c = part; c < d.k.n_cyl; c += G) {
+        const double reach = cyl[c].R + d.cull_w;
+        if (fabs(x - cyl[c].cx) <= reach && fabs(y - cyl[c].cy) <= reach) m |= (1ull << c);
+    }
+#pragma unroll
+    for (int off = LPW; off < 32; off <<= 1) m |= __shfl_xor_sync(full, m, off);
     return m;
 }
 
@@ -97,8 +127,9 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
         unsigned long long mask = 0ull;
         double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
         int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
+        EnvRegs s;
+        int scen = 0;
         if (valid) {
-            EnvRegs s;
             s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
             s.vx = d.vx[e]; s.vy = d.vy[e]; s.V = d.V[e];
             s.score = d.score[e]; s.total = d.total[e]; s.path_len = d.path_len[e];
@@ -106,8 +137,13 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
             s.done = d.done[e]; s.alias = d.alias[e];
             s.theta = d.theta[e];
-            int scen = d.scen[e];
-            mask = cull_mask(d, s_cyl, s.px, s.py);
+            scen = d.scen[e];
+        } else {
+            s.px = 0.0; s.py = 0.0;
+        }
+        // exact candidate cull, shared by the whole warp (the lanes beyond LPW would otherwise idle)
+        mask = cull_mask_coop<LPW>(d, s_cyl, s.px, s.py, ln);
+        if (valid) {
             if (DO_STEP) {
                 if (USE_PDL) { pdl_wait(); pdl_trigger(); }
                 double act;
@@ -189,6 +225,11 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
         if (ln < LPW) {
             s_pos[0][le] = px; s_pos[1][le] = py; s_pos[2][le] = pz;
             s_mask[le] = mask;
+            // Bounds shortcut for the 75 planar probes (offsets within +-20 m, z = pz): IEEE addition is monotonic in the
+            // offset, so if px-20 and px+20 (as rounded sums) are inside [0, width] every px+dx is, likewise y; z is pz
+            // itself.  Then PathPlan_City.py:218 is false for all of them and phase 2 need not evaluate it.
+            sm.safe[le] = (uint8_t)(!(dadd(px, -20.0) < 0.0) && !(dadd(px, 20.0) > d.k.width) && !(dadd(py, -20.0) < 0.0) &&
+                                    !(dadd(py, 20.0) > d.k.width) && !(pz < 0.0) && !(pz > d.k.h));
         }
         if (DO_STEP) {
             const unsigned full = 0xffffffffu;
@@ -234,10 +275,16 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     for (int idx = tid; idx < EPB * 80; idx += NT) {
         const int le = idx / 80, p = idx - 80 * le;
         if (e0 + le >= d.n) break;
-        double x, y, z;
-        int slot;
-        probe_point(p, s_pos[0][le], s_pos[1][le], s_pos[2][le], x, y, z, slot);
-        s_obs[le][slot] = threat_masked(d.k, s_cyl, s_mask[le], x, y, z) ? 1.0f : 0.0f;
+        const double x = dadd(s_pos[0][le], (double)kProbeDx[p]), y = dadd(s_pos[1][le], (double)kProbeDy[p]);
+        const double z = (p < 75) ? s_pos[2][le] : dadd(s_pos[2][le], (double)kProbeDz[p]);
+        int hit = (p < 75 && sm.safe[le]) ? 0 : out_of_bounds(d.k, x, y, z);
+        unsigned long long m = s_mask[le];
+        while (m && !hit) {
+            const int c = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            hit = cyl_hit(s_cyl[c], x, y, z);
+        }
+        s_obs[le][kProbeSlot[p]] = hit ? 1.0f : 0.0f;
     }
     __syncthreads();
 

@@ -87,6 +87,33 @@ UAVRL_HD double angle_xy(double dx, double dy)
     return dmul(ddiv(t, 180.0), kPi);
 }
 
+// cos|calculate_angle(a) - calculate_angle(b)| for two planar vectors WITHOUT the angles: the reference forms both angles with
+// atan2 -> degrees -> (+360) % 360 -> radians and takes the cosine of their difference (UAV.py:422-423,435,488-490), which
+// is the cosine of the angle between the vectors = their normalised dot product (the % 360 wrap and |.| do not change a
+// cosine).  calculate_angle of the zero vector is atan2(0, 0) = 0, i.e. the direction (1, 0).  Agrees with the literal
+// evaluation to a few 1e-16 (both are ~1 ulp evaluations of the same real number); nothing but the reward depends on it.
+// UAVRL_LITERAL_ANGLES=1 compiles the literal atan2 / cos chain instead (about 400 more dependent fp64 instructions per step).
+#ifndef UAVRL_LITERAL_ANGLES
+#define UAVRL_LITERAL_ANGLES 0
+#endif
+UAVRL_HD double cos_between(double ax, double ay, double bx, double by)
+{
+    double na = dsqrt(dadd(dmul(ax, ax), dmul(ay, ay)));
+    double nb = dsqrt(dadd(dmul(bx, bx), dmul(by, by)));
+    if (na == 0.0) { ax = 1.0; ay = 0.0; na = 1.0; }
+    if (nb == 0.0) { bx = 1.0; by = 0.0; nb = 1.0; }
+    return ddiv(dadd(dmul(ax, bx), dmul(ay, by)), dmul(na, nb));
+}
+
+// calculate_angle(0, V_vector) of V_vector = speed * (cos t, sin t), speed > 0: t wrapped into [0, 2 pi) -- what the
+// reference's atan2 -> degrees -> % 360 -> radians round trip returns up to its own rounding (~1e-15).
+UAVRL_HD double wrap_2pi(double t)
+{
+    if (t < 0.0) t = dadd(t, 2.0 * kPi);
+    if (t >= 2.0 * kPi) t = dsub(t, 2.0 * kPi);
+    return t;
+}
+
 // The reference evaluates calculate_angle(0, V_vector) three times per step on the SAME vector
 // (seta_old at :411 is last step's value, tri_V at :423 and state[7] at :526 are this step's):
 // EnvRegs.theta caches it -- identical value, one atan2 instead of three.
@@ -220,19 +247,33 @@ UAVRL_HD void step_core_apf(const EnvConst &k, EnvRegs &s, int act_mode, double 
     s.py = dadd(s.py, s.vy);                                         // :420
     if (act_mode == 1) s.pz = dadd(s.pz, dz);
     if (alias) { sg.x = s.px; sg.y = s.py; sg.z = s.pz; }            // the aliased sub-goal moved too
+#if UAVRL_LITERAL_ANGLES
     const double tri_goal = angle_xy(dsub(sg.x, s.px), dsub(sg.y, s.py));    // :422
     s.theta = angle_xy(s.vx, s.vy);
     double tri_V = s.theta;                                          // :423
+#else
+    const double tgx = dsub(sg.x, s.px), tgy = dsub(sg.y, s.py);     // :422 tri_goal = the direction of this vector
+    s.theta = (s.V > 0.0) ? wrap_2pi(seta_new) : angle_xy(s.vx, s.vy);
+    double tvx = s.vx, tvy = s.vy;                                   // :423 tri_V = the direction of V_vector
+#endif
     if (threat(s.px, s.py, s.pz)) {                                  // :425
         r = dsub(r, 0.3);
         s.px = ox; s.py = oy; s.pz = oz;                             // :427
+#if UAVRL_LITERAL_ANGLES
         tri_V = angle_xy(dsub(sg.x, s.px), dsub(sg.y, s.py));        // :428
+#else
+        tvx = dsub(sg.x, s.px); tvy = dsub(sg.y, s.py);              // :428
+#endif
         o.coll = 1;
     }
     const double dis_new = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);        // :429
     const double dg_new = dist3(s.px, s.py, s.pz, s.gx, s.gy, s.gz);         // :430
     r = dsub(r, dmul(0.13, fabs(a0)));                               // :434
+#if UAVRL_LITERAL_ANGLES
     r = dadd(r, dmul(0.2, cos(fabs(dsub(tri_goal, tri_V)))));        // :435
+#else
+    r = dadd(r, dmul(0.2, cos_between(tgx, tgy, tvx, tvy)));         // :435
+#endif
     r = dadd(r, dmul(0.4, dsub(dis_old, dis_new)));                  // :436
     r = dadd(r, dmul(0.4, dsub(dg_old, dg_new)));                    // :437
     r = dsub(r, 0.1);                                                // :438
@@ -247,8 +288,12 @@ UAVRL_HD void step_core_apf(const EnvConst &k, EnvRegs &s, int act_mode, double 
         sg.x = dadd(sg.x, f0.x); sg.y = dadd(sg.y, f0.y); sg.z = dadd(sg.z, f0.z);
         const P3 F = apf.force(s.px, s.py, s.pz);                    // :450
         const double force = dist3(0.0, 0.0, 0.0, F.x, F.y, F.z);    // :451
+#if UAVRL_LITERAL_ANGLES
         const double tri_force = angle_xy(F.x, F.y);                 // :452
         r = dadd(r, dmul(dmul(0.2, force), cos(fabs(dsub(tri_force, tri_V)))));     // :453
+#else
+        r = dadd(r, dmul(dmul(0.2, force), cos_between(F.x, F.y, tvx, tvy)));       // :452-453
+#endif
         dis_t = dist3(s.px, s.py, s.pz, sg.x, sg.y, sg.z);
     }
 
@@ -274,9 +319,13 @@ UAVRL_HD void step_core_apf(const EnvConst &k, EnvRegs &s, int act_mode, double 
                 const P3 fn = apf.force(ng.x, ng.y, ng.z);
                 ng.x = dadd(ng.x, fn.x); ng.y = dadd(ng.y, fn.y); ng.z = dadd(ng.z, fn.z);
             }
+#if UAVRL_LITERAL_ANGLES
             const double tg = angle_xy(dsub(ng.x, s.px), dsub(ng.y, s.py));   // :488
             const double tv = s.theta;                               // :489 (V_vector unchanged by the local reset)
             r = dadd(r, dmul(0.2, cos(fabs(dsub(tg, tv)))));         // :490
+#else
+            r = dadd(r, dmul(0.2, cos_between(dsub(ng.x, s.px), dsub(ng.y, s.py), s.vx, s.vy)));   // :488-490
+#endif
             r = dadd(r, (double)(k.max_step - s.step));              // :491
             s.score = dadd(s.score, r); s.total = dadd(s.total, r);
             o.reward = r; o.done_ret = 1; o.info = 1;

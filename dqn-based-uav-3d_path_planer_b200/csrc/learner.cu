@@ -280,19 +280,7 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
     pdl_trigger();
     float g = 0.f;
-    if (i < a.P && a.nparts > 0) {
-        // 4 groups x 8 independent loads in flight per thread: the partials are L2 resident, latency bound
-        float acc[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-        int c = cg;
-        for (; c + 28 < a.nparts; c += 32) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(c + 4 * u) * a.P + i];
-        }
-        for (; c < a.nparts; c += 4) acc[0] += partials[(size_t)c * a.P + i];
-        g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    }
+    if (i < a.P && a.nparts > 0) g = reduce_group(partials, a.P, a.nparts, i, cg);   // partials are L2 resident, latency bound
     red[cg][ix] = g;
     __syncthreads();
     if (cg == 0 && i < a.P) {
@@ -303,30 +291,11 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
             g = grad[i];                                  // already reduced (and all-reduced) by the caller
         }
         if (a.apply) {
-            // torch.optim.Adam single-tensor step: lerp, mul/addcmul, sqrt/div/add, addcdiv
-            float mi = m[i], vi = v[i], p = local[i];
-            mi = mi + (g - mi) * a.beta1_c;
-            vi = vi * a.beta2 + a.beta2_c * g * g;
-            const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
-            p = p - a.step_size * (mi / denom);
-            m[i] = mi; v[i] = vi; local[i] = p;
-            const int im = img_map[i];
-            img_local[im] = p;
-            if (a.hard) { target[i] = p; img_target[im] = p; }   // hard_update (DuelingDQN_Trainer.py:199-202)
-            if (tc_local) {                                      // tensor-core images: TF32 hi/lo split of the new value
-                const int ih = tc_hi[i], il = tc_lo[i];
-                float hi = p, lo = 0.f;
-                if (il >= 0) tf32_split(p, hi, lo);
-                tc_local[ih] = hi;
-                if (il >= 0) tc_local[il] = lo;
-                const int ih2 = tc_hi2[i], il2 = tc_lo2[i];
-                if (ih2 >= 0) { tc_local[ih2] = hi; tc_local[il2] = lo; }
-                if (a.hard) {
-                    tc_target[ih] = hi;
-                    if (il >= 0) tc_target[il] = lo;
-                    if (ih2 >= 0) { tc_target[ih2] = hi; tc_target[il2] = lo; }
-                }
-            }
+            AdamPtrs q;
+            q.partials = partials; q.loss_partials = loss_partials; q.grad = grad; q.local = local; q.m = m; q.v = v; q.target = target;
+            q.img_local = img_local; q.img_target = img_target; q.img_map = img_map; q.tc_local = tc_local; q.tc_target = tc_target;
+            q.tc_hi = tc_hi; q.tc_lo = tc_lo; q.tc_hi2 = tc_hi2; q.tc_lo2 = tc_lo2; q.loss_out = loss_out;
+            adam_update_one(a, q, i, g);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x >= 224 && loss_out && a.nparts > 0) {     // last warp: loss = sum / B
@@ -608,6 +577,21 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
     }
     if (mid) UAVRL_CUDA(cudaEventRecord(mid[0], st));
     int nparts = grid, n_loss_parts = grid;
+    // optimiser step arguments (needed before the weight-gradient launch: small batches fuse the step behind it)
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = l->net.P; a.apply = apply ? 1 : 0; a.world = l->world;
+    a.inv_b = 1.0f / (float)global_batch;
+    if (apply && !partials_only) {
+        l->adam_t += 1;
+        const double b1 = 0.9, b2 = 0.999;
+        const double bc1 = 1.0 - pow(b1, (double)l->adam_t), bc2 = 1.0 - pow(b2, (double)l->adam_t);
+        a.step_size = (float)((double)l->cfg.lr / bc1);
+        a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
+        a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
+        a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
+    }
+    bool adam_done = false;
     if (y_in && l->tc_train_ok) {
         // the whole update on the tensor cores: forward + dX chain, then split-K weight gradients (tc_train.cu)
         if (B > l->train_cap) {
@@ -618,7 +602,9 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
             l->train_cap = B;
         }
         if ((B + 127) / 128 > l->max_ctas) return fail(UAVRL_ERR_INVALID, "batch too large for the gradient partial buffer");
-        int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st, mid ? mid[1] : nullptr);
+        const bool may_fuse = apply && !partials_only && !per_batch;
+        int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st, mid ? mid[1] : nullptr,
+                                 may_fuse ? &a : nullptr, loss_out ? loss_out : l->loss_dev, &adam_done);
         if (rc) return rc;
     } else {
     UpdateArgs ua;
@@ -638,20 +624,9 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
     if (partials_only) {                                        // the data-parallel pair follows (launch_update_dp)
         if (per_batch) return per_set(l, B, l->per.idx, nullptr, l->per.abs_err, 1, st);
         return 0;
-    }     // the data-parallel pair that follows is launched plainly
-    AdamArgs a;
-    memset(&a, 0, sizeof(a));
-    a.P = l->net.P; a.nparts = nparts; a.n_loss_parts = n_loss_parts; a.apply = apply ? 1 : 0; a.world = l->world;
-    a.inv_b = 1.0f / (float)global_batch;
-    if (apply) {
-        l->adam_t += 1;
-        const double b1 = 0.9, b2 = 0.999;
-        const double bc1 = 1.0 - pow(b1, (double)l->adam_t), bc2 = 1.0 - pow(b2, (double)l->adam_t);
-        a.step_size = (float)((double)l->cfg.lr / bc1);
-        a.beta1_c = (float)(1.0 - b1); a.beta2 = (float)b2; a.beta2_c = (float)(1.0 - b2);
-        a.eps = 1e-8f; a.bc2_sqrt = (float)sqrt(bc2);
-        a.hard = (l->cfg.update_loop > 0 && (l->epoch % l->cfg.update_loop) == 0) ? 1 : 0;
     }
+    if (adam_done) return 0;                                    // the weight-gradient kernel applied the optimiser step itself
+    a.nparts = nparts; a.n_loss_parts = n_loss_parts;
     const bool chain = l->pdl_chain && g_pdl.load();
     UAVRL_CUDA(launch_kernel(reduce_adam_kernel, dim3((a.P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw && !mid, a,
                              l->partials, l->loss_partials, l->grad, l->local, l->m, l->v, l->target, l->img_local, l->img_target,
@@ -836,7 +811,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
     void *ptrs[] = { l->local, l->target, l->m, l->v, l->grad, l->partials, l->loss_partials, l->loss_dev, l->frames,
                      l->r_act, l->r_rew, l->r_done, l->comm_grad, l->comm_flags, l->comm_counter, l->peer_grad_dev, l->peer_flag_dev, l->img_local, l->img_target,
                      l->img_map, l->tc_img_local, l->tc_img_target, l->tc_hi_map, l->tc_lo_map, l->y_buf, l->astar_buf, l->tc_hi2_map,
-                     l->tc_lo2_map, l->act_buf, l->dz_buf };
+                     l->tc_lo2_map, l->act_buf, l->dz_buf, l->dw_bar };
     for (void *p : ptrs) cudaFree(p);
     per_free(l);
     delete l;

@@ -141,6 +141,8 @@ struct uavrl_learner {
     void *peer_grad_host[64] = { nullptr }, *peer_flag_host[64] = { nullptr };
     bool comm_ready = false;
     unsigned flag_epoch = 0;
+    unsigned long long *dw_bar = nullptr;      // grid-barrier counter of the fused weight-gradient + optimiser kernel
+    unsigned long long dw_bar_total = 0;
     int last_nparts = 0, last_n_loss_parts = 0;
     int last_global_batch = 0;
 };
@@ -214,7 +216,71 @@ struct AdamArgs {
     float step_size, beta1_c, beta2, beta2_c, eps, bc2_sqrt, inv_b;
 };
 
+// everything the optimiser step reads / writes (flat state_dict-ordered vectors + the kernel-layout weight images)
+struct AdamPtrs {
+    const float *partials, *loss_partials;
+    float *grad, *local, *m, *v, *target, *img_local, *img_target;
+    const int32_t *img_map;
+    float *tc_local, *tc_target;
+    const int32_t *tc_hi, *tc_lo, *tc_hi2, *tc_lo2;
+    float *loss_out;
+};
+
 #if defined(__CUDACC__)
+// Partial-gradient reduction in a FIXED order (run-to-run deterministic, and the same whichever kernel performs it):
+// partial c belongs to group c % 4; a group keeps 8 accumulators (8 independent loads in flight per pass over 32 partials);
+// the total is (g0 + g1) + (g2 + g3).
+__device__ __forceinline__ float reduce_group(const float *__restrict__ partials, int P, int nparts, int i, int cg)
+{
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    int c = cg;
+    for (; c + 28 < nparts; c += 32) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(c + 4 * u) * P + i];
+    }
+    for (; c < nparts; c += 4) acc[0] += partials[(size_t)c * P + i];
+    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
+__device__ __forceinline__ void tf32_split_f(float x, float &hi, float &lo)
+{
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// torch.optim.Adam single-tensor step for parameter i with gradient g (lerp, mul/addcmul, sqrt/div/add, addcdiv), the hard
+// target update (DuelingDQN_Trainer.py:199-202) and the refresh of the fp32 and tensor-core weight images
+__device__ __forceinline__ void adam_update_one(const AdamArgs &a, const AdamPtrs &q, int i, float g)
+{
+    float mi = q.m[i], vi = q.v[i], p = q.local[i];
+    mi = mi + (g - mi) * a.beta1_c;
+    vi = vi * a.beta2 + a.beta2_c * g * g;
+    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+    p = p - a.step_size * (mi / denom);
+    q.m[i] = mi; q.v[i] = vi; q.local[i] = p;
+    const int im = q.img_map[i];
+    q.img_local[im] = p;
+    if (a.hard) { q.target[i] = p; q.img_target[im] = p; }
+    if (q.tc_local) {                                        // tensor-core images: TF32 hi/lo split of the new value
+        const int ih = q.tc_hi[i], il = q.tc_lo[i];
+        float hi = p, lo = 0.f;
+        if (il >= 0) tf32_split_f(p, hi, lo);
+        q.tc_local[ih] = hi;
+        if (il >= 0) q.tc_local[il] = lo;
+        const int ih2 = q.tc_hi2[i], il2 = q.tc_lo2[i];
+        if (ih2 >= 0) { q.tc_local[ih2] = hi; q.tc_local[il2] = lo; }
+        if (a.hard) {
+            q.tc_target[ih] = hi;
+            if (il >= 0) q.tc_target[il] = lo;
+            if (ih2 >= 0) { q.tc_target[ih2] = hi; q.tc_target[il2] = lo; }
+        }
+    }
+}
+
 __global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,
                                    float *__restrict__ grad, float *__restrict__ local, float *__restrict__ m, float *__restrict__ v,
                                    float *__restrict__ target, float *__restrict__ img_local, float *__restrict__ img_target,

@@ -32,8 +32,10 @@ int tc_build(const uavrl_learner_config &c, const NetDev &net, TcNet &tc, std::v
              std::vector<int32_t> &hi2_map, std::vector<int32_t> &lo2_map);
 // tensor-core training path (tc_train.cu): forward + dX chain, then split-K dW; gradients land in l->partials
 int tc_train_init(uavrl_learner *l);
+// adam != nullptr: the optimiser step may be fused behind the weight-gradient kernel (*adam_done tells whether it was)
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
-                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain = nullptr);
+                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain = nullptr, const AdamArgs *adam = nullptr,
+                    float *loss_out = nullptr, bool *adam_done = nullptr);
 size_t tc_smem_bytes(const TcNet &tc);
 // the env step fused behind the act pass (tc_forward.cu): env batch + where the step writes
 struct EnvFuse { EnvDev d; float *obs_next; float *reward; uint8_t *done; };

@@ -11,9 +11,16 @@
 //   tc_dw_kernel     split-K weight gradients: CTA (layer l, chunk of 128 samples) computes
 //                    dW_l^T [in+1 x out] = [act_l ; 1]^T (in+1 x 128) * dZ_l (128 x out)  -- the extra all-ones
 //                    row yields the bias gradient for free -- and stores its slice of partial `chunk`.
-//                    reduce_adam_kernel then sums B/128 partials (instead of B/32) in a fixed order.
+//                    The contraction runs over SAMPLES, and both operands are stored [sample][feature]: exactly the
+//                    MN-major tcgen05 operand layout (umma.cuh), so the rows go from global memory to SMEM with plain
+//                    16-byte copies -- no transposition.  Small batches (grid <= SMs): the same kernel then meets at a
+//                    grid barrier and performs the partial reduction + Adam + image refresh itself (one launch less);
+//                    otherwise reduce_adam_kernel sums the B/128 partials.
 // All products use the hi*hi + hi*lo + lo*hi TF32 split (fp32-grade, see tc_forward.cu).
 #include <string.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "tc_forward.cuh"
 #include "tma.cuh"
@@ -39,7 +46,12 @@ struct TcDwArgs {
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_chunks][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
-    int32_t packed;                    // 1: LBO = 128 (core matrices packed, UAVRL_DW_PACKED), 0: skewed LBO = 144
+    // fused optimiser tail (fuse_adam = 1, only when every CTA of the grid is resident at once)
+    int32_t fuse_adam;
+    unsigned long long *bar_count;     // monotonic arrival counter of the grid barrier
+    unsigned long long bar_target;     // value the counter reaches when every CTA of THIS launch has arrived
+    AdamArgs adam;
+    AdamPtrs ptrs;
 };
 #define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
@@ -292,22 +304,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
 }
 
 // ------------------------------------------------------------------ split-K weight gradients
+constexpr uint32_t kDwBlk = (kDwChunk / 4) * kMnAtom;      // bytes of one 32-feature block: 128 samples x 128 B = 16 KB (the LBO)
+constexpr int kDwABlocks = 4;                               // A operand: M = 128 = 4 feature blocks (input features + the ones column)
+
+// rows [128 samples][width floats] in global memory -> hi/lo MN-major operand blocks.  8 consecutive lanes copy one 128-byte
+// row segment (coalesced), each as ONE 16-byte store into the swizzled position: no transposition, no bank conflicts.
+// ones_col >= 0: that feature column is set to 1 for valid samples (bias gradient).
+template <int U>
+__device__ __forceinline__ void dw_build_operand(const float *const *rows, int n_f4, int width, int ones_col, unsigned char *hi, unsigned char *lo)
+{
+    const int total = kDwChunk * n_f4;
+    for (int i0 = threadIdx.x; i0 < total; i0 += U * kTcThreads) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTcThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < total) {
+                const int b = i / n_f4, jc = i - b * n_f4;
+                if (rows[b] && 4 * jc < width) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[b]) + jc);
+                if (rows[b] && ones_col >= 0 && (ones_col >> 2) == jc) reinterpret_cast<float *>(&v[u])[ones_col & 3] = 1.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i >= total) continue;
+            const int b = i / n_f4, jc = i - b * n_f4;
+            float4 h, l;
+            tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+            const uint32_t off = umma_mn_off(4 * jc, b, kDwBlk);
+            *reinterpret_cast<float4 *>(hi + off) = h;
+            *reinterpret_cast<float4 *>(lo + off) = l;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int l = blockIdx.x % tc.n_layers, chunk = blockIdx.x / tc.n_layers;
     const TcLayer T = tc.L[l];
-    const int rowsA = T.K_real + 1;                           // input features + the all-ones row (bias gradient)
-    const int gA = (rowsA + 7) / 8, gB = T.N_pad / 8;
-    // K extent = 128 samples.  K-adjacent core matrices are spaced LBO = 144 B (128 + 16) instead of packed: the
-    // transposing 4-byte stores below walk the samples (K) for a fixed feature row, and with the 16-byte skew 32 consecutive
-    // samples land in 32 different banks (packed, they collide 8-way and the operand build dominates the kernel)
-    const uint32_t LBO = a.packed ? 128u : 144u;
-    const uint32_t SBO = (kDwChunk / 4) * LBO;                 // 4096 / 4608 B per 8 rows
-    unsigned char *Ahi = smem, *Alo = Ahi + gA * SBO, *Bhi = Alo + gA * SBO, *Blo = Bhi + gB * SBO;
+    const int rowsA = T.K_real + 1;                           // input features + the all-ones column (bias gradient)
+    const int nbB = T.N_pad / 32;                             // 32-wide output blocks of dZ (N_pad is 32 or 64 ...)
+    // A = [act ; 1] as [sample][feature], 4 feature blocks (M = 128; columns past rowsA are zero), hi then lo;
+    // B = dZ as [sample][out], hi blocks then lo blocks (adjacent: the concatenated 3xTF32 product reads them as N = 2 N_pad)
+    unsigned char *Ahi = smem, *Alo = Ahi + kDwABlocks * kDwBlk, *Bhi = Alo + kDwABlocks * kDwBlk, *Blo = Bhi + nbB * kDwBlk;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ const float *rows[kDwChunk];
+    __shared__ const float *drows[kDwChunk];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
     DW_TRACE(0);
@@ -316,7 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     const int b0 = chunk * kDwChunk;
     if (tid < kDwChunk) {
         const int b = b0 + tid;
-        const float *p = nullptr;
+        const float *p = nullptr, *dzp = nullptr;
         if (b < a.B) {
             if (l == 0) {
                 uint32_t pkey[4];
@@ -325,8 +371,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
             } else {
                 p = a.act_buf + (size_t)b * tc.act_stride + T.act_off;
             }
+            dzp = a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off;
         }
-        rows[tid] = p;
+        rows[tid] = p; drows[tid] = dzp;
     }
     tc_fence_before();
     __syncthreads();
@@ -336,97 +383,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // built from replay rows (written >= 2 kernels back) and is gathered before the wait
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
-
-    // A = [act ; 1]^T : element (row f, col b).  lanes walk samples (columns), each reads 4 features of its row; every
-    // load of a thread is in flight before the first is split / stored (one L2/HBM round trip per CTA).  The 4-byte
-    // transposing stores are 8-way bank conflicted and dominate this kernel (profiles/r01_tc_stage_trace.txt); tried and
-    // measured slower: a conflict-free scalar walk, a 4-lane shuffle transpose with 16-byte stores, and MN-major
-    // tcgen05 operands (kind::tf32 reads zeros from an unswizzled MN-major layout, tools/umma_layout_probe.cu).
-    const int fch = (T.K_real + 3) / 4;
-    {
-        constexpr int U = 13;                                  // 128 * 25 / 256 = 12.5 float4 per thread for the 100-wide input
-        for (int i0 = tid; i0 < kDwChunk * fch; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < kDwChunk * fch) { const int bl = i % kDwChunk, jc = i / kDwChunk; if (rows[bl]) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[bl]) + jc); }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= kDwChunk * fch) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int f = 4 * jc + e;
-                    if (f < T.K_real) {
-                        float hi, lo; tf32_split(vv[e], hi, lo);
-                        const uint32_t off = umma_off(f, bl, SBO, LBO);
-                        *reinterpret_cast<float *>(Ahi + off) = hi;
-                        *reinterpret_cast<float *>(Alo + off) = lo;
-                    }
-                }
-            }
-        }
-    }
+    const int wA = 32 * kDwABlocks;                            // 128 columns: features, the ones column, zero padding
+    dw_build_operand<8>(rows, wA / 4, T.K_real, T.K_real, Ahi, Alo);
     DW_TRACE(2);
-    for (int i = tid; i < kDwChunk * (gA * 8 - T.K_real); i += kTcThreads) {     // ones row, then zero padding rows
-        const int bl = i % kDwChunk, f = T.K_real + i / kDwChunk;
-        const uint32_t off = umma_off(f, bl, SBO, LBO);
-        *reinterpret_cast<float *>(Ahi + off) = (f == T.K_real && rows[bl]) ? 1.f : 0.f;
-        *reinterpret_cast<float *>(Alo + off) = 0.f;
-    }
-    DW_TRACE(3);
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    // B = dZ^T : element (row o, col b)
-    const int och = T.N_pad / 4;
-    {
-        constexpr int U = 8;
-        for (int i0 = tid; i0 < kDwChunk * och; i0 += U * kTcThreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < kDwChunk * och) {
-                    const int bl = i % kDwChunk, jc = i / kDwChunk, b = b0 + bl;
-                    if (b < a.B) v[u] = *reinterpret_cast<const float4 *>(a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off + 4 * jc);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kTcThreads;
-                if (i >= kDwChunk * och) continue;
-                const int bl = i % kDwChunk, jc = i / kDwChunk;
-                const float vv[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float hi, lo; tf32_split(vv[e], hi, lo);
-                    const uint32_t off = umma_off(4 * jc + e, bl, SBO, LBO);
-                    *reinterpret_cast<float *>(Bhi + off) = hi;
-                    *reinterpret_cast<float *>(Blo + off) = lo;
-                }
-            }
-        }
-    }
+    dw_build_operand<8>(drows, T.N_pad / 4, T.N_pad, -1, Bhi, Blo);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     DW_TRACE(4);
     if (tid == 0) {
-        issue_3xtf32(tmem, umma_desc(smem_u32(Ahi), SBO, LBO), umma_desc(smem_u32(Alo), SBO, LBO), umma_desc(smem_u32(Bhi), SBO, LBO),
-                     umma_desc(smem_u32(Blo), SBO, LBO), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0, LBO);
+        issue_3xtf32_mn(tmem, umma_desc_mn(smem_u32(Ahi), kDwBlk), umma_desc_mn(smem_u32(Alo), kDwBlk), umma_desc_mn(smem_u32(Bhi), kDwBlk),
+                        umma_desc_mn(smem_u32(Blo), kDwBlk), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
         umma_commit(&mbar);
     }
     DW_TRACE(5);
     mbar_wait(&mbar, 0);
     tc_fence_after();
     DW_TRACE(6);
-    // epilogue: accumulator row f = input feature (or the ones row), column o = output unit
+    // epilogue: accumulator row f = input feature (or the ones column), column o = output unit
     float *part = a.partials + (size_t)chunk * a.P;
     const int f = quad * 32 + lane;
     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
@@ -450,17 +426,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
     DW_TRACE(8);
+    if (!a.fuse_adam) return;
+    // ---- fused optimiser tail: grid barrier (every CTA of this launch is resident: grid <= SMs, one CTA per SM), then this
+    // CTA reduces its slice of the parameter vector over all partials in reduce_adam_kernel's order and applies Adam
+    if (tid == 0) {
+        __threadfence();                                       // this CTA's partial slice is visible device-wide
+        atomicAdd(a.bar_count, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long *>(a.bar_count) < a.bar_target) { }
+        __threadfence();
+    }
+    __syncthreads();
+    const int per = (a.P + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int i_end = min(a.P, ((int)blockIdx.x + 1) * per);
+    for (int i = (int)blockIdx.x * per + tid; i < i_end; i += kTcThreads) {
+        const float *pp = a.ptrs.partials;
+        // __ldcg: the partials were written by other SMs in this same launch (L1 holds nothing of them, but be explicit)
+        float g4[4];
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) {
+            float acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+            int c = cg;
+            for (; c + 28 < a.adam.nparts; c += 32) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += __ldcg(pp + (size_t)(c + 4 * u) * a.P + i);
+            }
+            for (; c < a.adam.nparts; c += 4) acc[0] += __ldcg(pp + (size_t)c * a.P + i);
+            g4[cg] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        }
+        const float g = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+        a.ptrs.grad[i] = g;
+        adam_update_one(a.adam, a.ptrs, i, g);
+    }
+    if (blockIdx.x == 0 && warp == 7 && a.ptrs.loss_out) {          // loss = sum of the training kernel's per-CTA partials / B
+        float sl = 0.f;
+        for (int c = lane; c < a.adam.n_loss_parts; c += 32) sl += __ldcg(a.ptrs.loss_partials + c);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, off);
+        if (lane == 0) *a.ptrs.loss_out = sl * a.adam.inv_b;
+    }
 }
 
 static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }
 static size_t dw_smem_bytes(const TcNet &tc)
 {
-    size_t mx = 0;
-    for (int l = 0; l < tc.n_layers; ++l) {
-        const size_t b = (size_t)2 * ((tc.L[l].K_real + 1 + 7) / 8 + tc.L[l].N_pad / 8) * (size_t)(kDwChunk / 4) * 144;
-        if (b > mx) mx = b;
-    }
-    return mx;
+    int maxN = 32;
+    for (int l = 0; l < tc.n_layers; ++l) if (tc.L[l].N_pad > maxN) maxN = tc.L[l].N_pad;
+    return (size_t)2 * (kDwABlocks + maxN / 32) * kDwBlk;       // A hi/lo (4 blocks each) + B hi/lo
 }
 
 int tc_train_init(uavrl_learner *l)
@@ -468,7 +481,7 @@ int tc_train_init(uavrl_learner *l)
     l->tc_train_ok = false;
     const TcNet &tc = l->tc;
     for (int i = 0; i < tc.n_layers; ++i)
-        if (tc.L[i].K_real + 1 > 128 || tc.L[i].K_real % 4 != 0) return 0;   // no room for the ones row / float4 feature chunks
+        if (tc.L[i].K_real + 1 > 128 || tc.L[i].K_real % 4 != 0 || tc.L[i].N_pad % 32 != 0) return 0;   // ones column / float4 chunks / 32-wide blocks
     // the M=128 MMA reads 16 row groups from each A buffer: with fewer real rows it runs into the next buffers,
     // which must still be inside the CTA's allocation
     if (train_smem_bytes(tc, 32) > 227 * 1024 || dw_smem_bytes(tc) > 227 * 1024) return 0;
@@ -484,8 +497,10 @@ int tc_train_init(uavrl_learner *l)
     return 0;
 }
 
+std::atomic<int> g_fuse_dw_adam{1};          // uavrl_set_fuse_dw_adam(); default on
+
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
-                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain)
+                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain, const AdamArgs *adam, float *loss_out, bool *adam_done)
 {
     const TcNet &tc = l->tc;
     TcTrainArgs a;
@@ -505,14 +520,30 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
     d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
-    static const bool packed = getenv("UAVRL_DW_PACKED") != nullptr;
-    d.packed = packed ? 1 : 0;
+    const int dw_grid = d.n_chunks * tc.n_layers;
+    // Fused optimiser tail: the kernel's grid barrier needs every CTA resident at once -- one CTA per SM (192 KB of shared
+    // memory each), so only when the grid fits the SMs; larger batches keep the separate reduce_adam_kernel.
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const bool fuse = adam != nullptr && g_fuse_dw_adam.load() && dw_grid <= n_sm;
+    if (adam_done) *adam_done = fuse;
+    if (fuse) {
+        if (!l->dw_bar) { UAVRL_CUDA(cudaMalloc((void **)&l->dw_bar, 8)); UAVRL_CUDA(cudaMemsetAsync(l->dw_bar, 0, 8, st)); l->dw_bar_total = 0; }
+        l->dw_bar_total += (unsigned long long)dw_grid;
+        d.fuse_adam = 1; d.bar_count = l->dw_bar; d.bar_target = l->dw_bar_total;
+        d.adam = *adam; d.adam.nparts = d.n_chunks; d.adam.n_loss_parts = grid;
+        AdamPtrs &q = d.ptrs;
+        q.partials = l->partials; q.loss_partials = l->loss_partials; q.grad = l->grad; q.local = l->local; q.m = l->m; q.v = l->v;
+        q.target = l->target; q.img_local = l->img_local; q.img_target = l->img_target; q.img_map = l->img_map;
+        q.tc_local = (float *)l->tc_img_local; q.tc_target = (float *)l->tc_img_target; q.tc_hi = l->tc_hi_map; q.tc_lo = l->tc_lo_map;
+        q.tc_hi2 = l->tc_hi2_map; q.tc_lo2 = l->tc_lo2_map; q.loss_out = loss_out;
+    }
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }
-    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(d.n_chunks * tc.n_layers), dim3(kTcThreads), dw_smem_bytes(tc), st,
+    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(dw_grid), dim3(kTcThreads), dw_smem_bytes(tc), st,
                              chain && !after_chain, tc, d));
-    l->pdl_prev = chain ? kPdlDw : kPdlNone;
+    l->pdl_prev = chain ? (fuse ? kPdlAdam : kPdlDw) : kPdlNone;
     UAVRL_LAUNCHED();
     if (trace_on) {
         long long h[16];
@@ -529,3 +560,5 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
 }
 
 }  // namespace uavrl
+
+extern "C" int uavrl_set_fuse_dw_adam(int32_t on) { uavrl::g_fuse_dw_adam.store(on ? 1 : 0); return 0; }

@@ -34,6 +34,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo, 
     return d;
 }
 
+// ---- MN-major operands (the contraction index K is the SLOW one: element (mn, k) and (mn+1, k) are adjacent).
+// kind::tf32 reads MN-major shared-memory operands only in layout_type 1 = SWIZZLE_128B_BASE32B (cute
+// Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (32 mn x 4 k):(1, 32); "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout", cutlass sm100_common.inl).  Measured on B200 with tools/umma_mn_probe.cu (every (mn, k) of an
+// M=128 x K=8 A operand and an N=16 x K=8 B operand, three LBO/SBO settings):
+//     byte(mn, k) = (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4
+// i.e. a [k][32 mn] row-major array of 128-byte rows whose four 32-byte chunks are XOR-swizzled with k%4; 4 k-rows form a
+// 512-byte atom (1024-byte aligned base), SBO = distance between 4-k groups, LBO = distance between 32-wide mn blocks.
+// A tensor stored [sample][feature] is therefore directly the MN-major operand of a product that contracts over samples.
+constexpr uint32_t kMnAtom = 512;                  // bytes of one 4-k x 32-mn atom (the natural SBO when k groups are contiguous)
+__device__ __forceinline__ uint32_t umma_mn_off(int mn, int k, uint32_t lbo, uint32_t sbo = kMnAtom)
+{
+    return (uint32_t)(mn >> 5) * lbo + (uint32_t)(k >> 2) * sbo + (uint32_t)(k & 3) * 128u +
+           ((((uint32_t)(mn & 31) >> 3) ^ (uint32_t)(k & 3)) << 5) + (uint32_t)(mn & 7) * 4u;
+}
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo = kMnAtom)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)1 << 61;                        // layout_type 1: SWIZZLE_128B_BASE32B
+    return d;
+}
+constexpr uint32_t kUmmaAMajorMN = 1u << 15, kUmmaBMajorMN = 1u << 16;   // instruction-descriptor transpose bits
+
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, both operands K-major
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
 {
@@ -135,6 +162,29 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t
     uint64_t da = a_hi, db = b_hi;
     if (concat) {
         const uint32_t wide = umma_idesc_tf32(M, 2 * N);
+        umma_tf32(d, da, db, wide, 0u);
+        for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, wide, 1u); }
+    } else {
+        umma_tf32(d, da, db, idesc, 0u);
+        for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
+        da = a_hi; db = b_lo;
+        for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
+    }
+    da = a_lo; db = b_hi;
+    for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
+}
+
+// The three TF32 products for operands that are BOTH MN-major (layout above), contraction over K = 8 * ksteps.  The k-th
+// step starts 2 * sbo further (two 4-k groups).  concat: [B_hi ; B_lo] are adjacent mn blocks (lbo apart), see issue_3xtf32.
+__device__ __forceinline__ void issue_3xtf32_mn(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int M, int N,
+                                                int ksteps, bool concat, uint32_t sbo = kMnAtom)
+{
+    const uint64_t kStep = (uint64_t)((2 * sbo) >> 4);
+    const uint32_t mn = kUmmaAMajorMN | kUmmaBMajorMN;
+    const uint32_t idesc = umma_idesc_tf32(M, N) | mn;
+    uint64_t da = a_hi, db = b_hi;
+    if (concat) {
+        const uint32_t wide = umma_idesc_tf32(M, 2 * N) | mn;
         umma_tf32(d, da, db, wide, 0u);
         for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, wide, 1u); }
     } else {

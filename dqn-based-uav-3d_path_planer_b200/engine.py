@@ -170,6 +170,43 @@ class EnvBatch:
             setattr(st, k, a.ctypes.data_as(C.POINTER(ct)))
         check(_lib.lib().uavrl_env_set_state(self.h, C.byref(st)))
 
+    # -- optional models (uavrl_env_set_extras): energy accumulator, moving-obstacle APF, trajectory recording
+    def set_extras(self, power=None, obstacle_v=None, track_envs=0, track_capacity=0):
+        """power: dict P_i, v_0, d_0, rho, s, A, P_b, F_b, xi (config/UAV.xml <Fly_power>; xi = 0.8 + 0.02 j) -> per-UAV energy;
+        obstacle_v: [n_buildings, 3] obstacle velocities -> APF_Enabled behaviour (UAV.py:156-210, 448-453);
+        track_envs / track_capacity: record UAV.path of the first track_envs UAVs.  Call before reset()."""
+        x = _lib.EnvExtras()
+        if power is not None:
+            x.energy_enabled = 1
+            for k in ("P_i", "v_0", "d_0", "rho", "s", "A", "P_b", "F_b", "xi"):
+                setattr(x, k, float(power[k]))
+        keep = None
+        if obstacle_v is not None:
+            keep = np.ascontiguousarray(obstacle_v, np.float64).reshape(-1, 3)
+            assert keep.shape[0] == self.city.buildings.shape[0]
+            x.apf_enabled = 1
+            x.obstacle_v_host = keep.ctypes.data_as(C.POINTER(C.c_double))
+        x.track_envs, x.track_capacity = int(track_envs), int(track_capacity)
+        check(_lib.lib().uavrl_env_set_extras(self.h, C.byref(x)))
+        self._track_cap = int(track_capacity)
+
+    def get_energy(self):
+        out = np.zeros(self.n, np.float64)
+        check(_lib.lib().uavrl_env_get_energy(self.h, _ptr(out)))
+        return out
+
+    def get_path(self, e, which=0):
+        """UAV.path of tracked UAV e: which = 0 the episode in progress, 1 the last finished episode -> [n, 3]."""
+        buf = np.zeros((self._track_cap, 3), np.float64)
+        n = C.c_int32()
+        check(_lib.lib().uavrl_env_get_path(self.h, int(e), int(which), self._track_cap, _ptr(buf), C.byref(n)))
+        return buf[:min(n.value, self._track_cap)].copy()
+
+    def get_subgoals(self):
+        out = np.zeros((self.n, self.K, 3), np.float64)
+        check(_lib.lib().uavrl_env_get_subgoals(self.h, _ptr(out)))
+        return out
+
     def threaten_rate(self, pts):
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
         out = np.zeros(pts.shape[0], np.uint8)

@@ -359,6 +359,10 @@ int uavrl_set_pdl(int32_t on);
  * actions it has just computed; results unchanged).  Process-wide switch, default 0: measured slower than the two
  * kernels chained with programmatic dependent launch (profiles/r01_fused_act_env.txt). */
 int uavrl_set_fuse_act_env(int32_t on);
+/* Small batches (weight-gradient grid <= number of SMs): the weight-gradient kernel meets at a grid barrier and applies the
+ * partial reduction + Adam + weight-image refresh itself instead of a separate optimiser launch (results unchanged: the
+ * reduction order is the optimiser kernel's).  Process-wide switch, default 1. */
+int uavrl_set_fuse_dw_adam(int32_t on);
 
 #ifdef __cplusplus
 }

@@ -328,3 +328,65 @@ def test_single_steps_next_to_every_decision_boundary(env_golden, env27_golden, 
         assert_close64(st[f], k("o_" + f), 1e-9, f)
     assert_obs(out["obs"], k("obs"), "obs")
     env.close()
+
+
+POWER = dict(P_i=89.0, v_0=4.05, d_0=0.6, rho=1.225, s=0.05, A=0.5, P_b=79.0, F_b=120.0, xi=0.8)     # config/UAV.xml <Fly_power>
+
+
+def test_energy_model_and_trajectory_recording(env_golden, env27_golden):
+    """uavrl_env_set_extras: the energy column is the running sum of Calc_Fly_Power(V) (Agents/UAV.py:239-245, oracle
+    ora_fly_power pinned to the reference formula) over the episode's steps, and the recorded trajectory is UAV.path
+    (UAV.py:432: the position after every step, post collision revert), double-buffered across the in-kernel reset.
+    The step outputs themselves are unchanged by the extras (same kernel body, EXTRAS instantiation)."""
+    from uavrl_b200 import engine
+    city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
+    N, P, K, T, CAP = 200, 512, 64, 260, 512
+    env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    ref = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    sc = make_pool(env, P, seed=29)
+    ref.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    env.set_extras(power=POWER, track_envs=8, track_capacity=CAP)
+    env.reset(0); ref.reset(0)
+    assert np.array_equal(env.get_energy(), np.zeros(N))
+    lib = O.lib()
+    fp = lambda V: lib.ora_fly_power(float(V), *[POWER[k] for k in ("P_i", "v_0", "d_0", "rho", "s", "A", "P_b", "F_b", "xi")])  # noqa: E731
+    rng = np.random.default_rng(2)
+    energy = np.zeros(N)
+    paths = [[] for _ in range(8)]
+    last = [None] * 8
+    for t in range(T):
+        a = rng.integers(0, 27, N).astype(np.int32)
+        if t == 1:
+            env.set_state(step=np.full(N, 120, np.int32)); ref.set_state(step=np.full(N, 120, np.int32))      # episodes end inside the test
+        out, out_ref = env.step(torch.tensor(a, device="cuda")), ref.step(torch.tensor(a, device="cuda"))
+        for k in ("obs", "reward", "done", "info", "collision", "ended"):
+            assert torch.equal(out[k], out_ref[k]), (k, t)
+        st = env.get_state()
+        ended = out["ended"].cpu().numpy().astype(bool)
+        # energy: + P(V of this step); an ended env restarts with 0.  V of an env that just restarted is the new episode's
+        # initial speed, so take this step's speed from |V_vector| before the reset: max_v or one of the speed levels
+        l = a % 3
+        speed = np.where(l == 0, params.min_v, np.where(l == 1, (params.min_v + params.max_v) / 2, params.max_v))
+        V_step = np.where(ended, speed, st["V"])
+        energy = np.where(ended, 0.0, energy + np.array([fp(v) for v in V_step]))
+        np.testing.assert_allclose(env.get_energy(), energy, rtol=1e-12, atol=1e-9)
+        for e in range(8):
+            if ended[e]:
+                last[e] = paths[e]          # the final position of the episode is appended by the kernel before the reset
+                paths[e] = []
+            else:
+                paths[e].append([st["px"][e], st["py"][e], st["pz"][e]])
+    n_checked = 0
+    for e in range(8):
+        cur = env.get_path(e, 0)
+        assert cur.shape[0] == len(paths[e])
+        if len(paths[e]):
+            np.testing.assert_array_equal(cur, np.array(paths[e]))
+        if last[e] is not None:
+            prev = env.get_path(e, 1)
+            assert prev.shape[0] == len(last[e]) + 1          # + the terminal step's position (recorded before UAV.reset)
+            if len(last[e]):
+                np.testing.assert_array_equal(prev[:-1], np.array(last[e]))
+            n_checked += 1
+    assert n_checked >= 4 and energy.max() > 0
+    env.close(); ref.close()

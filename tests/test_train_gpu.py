@@ -76,7 +76,8 @@ def test_training_loop_learns_and_counts(env_golden, env27_golden):
 @pytest.mark.parametrize("algo", ["dqn", "ddqn"])
 def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo):
     """Programmatic dependent launch inside the loop (kernel k+1's prologue overlaps kernel k's tail,
-    uavrl_set_pdl) and the fused get_action + Move_Agent kernel (uavrl_set_fuse_act_env) are scheduling changes only:
+    uavrl_set_pdl), the fused get_action + Move_Agent kernel (uavrl_set_fuse_act_env) and the optimiser step fused behind
+    the weight-gradient kernel's grid barrier (uavrl_set_fuse_dw_adam) are scheduling changes only:
     150 lockstep iterations with every on/off combination end in bit-identical parameters, replay contents, env state
     and counters."""
     from uavrl_b200 import _lib, engine
@@ -84,9 +85,11 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
     N = 1024
     out = []
     try:
-        for pdl, fuse in ((1, 1), (0, 0), (1, 0), (0, 1)):          # the fused act+step kernel is the same kind of change
+        # the fused act+step kernel and the optimiser step fused behind the weight-gradient kernel are the same kind of change
+        for pdl, fuse, fuse_dw in ((1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 1), (1, 0, 0)):
             _lib.lib().uavrl_set_pdl(pdl)
             _lib.lib().uavrl_set_fuse_act_env(fuse)
+            _lib.lib().uavrl_set_fuse_dw_adam(fuse_dw)
             env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
             sc = env.make_scenarios(1024, seed=8)
             env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
@@ -104,8 +107,9 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
                                    st.sum_reward, st.last_loss)))
             env.close(); L.close()
     finally:
-        _lib.lib().uavrl_set_pdl(1)                 # library defaults: PDL on, fused act+step off
+        _lib.lib().uavrl_set_pdl(1)                 # library defaults: PDL on, fused act+step off, optimiser fused behind dW
         _lib.lib().uavrl_set_fuse_act_env(0)
+        _lib.lib().uavrl_set_fuse_dw_adam(1)
     a = out[0]
     for b in out[1:]:
         assert a["stats"][:6] == b["stats"][:6] and a["stats"][1] == 150 and a["stats"][7] == b["stats"][7]
