@@ -66,6 +66,23 @@ open(os.path.join(HERE, "UAV_B200.xml"), "w").write("""<Agent>
 </Agent>
 """)
 
+# the same UAV with the reference's flight-power block (config/UAV.xml:27-36): enables the energy accumulator
+uav = open(os.path.join(HERE, "UAV_B200.xml")).read()
+open(os.path.join(HERE, "UAV_energy_B200.xml"), "w").write(uav.replace("</Agent>", """    <Power_param>
+        <Fly_power>
+            <P_i>89</P_i>
+            <v_0>4.05</v_0>
+            <d_0>0.6</d_0>
+            <rho>1.225</rho>
+            <s>0.05</s>
+            <A>0.5</A>
+            <P_b>79</P_b>
+            <F_b>120</F_b>
+        </Fly_power>
+        <Communication_power>3</Communication_power>
+    </Power_param>
+</Agent>"""))
+
 for name, ttype, net, extra in (("Trainer_DQN_B200.xml", "DQN_Trainer_B200", "QValueNet_SAC", ""),
                                 ("Trainer_DDQN_B200.xml", "DDQN_Trainer_B200", "QValueNet_SAC", ""),
                                 ("Trainer_DuelingDQN_B200.xml", "DuelingDQN_Trainer_B200", "VAnet2", "")):

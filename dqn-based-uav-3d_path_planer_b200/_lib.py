@@ -50,14 +50,14 @@ class LearnerConfig(C.Structure):
                 ("n_actions", C.c_int32), ("dueling", C.c_int32), ("algo", C.c_int32),
                 ("lr", C.c_float), ("gamma", C.c_float), ("batch_size", C.c_int32),
                 ("update_loop", C.c_int32), ("replay_capacity", C.c_int64),
-                ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32)]
+                ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("loss_kind", C.c_int32)]
 
 
 class SacConfig(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32), ("action_bound", C.c_float),
                 ("actor_lr", C.c_float), ("critic_lr", C.c_float), ("alpha_lr", C.c_float), ("target_entropy", C.c_float),
                 ("gamma", C.c_float), ("tau", C.c_float), ("batch_size", C.c_int32), ("replay_capacity", C.c_int64),
-                ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32)]
+                ("lockstep_envs", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("loss_kind", C.c_int32)]
 
 
 class TrainStats(C.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "uavrl_set_fuse_dw_adam": (C.c_int, [C.c_int32]),
     "uavrl_env_set_extras": (C.c_int, [VP, VP]),
     "uavrl_env_get_energy": (C.c_int, [VP, VP]),
+    "uavrl_env_get_energy_total": (C.c_int, [VP, C.POINTER(C.c_double)]),
     "uavrl_env_get_path": (C.c_int, [VP, C.c_int32, C.c_int32, C.c_int32, VP, VP]),
     "uavrl_env_get_subgoals": (C.c_int, [VP, VP]),
     "uavrl_per_enable": (C.c_int, [VP, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),

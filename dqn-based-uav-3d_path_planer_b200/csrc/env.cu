@@ -181,7 +181,7 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
     { int rc = dev_alloc(&d.done, n); if (rc) return rc; }
     { int rc = dev_alloc(&d.alias, n); if (rc) return rc; }
     { int rc = dev_alloc(&d.stat_counts, 8); if (rc) return rc; }
-    { int rc = dev_alloc(&d.stat_reward, 1); if (rc) return rc; }
+    { int rc = dev_alloc(&d.stat_reward, 2); if (rc) return rc; }      // [0] sum of rewards, [1] total flight energy (extras)
     UAVRL_CUDA(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
     *out = env;
     return 0;
@@ -411,6 +411,15 @@ int uavrl_env_get_energy(uavrl_env *env, double *energy_host)
     UAVRL_CUDA(cudaSetDevice(env->cfg.device));
     UAVRL_CUDA(cudaDeviceSynchronize());
     UAVRL_CUDA(cudaMemcpy(energy_host, env->d.energy, (size_t)env->d.n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uavrl_env_get_energy_total(uavrl_env *env, double *total_out)
+{
+    if (!env || !total_out) return fail(UAVRL_ERR_INVALID, "null argument");
+    UAVRL_CUDA(cudaSetDevice(env->cfg.device));
+    UAVRL_CUDA(cudaDeviceSynchronize());
+    UAVRL_CUDA(cudaMemcpy(total_out, env->d.stat_reward + 1, 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

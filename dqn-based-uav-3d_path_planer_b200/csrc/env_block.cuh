@@ -6,13 +6,22 @@
 
 namespace uavrl {
 
-// The 80 probes of UAV.state_PathPlan (UAV.py:533-555,562-566; probe_point in env_core.cuh) as offsets from the UAV position
-// and observation slots: 3 grids of 5 x 5 at 1 / 5 / 10 m, then 5 points below.  x = px + dx is the same IEEE operation the
-// per-probe arithmetic performs (the offsets are small integers, exact in fp64).
-static __constant__ signed char kProbeDx[80] = { -2, -2, -2, -2, -2, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, -10, -10, -10, -10, -10, -5, -5, -5, -5, -5, 0, 0, 0, 0, 0, 5, 5, 5, 5, 5, 10, 10, 10, 10, 10, -20, -20, -20, -20, -20, -10, -10, -10, -10, -10, 0, 0, 0, 0, 0, 10, 10, 10, 10, 10, 20, 20, 20, 20, 20, 0, 0, 0, 0, 0 };
-static __constant__ signed char kProbeDy[80] = { -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -10, -5, 0, 5, 10, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, -20, -10, 0, 10, 20, 0, 0, 0, 0, 0 };
-static __constant__ signed char kProbeDz[80] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, -2, -3, -4, -5 };
-static __constant__ unsigned char kProbeSlot[80] = { 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 90, 91, 92, 93, 94 };
+// The 80 probes of UAV.state_PathPlan (UAV.py:533-555,562-566) as integer offsets from the UAV position and observation
+// slots: 3 grids of 5 x 5 at 1 / 5 / 10 m, then 5 points below.  Built once per CTA in shared memory (a __constant__ table
+// indexed per lane would serialise); x = px + dx is the same IEEE operation probe_point performs (small integers are exact).
+struct ProbeOff { signed char dx, dy, dz; unsigned char slot; };
+__device__ __forceinline__ ProbeOff probe_offset(int p)
+{
+    ProbeOff o;
+    if (p < 75) {
+        const int g = p / 25, ij = p - 25 * g, i = ij / 5, j = ij - 5 * i;
+        const int sc = (g == 0) ? 1 : (g == 1) ? 5 : 10;
+        o.dx = (signed char)(sc * (i - 2)); o.dy = (signed char)(sc * (j - 2)); o.dz = 0; o.slot = (unsigned char)(11 + p);
+    } else {
+        o.dx = 0; o.dy = 0; o.dz = (signed char)(-(p - 75 + 1)); o.slot = (unsigned char)(90 + (p - 75));
+    }
+    return o;
+}
 
 template <int EPB>
 struct EnvSmem {
@@ -22,6 +31,7 @@ struct EnvSmem {
     unsigned long long mask[EPB];
     uint8_t flags[EPB];                 // EXTRAS/APF: 1 = shift this env's sub-goal queue, 2 = reload it from the pool
     uint8_t safe[EPB];                  // 1: none of this env's 75 planar probes can be out of bounds (phase 2 skips the test)
+    ProbeOff probe[80];
 };
 
 __device__ __forceinline__ void load_scenario(const EnvDev &d, int scen, EnvRegs &s)
@@ -106,6 +116,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     Cyl *s_cyl = sm.cyl;
     uint8_t *sm_flags = EXTRAS ? sm.flags : nullptr;
     if (EXTRAS && tid < EPB) sm.flags[tid] = 0;
+    if (tid < 80) sm.probe[tid] = probe_offset(tid);
     float (*s_obs)[kObsDim] = sm.obs;
     double (*s_pos)[EPB] = sm.pos;
     unsigned long long *s_mask = sm.mask;
@@ -168,7 +179,11 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                     step_core(d.k, s, mode, act, sub, threat, o);
                 }
                 if (EXTRAS) {
-                    if (d.extras & kExtraEnergy) d.energy[e] = dadd(d.energy[e], fly_power(d.pw, s.V));
+                    if (d.extras & kExtraEnergy) {
+                        const double pw = fly_power(d.pw, s.V);
+                        d.energy[e] = dadd(d.energy[e], pw);
+                        atomicAdd(d.stat_reward + 1, pw);          // lifetime total over all UAVs (UAV.energy_cost_total summed)
+                    }
                     if ((d.extras & kExtraTrack) && e < d.track_n) {           // UAV.path.append (UAV.py:432)
                         const int cur = d.path_cur[e];
                         const int np = d.path_n[cur * d.track_n + e];
@@ -275,8 +290,9 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     for (int idx = tid; idx < EPB * 80; idx += NT) {
         const int le = idx / 80, p = idx - 80 * le;
         if (e0 + le >= d.n) break;
-        const double x = dadd(s_pos[0][le], (double)kProbeDx[p]), y = dadd(s_pos[1][le], (double)kProbeDy[p]);
-        const double z = (p < 75) ? s_pos[2][le] : dadd(s_pos[2][le], (double)kProbeDz[p]);
+        const ProbeOff po = sm.probe[p];
+        const double x = dadd(s_pos[0][le], (double)po.dx), y = dadd(s_pos[1][le], (double)po.dy);
+        const double z = (p < 75) ? s_pos[2][le] : dadd(s_pos[2][le], (double)po.dz);
         int hit = (p < 75 && sm.safe[le]) ? 0 : out_of_bounds(d.k, x, y, z);
         unsigned long long m = s_mask[le];
         while (m && !hit) {
@@ -284,7 +300,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             m &= m - 1;
             hit = cyl_hit(s_cyl[c], x, y, z);
         }
-        s_obs[le][kProbeSlot[p]] = hit ? 1.0f : 0.0f;
+        s_obs[le][po.slot] = hit ? 1.0f : 0.0f;
     }
     __syncthreads();
 

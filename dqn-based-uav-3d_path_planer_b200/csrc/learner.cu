@@ -126,7 +126,7 @@ act_kernel(NetDev net, const float *__restrict__ params, const float *__restrict
 struct UpdateArgs {
     const float *img_local, *img_target;
     float *partials, *loss_partials;
-    int B, n_tiles, algo, dual;
+    int B, n_tiles, algo, dual, loss_kind;
     float gamma, inv_global_b;
     const float *y_in;                 // non-null: TD targets already computed (tensor-core pass); skip the target net
 };
@@ -227,8 +227,15 @@ update_kernel(NetDev net, BatchSrc src, UpdateArgs ua)
                 const float diff = Q[b * 32 + a] - y;
                 const float wb = src.is_w ? src.is_w[t * kTile + b] : 1.f;
                 if (src.abs_err) src.abs_err[t * kTile + b] = fabsf(diff);
-                lossb = wb * (diff * diff);
-                const float gq = (2.f * diff * wb) * ua.inv_global_b;
+                float gq;
+                if (ua.loss_kind == 0) {                          // MSELoss (BaseTrainer.py:40)
+                    lossb = wb * (diff * diff);
+                    gq = (2.f * diff * wb) * ua.inv_global_b;
+                } else {                                          // SmoothL1Loss(beta = 1)
+                    const float ad = fabsf(diff);
+                    lossb = wb * (ad < 1.f ? 0.5f * (diff * diff) : ad - 0.5f);
+                    gq = (fminf(fmaxf(diff, -1.f), 1.f) * wb) * ua.inv_global_b;
+                }
                 if (net.dueling) {
                     const float inv = 1.f / (float)nA;
                     for (int o = 0; o < nA; ++o) g[o] = gq * ((o == a ? 1.f : 0.f) - inv);
@@ -396,9 +403,6 @@ allreduce_adam_kernel(AdamArgs a, const float *recv, size_t stride, const unsign
     pdl_wait();                 // PDL: nothing may still read the weight images this kernel rewrites
     pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // Adam state of this parameter: independent of the peers, fetched while the flags are still in flight
-    float mi = 0.f, vi = 0.f, p = 0.f;
-    if (i < a.P) { mi = m[i]; vi = v[i]; p = local[i]; }
     if (threadIdx.x < a.world) {                                  // one thread per peer spins on that peer's flag (local memory)
         while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) { }
     }
@@ -416,28 +420,11 @@ allreduce_adam_kernel(AdamArgs a, const float *recv, size_t stride, const unsign
         }
         for (; q < a.world; ++q) g += ld_relaxed_sys(recv + (size_t)q * stride + i);
         grad[i] = g;
-        mi = mi + (g - mi) * a.beta1_c;
-        vi = vi * a.beta2 + a.beta2_c * g * g;
-        const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
-        p = p - a.step_size * (mi / denom);
-        m[i] = mi; v[i] = vi; local[i] = p;
-        const int im = img_map[i];
-        img_local[im] = p;
-        if (a.hard) { target[i] = p; img_target[im] = p; }
-        if (tc_local) {
-            const int ih = tc_hi[i], il = tc_lo[i];
-            float hi = p, lo = 0.f;
-            if (il >= 0) tf32_split(p, hi, lo);
-            tc_local[ih] = hi;
-            if (il >= 0) tc_local[il] = lo;
-            const int ih2 = tc_hi2[i], il2 = tc_lo2[i];
-            if (ih2 >= 0) { tc_local[ih2] = hi; tc_local[il2] = lo; }
-            if (a.hard) {
-                tc_target[ih] = hi;
-                if (il >= 0) tc_target[il] = lo;
-                if (ih2 >= 0) { tc_target[ih2] = hi; tc_target[il2] = lo; }
-            }
-        }
+        AdamPtrs ap;
+        ap.partials = nullptr; ap.loss_partials = nullptr; ap.grad = grad; ap.local = local; ap.m = m; ap.v = v; ap.target = target;
+        ap.img_local = img_local; ap.img_target = img_target; ap.img_map = img_map; ap.tc_local = tc_local; ap.tc_target = tc_target;
+        ap.tc_hi = tc_hi; ap.tc_lo = tc_lo; ap.tc_hi2 = tc_hi2; ap.tc_lo2 = tc_lo2; ap.loss_out = loss_out;
+        adam_update_one(a, ap, i, g);
     }
     if (i == 0 && loss_out) {
         float s = 0.f;
@@ -610,6 +597,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
     UpdateArgs ua;
     ua.img_local = l->img_local; ua.img_target = l->img_target; ua.partials = l->partials; ua.loss_partials = l->loss_partials;
     ua.B = B; ua.n_tiles = n_tiles; ua.algo = l->cfg.algo; ua.gamma = l->cfg.gamma; ua.dual = l->dual_weights;
+    ua.loss_kind = l->cfg.loss_kind;
     ua.inv_global_b = 1.0f / (float)global_batch;
     ua.y_in = y_in;
     update_kernel<<<grid, kNetThreads, upd_smem_bytes(l->net, l->dual_weights), st>>>(l->net, src, ua);
@@ -749,6 +737,7 @@ int uavrl_learner_create(const uavrl_learner_config *cfg, uavrl_learner **out)
     if (!cfg || !out) return fail(UAVRL_ERR_INVALID, "uavrl_learner_create: null argument");
     if (cfg->batch_size <= 0 || cfg->replay_capacity <= 0) return fail(UAVRL_ERR_INVALID, "batch_size and replay_capacity must be > 0");
     if (cfg->algo < 0 || cfg->algo > 2) return fail(UAVRL_ERR_INVALID, "unknown algo");
+    if (cfg->loss_kind < 0 || cfg->loss_kind > 1) return fail(UAVRL_ERR_INVALID, "loss_kind must be 0 (MSE) or 1 (Huber)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(UAVRL_ERR_CUDA, "no CUDA device: the learner has no CPU fallback");

@@ -256,11 +256,13 @@ __device__ __forceinline__ void tf32_split_f(float x, float &hi, float &lo)
 // target update (DuelingDQN_Trainer.py:199-202) and the refresh of the fp32 and tensor-core weight images
 __device__ __forceinline__ void adam_update_one(const AdamArgs &a, const AdamPtrs &q, int i, float g)
 {
+    // every operation individually rounded (no FMA contraction): the optimiser kernels that share this function (stand-alone,
+    // fused behind the weight-gradient kernel, all-reduce) then produce bit-identical parameters by construction
     float mi = q.m[i], vi = q.v[i], p = q.local[i];
-    mi = mi + (g - mi) * a.beta1_c;
-    vi = vi * a.beta2 + a.beta2_c * g * g;
-    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
-    p = p - a.step_size * (mi / denom);
+    mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(g, mi), a.beta1_c));                                  // exp_avg.lerp_(grad, 1 - beta1)
+    vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.beta2_c, g), g));               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), a.bc2_sqrt), a.eps);                 // (sqrt(v) / sqrt(bc2)).add_(eps)
+    p = __fsub_rn(p, __fmul_rn(a.step_size, __fdiv_rn(mi, denom)));                              // param.addcdiv_(m, denom, -step_size)
     q.m[i] = mi; q.v[i] = vi; q.local[i] = p;
     const int im = q.img_map[i];
     q.img_local[im] = p;

@@ -38,6 +38,7 @@ struct TcTrainArgs {
     float inv_global_b;
     float *act_buf, *dz_buf;           // per-sample scratch rows
     float *loss_partials;              // [grid]
+    int32_t loss_kind;                 // 0 MSE (reference), 1 Huber (delta = 1)
 };
 
 struct TcDwArgs {
@@ -209,8 +210,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         const float diff = qa - s_y[row];
                         const float wb = a.src.is_w ? a.src.is_w[gb] : 1.f;
                         if (a.src.abs_err) a.src.abs_err[gb] = fabsf(diff);
-                        atomicAdd(&s_loss, wb * (diff * diff));
-                        gq = (2.f * diff * wb) * a.inv_global_b;
+                        if (a.loss_kind == 0) {                       // MSELoss (BaseTrainer.py:40)
+                            atomicAdd(&s_loss, wb * (diff * diff));
+                            gq = (2.f * diff * wb) * a.inv_global_b;
+                        } else {                                      // SmoothL1Loss(beta = 1)
+                            const float ad = fabsf(diff);
+                            atomicAdd(&s_loss, wb * (ad < 1.f ? 0.5f * (diff * diff) : ad - 0.5f));
+                            gq = (fminf(fmaxf(diff, -1.f), 1.f) * wb) * a.inv_global_b;
+                        }
                     }
                     float g[32];
                     const float inv = 1.f / (float)nA;
@@ -309,34 +316,38 @@ constexpr int kDwABlocks = 4;                               // A operand: M = 12
 
 // rows [128 samples][width floats] in global memory -> hi/lo MN-major operand blocks.  8 consecutive lanes copy one 128-byte
 // row segment (coalesced), each as ONE 16-byte store into the swizzled position: no transposition, no bank conflicts.
+// LOG2F4 = log2(float4 per row) (5 for the 128-wide A operand, 3 / 4 for a 32- / 64-wide B operand); U float4 per thread,
+// ALL loaded before the first is converted (the loads are the latency that matters: one round trip per operand).
 // ones_col >= 0: that feature column is set to 1 for valid samples (bias gradient).
-template <int U>
-__device__ __forceinline__ void dw_build_operand(const float *const *rows, int n_f4, int width, int ones_col, unsigned char *hi, unsigned char *lo)
+template <int LOG2F4, int U>
+__device__ __forceinline__ void dw_load_rows(const float *const *rows, int width, int ones_col, float4 (&v)[U])
 {
-    const int total = kDwChunk * n_f4;
-    for (int i0 = threadIdx.x; i0 < total; i0 += U * kTcThreads) {
-        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * kTcThreads;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < total) {
-                const int b = i / n_f4, jc = i - b * n_f4;
-                if (rows[b] && 4 * jc < width) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[b]) + jc);
-                if (rows[b] && ones_col >= 0 && (ones_col >> 2) == jc) reinterpret_cast<float *>(&v[u])[ones_col & 3] = 1.f;
+    for (int u = 0; u < U; ++u) {
+        const int i = threadIdx.x + u * kTcThreads;
+        const int b = i >> LOG2F4, jc = i & ((1 << LOG2F4) - 1);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < kDwChunk && rows[b]) {
+            if (4 * jc < width) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[b]) + jc);
+            if (ones_col >= 0 && (ones_col >> 2) == jc) {       // K_real % 4 == 0 (tc_train_init): the ones column is component 0
+                v[u].x = 1.f;
             }
         }
+    }
+}
+template <int LOG2F4, int U>
+__device__ __forceinline__ void dw_store_rows(const float4 (&v)[U], unsigned char *hi, unsigned char *lo)
+{
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * kTcThreads;
-            if (i >= total) continue;
-            const int b = i / n_f4, jc = i - b * n_f4;
-            float4 h, l;
-            tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
-            const uint32_t off = umma_mn_off(4 * jc, b, kDwBlk);
-            *reinterpret_cast<float4 *>(hi + off) = h;
-            *reinterpret_cast<float4 *>(lo + off) = l;
-        }
+    for (int u = 0; u < U; ++u) {
+        const int i = threadIdx.x + u * kTcThreads;
+        const int b = i >> LOG2F4, jc = i & ((1 << LOG2F4) - 1);
+        if (b >= kDwChunk) continue;
+        float4 h, l;
+        tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+        const uint32_t off = umma_mn_off(4 * jc, b, kDwBlk);
+        *reinterpret_cast<float4 *>(hi + off) = h;
+        *reinterpret_cast<float4 *>(lo + off) = l;
     }
 }
 
@@ -383,11 +394,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // built from replay rows (written >= 2 kernels back) and is gathered before the wait
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
-    const int wA = 32 * kDwABlocks;                            // 128 columns: features, the ones column, zero padding
-    dw_build_operand<8>(rows, wA / 4, T.K_real, T.K_real, Ahi, Alo);
-    DW_TRACE(2);
+    // A: 128 samples x 128 columns (features, the ones column, zero padding) = 16 float4 per thread; B: 128 x N_pad
+    float4 va[16], vb[8];
+    dw_load_rows<5, 16>(rows, T.K_real, T.K_real, va);
     if (l == 0) { pdl_wait(); pdl_trigger(); }
-    dw_build_operand<8>(drows, T.N_pad / 4, T.N_pad, -1, Bhi, Blo);
+    if (T.N_pad == 32) {
+#pragma unroll
+        for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dw_load_rows<3, 4>(drows, 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+    } else {
+        dw_load_rows<4, 8>(drows, 64, -1, vb);                  // N_pad = 64: two 32-column blocks, kDwBlk apart
+    }
+    DW_TRACE(2);
+    dw_store_rows<5, 16>(va, Ahi, Alo);
+    if (T.N_pad == 32) dw_store_rows<3, 4>(reinterpret_cast<float4 (&)[4]>(vb), Bhi, Blo);
+    else dw_store_rows<4, 8>(vb, Bhi, Blo);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -402,22 +423,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     mbar_wait(&mbar, 0);
     tc_fence_after();
     DW_TRACE(6);
-    // epilogue: accumulator row f = input feature (or the ones column), column o = output unit
+    // epilogue: accumulator row f = input feature (or the ones column), column o = output unit.  Lanes hold consecutive f:
+    // every store instruction writes 32 consecutive floats of one weight row.
     float *part = a.partials + (size_t)chunk * a.P;
     const int f = quad * 32 + lane;
     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
         if (quad * 32 >= rowsA) break;
         float v[32];
         tmem_ld32_sum(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, tc.concat ? (uint32_t)T.N_pad : 0u, v);
-        if (f < rowsA) {
+        if (f < T.K_real) {
+            float *wrow = part + T.w_off + f;                                            // + o * K_real
+            float *vrow = part + (T.w2_off >= 0 ? T.w2_off : 0) + f - T.out_main * T.K_real;  // dueling value head rows
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int o = c0 + j;                                                    // warp-uniform
+                if (o < T.out_main) wrow[o * T.K_real] = v[j];
+                else if (o < T.N_real) vrow[o * T.K_real] = v[j];
+            }
+        } else if (f == T.K_real) {                                                      // the ones column: bias gradients
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int o = c0 + j;
-                if (o < T.N_real) {
-                    const bool vrow = o >= T.out_main;                                   // dueling value head row
-                    if (f < T.K_real) part[vrow ? T.w2_off + (o - T.out_main) * T.K_real + f : T.w_off + o * T.K_real + f] = v[j];
-                    else part[vrow ? T.b2_off + (o - T.out_main) : T.b_off + o] = v[j];
-                }
+                if (o < T.out_main) part[T.b_off + o] = v[j];
+                else if (o < T.N_real) part[T.b2_off + (o - T.out_main)] = v[j];
             }
         }
     }
@@ -481,7 +509,7 @@ int tc_train_init(uavrl_learner *l)
     l->tc_train_ok = false;
     const TcNet &tc = l->tc;
     for (int i = 0; i < tc.n_layers; ++i)
-        if (tc.L[i].K_real + 1 > 128 || tc.L[i].K_real % 4 != 0 || tc.L[i].N_pad % 32 != 0) return 0;   // ones column / float4 chunks / 32-wide blocks
+        if (tc.L[i].K_real + 1 > 128 || tc.L[i].K_real % 4 != 0 || (tc.L[i].N_pad != 32 && tc.L[i].N_pad != 64)) return 0;   // ones column / float4 chunks / 1-2 blocks
     // the M=128 MMA reads 16 row groups from each A buffer: with fewer real rows it runs into the next buffers,
     // which must still be inside the CTA's allocation
     if (train_smem_bytes(tc, 32) > 227 * 1024 || dw_smem_bytes(tc) > 227 * 1024) return 0;
@@ -497,7 +525,7 @@ int tc_train_init(uavrl_learner *l)
     return 0;
 }
 
-std::atomic<int> g_fuse_dw_adam{1};          // uavrl_set_fuse_dw_adam(); default on
+std::atomic<int> g_fuse_dw_adam{0};          // uavrl_set_fuse_dw_adam(); default off: measured no faster than the PDL-chained pair
 
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
                     int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain, const AdamArgs *adam, float *loss_out, bool *adam_done)
@@ -507,6 +535,7 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     memset(&a, 0, sizeof(a));
     a.img = l->tc_img_local; a.src = src; a.B = B; a.y = y; a.inv_global_b = 1.0f / (float)global_batch;
     a.act_buf = l->act_buf; a.dz_buf = l->dz_buf; a.loss_partials = l->loss_partials;
+    a.loss_kind = l->cfg.loss_kind;
     a.R = (B >= 64 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
     a.n_tiles = (B + a.R - 1) / a.R;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;

@@ -195,6 +195,11 @@ class EnvBatch:
         check(_lib.lib().uavrl_env_get_energy(self.h, _ptr(out)))
         return out
 
+    def get_energy_total(self):
+        t = C.c_double()
+        check(_lib.lib().uavrl_env_get_energy_total(self.h, C.byref(t)))
+        return t.value
+
     def get_path(self, e, which=0):
         """UAV.path of tracked UAV e: which = 0 the episode in progress, 1 the last finished episode -> [n, 3]."""
         buf = np.zeros((self._track_cap, 3), np.float64)
@@ -228,9 +233,10 @@ class Learner:
     """Q-network + Adam + replay on one GPU (DQN / DDQN / DuelingDQN trainers of the reference)."""
 
     def __init__(self, in_dim=OBS_DIM, hidden=(64, 64), n_actions=27, dueling=False, algo=ALGO_DDQN, lr=5e-4,
-                 gamma=0.99, batch_size=64, update_loop=3, replay_capacity=10000, lockstep_envs=0, seed=42, device=0):
+                 gamma=0.99, batch_size=64, update_loop=3, replay_capacity=10000, lockstep_envs=0, seed=42, device=0, loss="mse"):
         self.device = torch.device("cuda", device)
         c = _lib.LearnerConfig()
+        c.loss_kind = {"mse": 0, "huber": 1}[loss]
         c.in_dim, c.n_hidden, c.n_actions, c.dueling, c.algo = in_dim, len(hidden), n_actions, int(dueling), algo
         for i, h in enumerate(hidden):
             c.hidden[i] = int(h)

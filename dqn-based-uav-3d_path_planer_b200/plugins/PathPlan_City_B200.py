@@ -32,7 +32,6 @@ class UAVBatchView:
         self.Step = 0
         self.done = False
         self.UEs = []
-        self.energy_cost_total = 0
         self.task_collect = 0
         self.transition_dict = {'states': [], 'actions': [], 'next_states': [], 'rewards': [], 'dones': []}
 
@@ -44,8 +43,41 @@ class UAVBatchView:
     def state(self):
         return self.env.states()
 
-    def record_list(self):
+    @property
+    def energy_cost_total(self):
+        """UAV.energy_cost_total (Agents/UAV.py:93) summed over the batch: the accumulated Calc_Fly_Power (UAV.py:239-245) when
+        the UAV XML carries <Power_param><Fly_power>, else 0 like the reference (which never accumulates it)."""
+        return self.env.batch.get_energy_total() if self.env.energy_enabled else 0
+
+    @energy_cost_total.setter
+    def energy_cost_total(self, v):
         pass
+
+    # UAV.Init_Record_Mod / record_list (Agents/UAV.py:269-307): logs/<name>_<time>.csv, one row per call
+    CSV_HEADER = ["sum_Episode", "Episode", " Score", " Avg.Score", "eps-greedy", "success", "failed", "meet_threaten", 'loss', 'ALL_UEs_D',
+                  'ALL_UEs_F', 'energy_cost', 'task_collect', 'Energy_Efficent', 'UE_waiting_time', 'Covered_rate', 'task_executed',
+                  'executed_rate', 'KL', 'Train_time', 'Testing_time']
+
+    def Init_Record_Mod(self, directory="logs"):
+        import csv
+        import datetime
+        os.makedirs(directory, exist_ok=True)
+        cur_time = datetime.datetime.now().strftime('%m_%d_%Y(%H_%M_%S)')
+        self.csv_path = os.path.join(directory, '%s_%s.csv' % (self.name, cur_time))
+        self._csv_file = open(self.csv_path, 'a+', newline="")
+        self.CsvWriter = csv.writer(self._csv_file)
+        self.CsvWriter.writerow(self.CSV_HEADER)
+
+    def record_list(self):
+        """One row in the reference's column order (UAV.py:280-307); the UE / task columns are 0 (no UEs on this path)."""
+        if getattr(self, "CsvWriter", None) is None:
+            return
+        res = self.env.result
+        energy = self.energy_cost_total
+        self.CsvWriter.writerow([self.Trainer.epoch, self.Trainer.epoch, self.score, self.score, res.get('eps', 0), res.get('success', 0),
+                                 res.get('lose', 0), res.get('meet_threaten', 0), res.get('loss', 0), 0, 0, energy, self.task_collect,
+                                 self.task_collect / (energy + 0.001), 0, 0, 0, 0, [], self.Train_time, self.Testing_time])
+        self._csv_file.flush()
 
     def reset(self):
         self.env.Scene_Random_Reset()
@@ -100,6 +132,18 @@ class PathPlan_City_B200:
                                        rrt_step=self.sub_granularity)
         self.batch.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
         self._next_first = 0
+        # optional models of the UAV (uavrl_env_set_extras): the energy model when the UAV XML carries the reference's
+        # <Power_param><Fly_power> block (config/UAV.xml:27-36), trajectory recording for path.csv when record_csv = 1
+        self.record_csv = int(None2Value(param.get("record_csv"), 0))
+        fp = (self.uav_dict.get("Power_param") or {}).get("Fly_power") if isinstance(self.uav_dict.get("Power_param"), dict) else None
+        self.energy_enabled = fp is not None
+        power = None
+        if fp is not None:
+            power = {k: float(fp[k]) for k in ("P_i", "v_0", "d_0", "rho", "s", "A", "P_b", "F_b")}
+            power["xi"] = 0.8                                      # UAV.py:58 with j = 0 (one shared parameter set)
+        if power is not None or self.record_csv:
+            self.batch.set_extras(power=power, track_envs=(1 if self.record_csv else 0),
+                                  track_capacity=(64 * self.uav_params.max_step if self.record_csv else 0))
         # trainer (one, shared)
         tpath = os.path.normpath(agents_params['Trainer']['Trainer_path'])
         tdict = XML2Dict(tpath).get('Trainer')
@@ -117,6 +161,8 @@ class PathPlan_City_B200:
             mod = importlib.import_module(ttype)
         self.Trainer = getattr(mod, ttype)(tdict)
         self.Agents = [UAVBatchView(self)]
+        if self.record_csv:
+            self.Agents[0].Init_Record_Mod()
         self.result = {}
         self.epoch = 0
         self.print_loop = int(None2Value(param.get('print_loop'), 2))
@@ -240,7 +286,23 @@ class PathPlan_City_B200:
                            step=iters, env_steps=steps, updates=updates, collisions=coll, episodes=ended)
         self.epoch += 1
         self.executed_time += dt
+        if self.record_csv:
+            self._write_path_csv()
+            if self.print_loop > 0 and self.epoch % self.print_loop == 0:
+                ag.record_list()                                   # PathPlan_City.run_eposide :463-468 (every print_loop episodes)
         return self.result
+
+    def _write_path_csv(self, path="path.csv"):
+        """UAV.py:461-464 / :479-482 / :505-508: at a terminal step the reference rewrites path.csv (CWD-relative) with the
+        finished episode's UAV.path, one x,y,z row per step.  Here: the last finished episode of the tracked UAV 0."""
+        import csv
+        pts = self.batch.get_path(0, which=1)
+        if len(pts) == 0:
+            return
+        with open(path, 'w', newline='') as f:
+            w = csv.writer(f)
+            for row in pts:
+                w.writerow([float(row[0]), float(row[1]), float(row[2])])
 
     def run_XML_scene(self):
         pass

@@ -104,6 +104,11 @@ void ora_act(const ora_net *n, const float *params, const float *x, int32_t B, f
  * mean(w_i (Q-y)^2), |Q-y| per sample returned for ReplayTree.batch_update.  The reference multiplies the importance
  * weights into the loss the same way (SAC_Trainer.py:348-352) but on the already averaged loss, which is not
  * back-propagatable; the per-sample form is the standard one. */
+/* 0 = MSE (every reference trainer, BaseTrainer.py:40); 1 = Huber = torch.nn.SmoothL1Loss(beta = 1), the option the
+ * product offers beside it.  Test-only switch. */
+static int g_loss_kind = 0;
+void ora_set_loss_kind(int32_t k) { g_loss_kind = k; }
+
 static float dqn_update_impl(const ora_net *n, int32_t algo, float *local, const float *target,
                      float *m, float *v, int64_t *t,
                      const float *s, const int32_t *a, const float *r, const float *s2,
@@ -140,8 +145,15 @@ static float dqn_update_impl(const ora_net *n, int32_t algo, float *local, const
             const float diff = q[a[b]] - y;
             const float wb = is_w ? is_w[b] : 1.f;
             if (abs_err_out) abs_err_out[b] = fabsf(diff);
-            lsum += (double)(wb * (diff * diff));
-            const float gq = (2.f * diff * wb) / (float)B;                /* d mean(w (Q-y)^2) / dQ */
+            float gq;
+            if (g_loss_kind == 0) {
+                lsum += (double)(wb * (diff * diff));
+                gq = (2.f * diff * wb) / (float)B;                        /* d mean(w (Q-y)^2) / dQ */
+            } else {
+                const float ad = fabsf(diff);
+                lsum += (double)(wb * (ad < 1.f ? 0.5f * (diff * diff) : ad - 0.5f));
+                gq = ((diff > 1.f ? 1.f : diff < -1.f ? -1.f : diff) * wb) / (float)B;
+            }
             /* backward through the head(s) */
             float dh[MAXW], dh_prev[MAXW];
             const int top = n->n_hidden;          /* index of the A / plain head */

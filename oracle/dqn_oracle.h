@@ -16,6 +16,8 @@
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
+void ora_set_loss_kind(int32_t k);   /* 0 MSE (reference), 1 Huber / SmoothL1(beta=1) */
+
 #endif
 
 #define ORA_MAX_HIDDEN 4

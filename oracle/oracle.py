@@ -281,6 +281,11 @@ class OracleLearner:
         return (float(loss), grads) if is_w is None else (float(loss), grads, abs_err)
 
 
+def set_loss_kind(kind):
+    """0 = MSE (what every reference trainer uses), 1 = Huber / SmoothL1Loss(beta=1) for the learner oracle."""
+    lib().ora_set_loss_kind(C.c_int32({"mse": 0, "huber": 1}.get(kind, kind)))
+
+
 def set_threads(n=0):
     """Set (n > 0) / query the number of host threads the oracle's batched loops use."""
     return int(lib().ora_set_threads(C.c_int32(n)))

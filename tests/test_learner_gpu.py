@@ -171,3 +171,33 @@ def test_data_parallel_split_equals_fused_update(dqn_golden):
     assert np.array_equal(Ls[0].get_params(1), Ls[1].get_params(1))
     for L in Ls:
         L.close()
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_huber_loss_option_vs_oracle(dqn_golden, tc):
+    """loss_kind = 1 (Huber / SmoothL1Loss(beta = 1), an option beside the reference's MSE): tensor-core and fp32 paths
+    against the oracle, whose Huber form is pinned to torch autograd (tests/test_oracle_golden.py)."""
+    from uavrl_b200 import engine
+    g = dqn_golden
+    name = "ddqn_qvalue3"
+    net = O.make_net(100, [64, 64], 27, 0)
+    L = engine.Learner(100, [64, 64], 27, False, 1, lr=5e-4, gamma=0.99, batch_size=64, update_loop=3, replay_capacity=1000, loss="huber")
+    assert L.set_tensor_cores(tc) == tc
+    L.set_params(g[name + "_local0"], 0); L.set_params(g[name + "_target0"], 1)
+    O.set_loss_kind("huber")
+    try:
+        OL = O.OracleLearner(net, 1, g[name + "_local0"], update_loop=3)
+        OL.target[:] = g[name + "_target0"]
+        loss = torch.zeros(1, device="cuda")
+        for step in range(6):
+            r = g["batch_r"][step] * 3.0                          # part of the batch beyond |Q - y| = 1: the linear branch
+            L.update_batch(dev(g["batch_s"][step]), dev(g["batch_a"][step], torch.int32), dev(r), dev(g["batch_s2"][step]),
+                           dev(g["batch_d"][step]), loss)
+            lo, grads = OL.update(g["batch_s"][step], g["batch_a"][step], r, g["batch_s2"][step], g["batch_d"][step])
+            torch.cuda.synchronize()
+            assert np.isclose(float(loss), lo, rtol=2e-5), (step, float(loss), lo)
+            np.testing.assert_allclose(L.get_params(4), grads, rtol=2e-4, atol=2e-6)
+            np.testing.assert_allclose(L.get_params(0), OL.local, rtol=0, atol=2e-5)
+    finally:
+        O.set_loss_kind("mse")
+    L.close()

@@ -37,3 +37,26 @@ def test_uav_parameters_follow_reference_casts(env_golden):
 def test_epsilon_annealing_kat(dqn_golden):
     for mx, mn, ep, want in dqn_golden["eps_schedule"]:
         assert xmlconfig.epsilon_annealing(ep, mn, mx) == want
+
+
+def test_seeded_city_generator_matches_reference_script(tmp_path):
+    """configs/generate_city.py == the reference's config/generate_building.py run after random.seed(seed) (golden recorded by
+    executing the reference script), and its XML parses back to the same table through the plug-ins' loader."""
+    import importlib.util
+    import os
+    import numpy as np
+    from conftest import GOLDEN, ROOT
+    from uavrl_b200.plugins import xmlconfig
+    spec = importlib.util.spec_from_file_location("generate_city", os.path.join(ROOT, "configs", "generate_city.py"))
+    gc = importlib.util.module_from_spec(spec); spec.loader.exec_module(gc)
+    g = np.load(os.path.join(GOLDEN, "city_golden.npz"))
+    for key in g.files:
+        seed, n = int(key.split("_")[0][4:]), int(key.split("_n")[1])
+        t = gc.generate_city(seed, n)
+        assert np.array_equal(t, g[key]), key
+        path = os.path.join(tmp_path, key + ".xml")
+        gc.write_buildings_xml(t, path)
+        th = xmlconfig.XML2Dict(path)["buildings"]["Threaten"]
+        back = np.array([[float(x["position"]["x"]), float(x["position"]["y"]), float(x["position"]["z"]), float(x["_R"]), float(x["_H"])] for x in th])
+        assert np.array_equal(back, t)
+    assert (t[:, 3] >= 10).all() and (t[:, 3] <= 50).all() and (t[:, :2] >= 0).all() and (t[:, :2] <= 500).all()

@@ -197,3 +197,78 @@ def test_prioritised_replay_through_the_trainer_plugin():
     assert np.array_equal(after[untouched], leaves[untouched])
     res = tr.learn_off_policy()
     assert res["sum_epoch"] == 2 and np.isfinite(float(res["loss"]))
+
+
+def test_env_plugin_writes_csv_path_and_energy(tmp_path):
+    """record_csv = 1 + the reference's <Power_param><Fly_power> block: run_eposide leaves logs/<name>_<time>.csv with the
+    reference's header (Agents/UAV.py:269-277) and one row per print_loop episodes, path.csv with the finished episode's
+    x,y,z rows (UAV.py:461-464), and energy_cost_total = accumulated Calc_Fly_Power; checkpoints appear every save_loop
+    epochs although the loop runs on the device (DuelingDQN_Trainer.py:187-188)."""
+    import csv
+    import importlib
+    from uavrl_b200.plugins import xmlconfig
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        cfg = xmlconfig.XML2Dict(os.path.join(ROOT, "configs", "PathPlan_City_B200.xml"))["simulator"]
+        ed = cfg["env"]
+        ed["num_UAV"], ed["scenario_pool"], ed["record_csv"], ed["print_loop"] = "128", "256", "1", "1"
+        ed["Agent"]["xml_path_agent"] = os.path.join(ROOT, "configs", "UAV_energy_B200.xml")
+        ed["Obstacles"]["buildings"] = os.path.join(ROOT, "configs", "buildings.xml")
+        ed["Agent"]["Trainer"]["Trainer_path"] = os.path.join(ROOT, "configs", "Trainer_DDQN_B200.xml")
+        mod = importlib.import_module("uavrl_b200.plugins." + ed["Env_Type"])
+        os.chdir(tmp_path)                           # logs/, path.csv and Mod/ are CWD-relative like in the reference
+        orig = mod.XML2Dict
+
+        def patched(path):
+            d = orig(path)
+            if "Trainer" in d and isinstance(d["Trainer"], dict):
+                d["Trainer"].update(Batch_Size="128", replay_size="16384", save_loop="64", model_path=str(tmp_path / "Mod"))
+            return d
+        mod.XML2Dict = patched
+        try:
+            env = getattr(mod, ed["Env_Type"])(ed)
+        finally:
+            mod.XML2Dict = orig
+        info = env.run_eposide(0.3)
+        info = env.run_eposide(0.1)
+    finally:
+        os.chdir(cwd)
+    assert info["episodes"] >= 128
+    logs = os.listdir(tmp_path / "logs")
+    assert len(logs) == 1 and logs[0].startswith("UAV_batch_") and logs[0].endswith(".csv")
+    rows = list(csv.reader(open(tmp_path / "logs" / logs[0])))
+    assert rows[0][:9] == ["sum_Episode", "Episode", " Score", " Avg.Score", "eps-greedy", "success", "failed", "meet_threaten", "loss"]
+    assert len(rows) == 3 and len(rows[1]) == 21 and float(rows[2][11]) > 0          # energy_cost column
+    pts = np.array([[float(x) for x in r] for r in csv.reader(open(tmp_path / "path.csv"))])
+    assert pts.ndim == 2 and pts.shape[1] == 3 and len(pts) >= 2
+    assert (np.abs(np.diff(pts[:, :2], axis=0)).max(1) <= 1.0 + 1e-9).all()          # one step of at most Max_V per row
+    assert env.Agents[0].energy_cost_total > 0
+    saved = sorted(os.listdir(tmp_path / "Mod"))
+    assert saved == ["q_local_DDQN_UAV_0.pth", "q_target_DDQN_UAV_0.pth"], saved
+
+
+def test_is_train_0_is_greedy_in_the_device_loop(tmp_path):
+    """Trainer.Is_Train = 0 (evaluation): get_action is greedy whatever eps is (DuelingDQN_Trainer.py:90) also inside the
+    device-resident loop -- every stored action equals argmax_a q_local(state) -- and update() still counts epochs."""
+    from uavrl_b200 import engine
+    tr = make("DDQN_Trainer_B200", "QValueNet_SAC", tmp_path, Is_Train="0", lockstep_envs="64", replay_size="4096")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "env_golden.npz"))
+    city = engine.City(g["dims"][0], g["dims"][1], g["dims"][2], g["buildings"])
+    p = g["uav_params"]
+    env = engine.EnvBatch(city, engine.UavParams(p[0], p[1], p[2], 1.0, int(p[3])), 64, max_subgoals=64, auto_reset=True)
+    sc = env.make_scenarios(128, seed=3)
+    env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+    env.reset(0)
+    st = engine.train_run(env, tr._learner, 20, 0.9, 1, False)
+    assert st.env_steps == 64 * 20
+    s, a, r, s2, d = tr._learner.gather(np.arange(64 * 20))
+    q = tr.get_q(s)
+    top2 = np.sort(q, 1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5
+    assert clear.mean() > 0.95 and np.array_equal(a[clear], q.argmax(1)[clear])
+    e0 = tr.epoch
+    tr.update({"states": s[:8].tolist(), "actions": a[:8].tolist(), "next_states": s2[:8].tolist(), "rewards": r[:8].tolist(),
+               "dones": d[:8].tolist()})
+    assert tr.epoch == e0 + 1
+    env.close()

@@ -107,9 +107,9 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
                                    st.sum_reward, st.last_loss)))
             env.close(); L.close()
     finally:
-        _lib.lib().uavrl_set_pdl(1)                 # library defaults: PDL on, fused act+step off, optimiser fused behind dW
+        _lib.lib().uavrl_set_pdl(1)                 # library defaults: PDL on, fused act+step off, optimiser not fused behind dW
         _lib.lib().uavrl_set_fuse_act_env(0)
-        _lib.lib().uavrl_set_fuse_dw_adam(1)
+        _lib.lib().uavrl_set_fuse_dw_adam(0)
     a = out[0]
     for b in out[1:]:
         assert a["stats"][:6] == b["stats"][:6] and a["stats"][1] == 150 and a["stats"][7] == b["stats"][7]
