@@ -588,7 +588,6 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
             UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, (size_t)B * (size_t)l->tc.dz_stride * 4));
             l->train_cap = B;
         }
-        if ((B + 127) / 128 > l->max_ctas) return fail(UAVRL_ERR_INVALID, "batch too large for the gradient partial buffer");
         const bool may_fuse = apply && !partials_only && !per_batch;
         int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st, mid ? mid[1] : nullptr,
                                  may_fuse ? &a : nullptr, loss_out ? loss_out : l->loss_dev, &adam_done);

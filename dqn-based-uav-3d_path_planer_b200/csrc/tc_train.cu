@@ -44,8 +44,9 @@ struct TcTrainArgs {
 struct TcDwArgs {
     BatchSrc src;
     int32_t B, n_chunks, P;
+    int32_t n_slices;                  // CTAs per layer; slice i accumulates chunks i, i + n_slices, ... into partial i
     const float *act_buf, *dz_buf;
-    float *partials;                   // [n_chunks][P]
+    float *partials;                   // [n_slices][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
     // fused optimiser tail (fuse_adam = 1, only when every CTA of the grid is resident at once)
     int32_t fuse_adam;
@@ -354,38 +355,37 @@ __device__ __forceinline__ void dw_store_rows(const float4 (&v)[U], unsigned cha
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int l = blockIdx.x % tc.n_layers, chunk = blockIdx.x / tc.n_layers;
+    const int l = blockIdx.x % tc.n_layers, slice = blockIdx.x / tc.n_layers;
+    const int chunk = slice;                                  // partial index
     const TcLayer T = tc.L[l];
     const int rowsA = T.K_real + 1;                           // input features + the all-ones column (bias gradient)
-    const int nbB = T.N_pad / 32;                             // 32-wide output blocks of dZ (N_pad is 32 or 64 ...)
+    const int nbB = T.N_pad / 32;                             // 32-wide output blocks of dZ (N_pad is 32 or 64)
     // A = [act ; 1] as [sample][feature], 4 feature blocks (M = 128; columns past rowsA are zero), hi then lo;
     // B = dZ as [sample][out], hi blocks then lo blocks (adjacent: the concatenated 3xTF32 product reads them as N = 2 N_pad)
     unsigned char *Ahi = smem, *Alo = Ahi + kDwABlocks * kDwBlk, *Bhi = Alo + kDwABlocks * kDwBlk, *Blo = Bhi + nbB * kDwBlk;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ const float *rows[kDwChunk];
-    __shared__ const float *drows[kDwChunk];
+    __shared__ const float *rows[2][kDwChunk];               // double buffered: chunk c + 1 is resolved while chunk c is loaded
+    __shared__ const float *drows[2][kDwChunk];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
     DW_TRACE(0);
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
     if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
-    const int b0 = chunk * kDwChunk;
-    if (tid < kDwChunk) {
-        const int b = b0 + tid;
-        const float *p = nullptr, *dzp = nullptr;
-        if (b < a.B) {
-            if (l == 0) {
-                uint32_t pkey[4];
-                Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
-                p = resolve_transition(a.src, b, tc.in_dim, pkey).s;
-            } else {
-                p = a.act_buf + (size_t)b * tc.act_stride + T.act_off;
+    uint32_t pkey[4];
+    Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+    auto resolve_chunk = [&](int c, int buf) {                // row pointers of chunk c (128 samples)
+        if (tid < kDwChunk) {
+            const int b = c * kDwChunk + tid;
+            const float *p = nullptr, *dzp = nullptr;
+            if (c < a.n_chunks && b < a.B) {
+                p = (l == 0) ? resolve_transition(a.src, b, tc.in_dim, pkey).s : a.act_buf + (size_t)b * tc.act_stride + T.act_off;
+                dzp = a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off;
             }
-            dzp = a.dz_buf + (size_t)b * tc.dz_stride + T.dz_off;
+            rows[buf][tid] = p; drows[buf][tid] = dzp;
         }
-        rows[tid] = p; drows[tid] = dzp;
-    }
+    };
+    resolve_chunk(slice, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -394,33 +394,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // built from replay rows (written >= 2 kernels back) and is gathered before the wait
     if (l != 0) { pdl_wait(); pdl_trigger(); }
     DW_TRACE(1);
-    // A: 128 samples x 128 columns (features, the ones column, zero padding) = 16 float4 per thread; B: 128 x N_pad
+    // A: 128 samples x 128 columns (features, the ones column, zero padding) = 16 float4 per thread; B: 128 x N_pad.
+    // Persistent over this slice's chunks: the loads of chunk c + 1 are in flight while the tensor core works on chunk c,
+    // whose products accumulate in the same TMEM columns -> one partial per slice however large the batch.
     float4 va[16], vb[8];
-    dw_load_rows<5, 16>(rows, T.K_real, T.K_real, va);
-    if (l == 0) { pdl_wait(); pdl_trigger(); }
-    if (T.N_pad == 32) {
+    auto load_chunk = [&](int buf) {
+        dw_load_rows<5, 16>(rows[buf], T.K_real, T.K_real, va);
+        if (T.N_pad == 32) {
 #pragma unroll
-        for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        dw_load_rows<3, 4>(drows, 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+            for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dw_load_rows<3, 4>(drows[buf], 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+        } else {
+            dw_load_rows<4, 8>(drows[buf], 64, -1, vb);         // N_pad = 64: two 32-column blocks, kDwBlk apart
+        }
+    };
+    if (l == 0) {                                              // replay rows first, dZ after the predecessor has finished
+        dw_load_rows<5, 16>(rows[0], T.K_real, T.K_real, va);
+        pdl_wait(); pdl_trigger();
+        if (T.N_pad == 32) {
+#pragma unroll
+            for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dw_load_rows<3, 4>(drows[0], 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+        } else {
+            dw_load_rows<4, 8>(drows[0], 64, -1, vb);
+        }
     } else {
-        dw_load_rows<4, 8>(drows, 64, -1, vb);                  // N_pad = 64: two 32-column blocks, kDwBlk apart
+        load_chunk(0);
     }
     DW_TRACE(2);
-    dw_store_rows<5, 16>(va, Ahi, Alo);
-    if (T.N_pad == 32) dw_store_rows<3, 4>(reinterpret_cast<float4 (&)[4]>(vb), Bhi, Blo);
-    else dw_store_rows<4, 8>(vb, Bhi, Blo);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    DW_TRACE(4);
-    if (tid == 0) {
-        issue_3xtf32_mn(tmem, umma_desc_mn(smem_u32(Ahi), kDwBlk), umma_desc_mn(smem_u32(Alo), kDwBlk), umma_desc_mn(smem_u32(Bhi), kDwBlk),
-                        umma_desc_mn(smem_u32(Blo), kDwBlk), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0);
-        umma_commit(&mbar);
+    uint32_t mphase = 0;
+    int it = 0;
+    for (int c = slice; c < a.n_chunks; c += a.n_slices, ++it) {
+        if (it > 0) { mbar_wait(&mbar, mphase); mphase ^= 1; tc_fence_after(); }     // the MMAs of the previous chunk have read SMEM
+        dw_store_rows<5, 16>(va, Ahi, Alo);
+        if (T.N_pad == 32) dw_store_rows<3, 4>(reinterpret_cast<float4 (&)[4]>(vb), Bhi, Blo);
+        else dw_store_rows<4, 8>(vb, Bhi, Blo);
+        const int cn = c + a.n_slices;
+        resolve_chunk(cn, (it + 1) & 1);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        DW_TRACE(4);
+        if (tid == 0) {
+            issue_3xtf32_mn(tmem, umma_desc_mn(smem_u32(Ahi), kDwBlk), umma_desc_mn(smem_u32(Alo), kDwBlk), umma_desc_mn(smem_u32(Bhi), kDwBlk),
+                            umma_desc_mn(smem_u32(Blo), kDwBlk), kTcTile, T.N_pad, kDwChunk / 8, tc.concat != 0, it > 0 ? 1u : 0u);
+            umma_commit(&mbar);
+        }
+        if (cn < a.n_chunks) load_chunk((it + 1) & 1);         // next chunk's rows -> registers while the MMAs run
     }
     DW_TRACE(5);
-    mbar_wait(&mbar, 0);
+    mbar_wait(&mbar, mphase);
     tc_fence_after();
     DW_TRACE(6);
     // epilogue: accumulator row f = input feature (or the ones column), column o = output unit.  Lanes hold consecutive f:
@@ -549,18 +573,21 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     memset(&d, 0, sizeof(d));
     d.src = src; d.B = B; d.n_chunks = (B + kDwChunk - 1) / kDwChunk; d.P = l->net.P;
     d.act_buf = l->act_buf; d.dz_buf = l->dz_buf; d.partials = l->partials;
-    const int dw_grid = d.n_chunks * tc.n_layers;
-    // Fused optimiser tail: the kernel's grid barrier needs every CTA resident at once -- one CTA per SM (192 KB of shared
-    // memory each), so only when the grid fits the SMs; larger batches keep the separate reduce_adam_kernel.
     static int n_sm = 0;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    // one CTA per SM (192 KB of shared memory): at most n_sm / n_layers slices per layer, each looping over its chunks
+    const int max_slices = n_sm / tc.n_layers > 0 ? n_sm / tc.n_layers : 1;
+    d.n_slices = d.n_chunks < max_slices ? d.n_chunks : max_slices;
+    const int dw_grid = d.n_slices * tc.n_layers;
+    // Fused optimiser tail: the kernel's grid barrier needs every CTA resident at once -- one CTA per SM (192 KB of shared
+    // memory each), so only when the grid fits the SMs; larger batches keep the separate reduce_adam_kernel.
     const bool fuse = adam != nullptr && g_fuse_dw_adam.load() && dw_grid <= n_sm;
     if (adam_done) *adam_done = fuse;
     if (fuse) {
         if (!l->dw_bar) { UAVRL_CUDA(cudaMalloc((void **)&l->dw_bar, 8)); UAVRL_CUDA(cudaMemsetAsync(l->dw_bar, 0, 8, st)); l->dw_bar_total = 0; }
         l->dw_bar_total += (unsigned long long)dw_grid;
         d.fuse_adam = 1; d.bar_count = l->dw_bar; d.bar_target = l->dw_bar_total;
-        d.adam = *adam; d.adam.nparts = d.n_chunks; d.adam.n_loss_parts = grid;
+        d.adam = *adam; d.adam.nparts = d.n_slices; d.adam.n_loss_parts = grid;
         AdamPtrs &q = d.ptrs;
         q.partials = l->partials; q.loss_partials = l->loss_partials; q.grad = l->grad; q.local = l->local; q.m = l->m; q.v = l->v;
         q.target = l->target; q.img_local = l->img_local; q.img_target = l->img_target; q.img_map = l->img_map;
@@ -583,7 +610,7 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
         for (int i = 1; i < 9; ++i) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
         fprintf(stderr, "\n");
     }
-    *n_grad_parts = d.n_chunks;
+    *n_grad_parts = d.n_slices;
     *n_loss_parts = grid;
     return 0;
 }

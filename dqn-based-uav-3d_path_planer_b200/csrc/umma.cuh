@@ -176,8 +176,9 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t
 
 // The three TF32 products for operands that are BOTH MN-major (layout above), contraction over K = 8 * ksteps.  The k-th
 // step starts 2 * sbo further (two 4-k groups).  concat: [B_hi ; B_lo] are adjacent mn blocks (lbo apart), see issue_3xtf32.
+// accumulate != 0: add to what the accumulator already holds (a CTA summing several sample chunks into one partial).
 __device__ __forceinline__ void issue_3xtf32_mn(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int M, int N,
-                                                int ksteps, bool concat, uint32_t sbo = kMnAtom)
+                                                int ksteps, bool concat, uint32_t accumulate = 0u, uint32_t sbo = kMnAtom)
 {
     const uint64_t kStep = (uint64_t)((2 * sbo) >> 4);
     const uint32_t mn = kUmmaAMajorMN | kUmmaBMajorMN;
@@ -185,10 +186,10 @@ __device__ __forceinline__ void issue_3xtf32_mn(uint32_t d, uint64_t a_hi, uint6
     uint64_t da = a_hi, db = b_hi;
     if (concat) {
         const uint32_t wide = umma_idesc_tf32(M, 2 * N) | mn;
-        umma_tf32(d, da, db, wide, 0u);
+        umma_tf32(d, da, db, wide, accumulate);
         for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, wide, 1u); }
     } else {
-        umma_tf32(d, da, db, idesc, 0u);
+        umma_tf32(d, da, db, idesc, accumulate);
         for (int k = 1; k < ksteps; ++k) { da += kStep; db += kStep; umma_tf32(d, da, db, idesc, 1u); }
         da = a_hi; db = b_lo;
         for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }

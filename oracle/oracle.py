@@ -281,6 +281,20 @@ class OracleLearner:
         return (float(loss), grads) if is_w is None else (float(loss), grads, abs_err)
 
 
+_apf_keep = None
+
+
+def set_apf(obstacle_v):
+    """APF_Enabled with moving obstacles (UAV.py:156-210, 448-453): obstacle_v [n, 3] = the obstacles' `v`; None = off."""
+    global _apf_keep
+    if obstacle_v is None:
+        _apf_keep = None
+        lib().ora_set_apf(None, 0)
+        return
+    _apf_keep = np.ascontiguousarray(obstacle_v, np.float64).reshape(-1, 3)
+    lib().ora_set_apf(_apf_keep.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(_apf_keep.shape[0]))
+
+
 def set_loss_kind(kind):
     """0 = MSE (what every reference trainer uses), 1 = Huber / SmoothL1Loss(beta=1) for the learner oracle."""
     lib().ora_set_loss_kind(C.c_int32({"mse": 0, "huber": 1}.get(kind, kind)))

@@ -92,6 +92,48 @@ double ora_fly_power(double V, double P_i, double v_0, double d_0, double rho, d
     return induced + parasite + blade;
 }
 
+/* ---- APF (moving obstacles): Agents/UAV.py:156-210, reward term :448-453.  The shipped obstacles carry no velocity
+ * (Obstacles/building.py:6-11) and APF_Enabled = 0 (config/UAV.xml:6); ora_set_apf() supplies the `v` attribute of every
+ * obstacle and switches the branch on (test-only global, like the reference's per-UAV flag).  NULL switches it off. */
+static const double *g_apf_v = 0;
+static int32_t g_apf_n = 0;
+void ora_set_apf(const double *obstacle_v, int32_t n) { g_apf_v = obstacle_v; g_apf_n = n; }
+
+/* UAV.cal_force :174-210 */
+ora_loc ora_cal_force(const ora_city *c, ora_loc p)
+{
+    ora_loc total = { 0, 0, 0 };
+    const ora_loc origin = { 0, 0, 0 };
+    double cum_force = 0;
+    for (int32_t i = 0; i < c->n_buildings && i < g_apf_n; ++i) {
+        const double *b = c->buildings + 5 * i;
+        const ora_loc v = { g_apf_v[3 * i], g_apf_v[3 * i + 1], g_apf_v[3 * i + 2] };
+        if (v.x == 0 && v.y == 0 && v.z == 0) continue;                       /* :180-182 */
+        const ora_loc centre = { b[0], b[1], b[2] };
+        const double dis = ora_distance(p, centre);                            /* :183 */
+        const double dis2edge = dis - b[3];                                    /* :185 */
+        if (dis2edge > 60) continue;                                           /* :186-187 */
+        const double vmag = ora_distance(origin, v);                           /* :189 */
+        double f1 = 1 * b[3] / (dis2edge * dis2edge);                          /* :190  min(1, w R / d^2) */
+        if (!(f1 < 1)) f1 = 1;
+        const double f1_seta = ora_angle(p, centre);                           /* :191 */
+        const double v_seta = ora_angle(origin, v);                            /* :193 */
+        if (dis2edge < 0) f1 = (-dis2edge > 2) ? -dis2edge : 2;                /* :196-197 max(-d, 2) */
+        const double f1x = -f1 * cos(f1_seta), f1y = -f1 * sin(f1_seta);       /* :198 */
+        double f2 = vmag * b[3] / (dis2edge * dis2edge);                       /* :200 */
+        if (!(f2 < 1)) f2 = 1;
+        const double f2x = f2 * cos(v_seta), f2y = f2 * sin(v_seta);           /* :201 */
+        cum_force += (f1 + f2);                                                /* :202 */
+        total.x = total.x + f1x + f2x;                                         /* :203  Loc.__add__ twice */
+        total.y = total.y + f1y + f2y;
+        total.z = total.z + 0 + 0;
+        /* :205-208: beyond 100 the reference calls Cal_SubTask_Dynamic() without its arguments (TypeError).  Unreachable with
+         * fewer than ~50 obstacles in range; the product returns the force accumulated so far, and so does this oracle. */
+        if (cum_force > 100) return total;
+    }
+    return total;
+}
+
 /* Agents/UAV.py:397-513  update_PathPlan */
 void ora_step(const ora_city *c, ora_uav *u, int32_t act_mode, double action, ora_step_out *out)
 {
@@ -149,8 +191,16 @@ void ora_step(const ora_city *c, ora_uav *u, int32_t act_mode, double action, or
     r -= 0.1;                                                  /* :438 */
     r -= 0.01 * fabs(u->pos.z - sg->z);                        /* :439-440 */
     u->path_len += u->V;                                       /* :443 */
-    /* :448-453 APF: obstacles carry no velocity in the shipped city -> cal_force skips all of
-     * them (UAV.py:180-182) and the term is exactly 0; not restated here. */
+    if (g_apf_v) {                                             /* :448-453, APF_Enabled == 1 */
+        for (int32_t i = u->cursor; i < u->n_sub; ++i) {       /* Adjust_subgoal :156-166: every remaining sub-goal moves */
+            const ora_loc f = ora_cal_force(c, u->sub[i]);
+            u->sub[i].x = u->sub[i].x + f.x; u->sub[i].y = u->sub[i].y + f.y; u->sub[i].z = u->sub[i].z + f.z;
+        }
+        const ora_loc total_force = ora_cal_force(c, u->pos);  /* :450 */
+        const double force = ora_distance(origin, total_force);                /* :451 */
+        const double tri_force = ora_angle(origin, total_force);               /* :452 */
+        r += 0.2 * force * cos(fabs(tri_force - tri_V));       /* :453 */
+    }
 
     if (u->step >= u->max_step) {                              /* :456-465 */
         u->done = 1;

@@ -13,13 +13,15 @@ from gpu_util import assert_close64, assert_obs, city_and_params
 pytestmark = pytest.mark.gpu
 
 
-def run_golden(g, env_golden, env27_golden, kind_name):
+def run_golden(g, env_golden, env27_golden, kind_name, apf_v=None):
     from uavrl_b200 import engine
     city, params, _, _ = city_and_params(env_golden, env27_golden)
     ne = int(g["epn_episodes"])
     eps = [episode(g, i) for i in range(ne)]
     K = eps[0]["sub"].shape[0]
     env = engine.EnvBatch(city, params, ne, max_subgoals=K, auto_reset=False)
+    if apf_v is not None:
+        env.set_extras(obstacle_v=apf_v)
     env.set_pool(np.stack([e["start"] for e in eps]), np.stack([e["goal"] for e in eps]),
                  np.array([e["heading"] for e in eps]), np.stack([e["sub"] for e in eps]),
                  np.array([e["n_sub"] for e in eps]), np.array([e["alias0"] for e in eps]))
@@ -55,6 +57,13 @@ def run_golden(g, env_golden, env27_golden, kind_name):
                 assert_close64(st[k][i], e[k][t], 1e-9, w + " " + k)
             assert_obs(o["obs"][i], e["obs"][t], w)
             checked += 1
+        if apf_v is not None:                      # Adjust_subgoal: the whole remaining queue, shifted every step
+            subs = env.get_subgoals()
+            for i, e in enumerate(eps):
+                if t >= len(e["action"]):
+                    continue
+                c, n = int(e["cursor"][t]), int(e["n_sub"])
+                assert_close64(subs[i, c:n], e["subq"][t][:n - c], 1e-9, "sub-goal queue ep%d t%d" % (i, t))
     env.close()
     return checked
 
@@ -65,6 +74,65 @@ def test_golden_episodes_continuous(env_golden, env27_golden):
 
 def test_golden_episodes_discrete27(env_golden, env27_golden):
     assert run_golden(env27_golden, env_golden, env27_golden, "discrete27") > 4000
+
+
+def test_golden_episodes_apf_moving_obstacles(env_golden, env27_golden):
+    """APF_Enabled with moving obstacles (UAV.cal_force / Adjust_subgoal / the reward term, Agents/UAV.py:156-210, 448-453)
+    against 1750 steps of the unmodified reference UAV (tests/golden/make_apf_golden.py): every integer output exact, fp64
+    state and reward 1e-9, observation 1e-5 / bits exact, and every UAV's shifted sub-goal queue after every step."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "apf_golden.npz"))
+    assert np.array_equal(g["buildings"], env_golden["buildings"])
+    assert run_golden(g, env_golden, env27_golden, "continuous", apf_v=g["obstacle_v"]) == 1750
+
+
+def test_apf_against_oracle_with_auto_reset(env_golden, env27_golden):
+    """512 UAVs x 120 steps, discrete-27 actions, moving obstacles, in-kernel UAV.reset(): the APF step (per-UAV sub-goal
+    queues shifted every step, reloaded from the scenario at a restart) against the oracle, which is pinned bit-exact to
+    the reference's APF branch."""
+    from uavrl_b200 import engine
+    city, params, ocity, oparams = city_and_params(env_golden, env27_golden)
+    N, P, T, K = 512, 1024, 120, 64
+    rng = np.random.default_rng(31)
+    nb = env_golden["buildings"].shape[0]
+    vel = np.zeros((nb, 3)); mv = rng.uniform(size=nb) < 0.6
+    vel[mv, :2] = rng.normal(0, 1.5, (int(mv.sum()), 2))
+    env = engine.EnvBatch(city, params, N, max_subgoals=K, auto_reset=True)
+    sc = make_pool(env, P, seed=41)
+    env.set_extras(obstacle_v=vel)
+    env.reset(0)
+    scen = np.arange(N) % P
+    ob = O.OracleBatch(ocity, oparams, N, K)
+    ob.reset(sc["start"][scen], sc["goal"][scen], sc["heading"][scen], sc["sub"][scen], sc["n_sub"][scen])
+    O.set_apf(vel)
+    try:
+        resets = 0
+        for t in range(T):
+            a = rng.integers(0, 27, N).astype(np.int32)
+            out = env.step(torch.tensor(a, device="cuda"))
+            rew, done, info, coll, _ = ob.step_(a.astype(np.float64), O.ACT_DISCRETE27, want_obs=False)
+            o = {k: v.cpu().numpy() for k, v in out.items()}
+            assert np.array_equal(o["done"], done) and np.array_equal(o["info"], info), t
+            assert np.array_equal(o["collision"], coll) and np.array_equal(o["ended"], ob.done), t
+            st = env.get_state()
+            assert_close64(st["reward64"], rew, 1e-9, "reward t%d" % t)
+            resets += oracle_auto_reset(ob, sc, scen, N, P, ocity, oparams, K)
+            assert np.array_equal(st["cursor"], ob.cursor) and np.array_equal(st["step"], ob.step), t
+            for k in ("px", "py", "pz", "vx", "vy", "V"):
+                assert_close64(st[k], getattr(ob, k), 1e-9, "%s t%d" % (k, t))
+            assert_obs(o["obs"], ob.state(want64=True)[1], "obs t%d" % t)
+            subs = env.get_subgoals()
+            for e in range(0, N, 37):
+                c, n = int(ob.cursor[e]), int(ob.n_sub[e])
+                assert_close64(subs[e, c:n], ob.sub[e, c:n], 1e-9, "queue e%d t%d" % (e, t))
+            if t == 0:
+                aged = rng.integers(60, 150, N).astype(np.int32)
+                env.set_state(step=aged); ob.step[:] = aged
+        assert resets > N // 4
+    finally:
+        O.set_apf(None)
+    env.close()
 
 
 def test_threaten_rate_kat(env_golden, env27_golden):
