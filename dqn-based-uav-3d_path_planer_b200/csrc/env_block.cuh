@@ -120,38 +120,48 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     float (*s_obs)[kObsDim] = sm.obs;
     double (*s_pos)[EPB] = sm.pos;
     unsigned long long *s_mask = sm.mask;
-    for (int i = tid; i < d.k.n_cyl * 6; i += NT)
-        reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
-    __syncthreads();
     // PDL: the predecessor in the lockstep loops is the act kernel, which only writes `actions`; per-env state and
-    // the pool were last written by the previous env step.  Warp 0 loads its state first and waits just before it
-    // reads the action; the other warps have nothing to do until phase 2.
+    // the pool were last written by the previous env step.  The phase-1 lanes load their state (and the sub-goals the step
+    // will read) while the cylinder table is still on its way to shared memory, and wait just before they read the action;
+    // the other warps have nothing to do until phase 2.
     constexpr int NW1 = EPB / LPW;
     static_assert(EPB % LPW == 0 && LPW <= 32 && NW1 * 32 <= NT, "phase-1 warp layout");
     const int wp = tid >> 5, ln = tid & 31;
+    const int le = wp * LPW + ln;                            // local env of this lane (valid lanes only)
+    const int e = e0 + le;
+    const bool valid = (wp < NW1) && (ln < LPW) && (e < d.n);
+    EnvRegs s;
+    int scen = 0;
+    P3 sgc[3];                                               // sub-goal queue entries cursor, cursor + 1, cursor + 2 (prefetched)
+    s.px = 0.0; s.py = 0.0;
+    if (valid) {
+        s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
+        s.vx = d.vx[e]; s.vy = d.vy[e]; s.V = d.V[e];
+        s.score = d.score[e]; s.total = d.total[e]; s.path_len = d.path_len[e];
+        s.gx = d.gx[e]; s.gy = d.gy[e]; s.gz = d.gz[e];
+        s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
+        s.done = d.done[e]; s.alias = d.alias[e];
+        s.theta = d.theta[e];
+        scen = d.scen[e];
+        const bool apf_q = EXTRAS && (d.extras & kExtraApf);
+        const double *q = apf_q ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = s.cursor + j;
+            if (i < s.n_sub && i < d.K) { sgc[j].x = q[3 * i]; sgc[j].y = q[3 * i + 1]; sgc[j].z = q[3 * i + 2]; }
+            else { sgc[j].x = 0.0; sgc[j].y = 0.0; sgc[j].z = 0.0; }
+        }
+    }
+    const int cur0 = s.cursor;
+    for (int i = tid; i < d.k.n_cyl * 6; i += NT)
+        reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
+    __syncthreads();
     if (USE_PDL && wp >= NW1) { pdl_wait(); pdl_trigger(); }
 
     if (wp < NW1) {
-        const int le = wp * LPW + ln;                        // local env of this lane (valid lanes only)
-        const int e = e0 + le;
-        const bool valid = (ln < LPW) && (e < d.n);
         unsigned long long mask = 0ull;
         double px = 0.0, py = 0.0, pz = 0.0, rew = 0.0;
         int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
-        EnvRegs s;
-        int scen = 0;
-        if (valid) {
-            s.px = d.px[e]; s.py = d.py[e]; s.pz = d.pz[e];
-            s.vx = d.vx[e]; s.vy = d.vy[e]; s.V = d.V[e];
-            s.score = d.score[e]; s.total = d.total[e]; s.path_len = d.path_len[e];
-            s.gx = d.gx[e]; s.gy = d.gy[e]; s.gz = d.gz[e];
-            s.step = d.step[e]; s.cursor = d.cursor[e]; s.n_sub = d.n_sub[e];
-            s.done = d.done[e]; s.alias = d.alias[e];
-            s.theta = d.theta[e];
-            scen = d.scen[e];
-        } else {
-            s.px = 0.0; s.py = 0.0;
-        }
         // exact candidate cull, shared by the whole warp (the lanes beyond LPW would otherwise idle)
         mask = cull_mask_coop<LPW>(d, s_cyl, s.px, s.py, ln);
         if (valid) {
@@ -165,7 +175,14 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
                 const bool apf_on = EXTRAS && (d.extras & kExtraApf);
                 const double *q = apf_on ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
-                auto sub = [q](int i) { P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p; };
+                // entries cursor .. cursor + 2 were prefetched with the state (the step reads cursor and, after a pop, cursor + 1)
+                auto sub = [q, cur0, &sgc](int i) {
+                    const int j = i - cur0;
+                    if (j == 0) return sgc[0];
+                    if (j == 1) return sgc[1];
+                    if (j == 2) return sgc[2];
+                    P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; return p;
+                };
                 const Cyl *cyl = s_cyl;
                 const EnvConst kk = d.k;
                 auto threat = [&kk, cyl, mask](double x, double y, double z) {
@@ -228,8 +245,12 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 const double *q = own_q ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
                 const bool shift = own_q && DO_STEP;
                 const ApfObs *aob = d.apf_obs; const int an = d.k.n_cyl;
-                auto sub = [q, shift, aob, an](int i) {
-                    P3 p; p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2];
+                const bool same_q = !(DO_STEP && d.auto_reset && n_ended);       // still the queue the prefetch read
+                auto sub = [q, shift, aob, an, same_q, cur0, &sgc](int i) {
+                    P3 p;
+                    const int j = i - cur0;
+                    if (same_q && j >= 0 && j <= 2) p = (j == 0) ? sgc[0] : (j == 1) ? sgc[1] : sgc[2];
+                    else { p.x = q[3 * i]; p.y = q[3 * i + 1]; p.z = q[3 * i + 2]; }
                     if (EXTRAS && shift) { const P3 f = apf_force(aob, an, p.x, p.y, p.z); p.x = dadd(p.x, f.x); p.y = dadd(p.y, f.y); p.z = dadd(p.z, f.z); }
                     return p;
                 };

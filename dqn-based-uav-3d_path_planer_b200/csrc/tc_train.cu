@@ -321,31 +321,31 @@ constexpr int kDwABlocks = 4;                               // A operand: M = 12
 // ALL loaded before the first is converted (the loads are the latency that matters: one round trip per operand).
 // ones_col >= 0: that feature column is set to 1 for valid samples (bias gradient).
 template <int LOG2F4, int U>
-__device__ __forceinline__ void dw_load_rows(const float *const *rows, int width, int ones_col, float4 (&v)[U])
+__device__ __forceinline__ void dw_load_rows(const float *const *rows, int width, float4 (&v)[U])
 {
+    // nothing but loads here: a register that a load is still going to write must not be touched again before the data
+    // is consumed, or the warp stalls on that load before issuing the next one (the ones column is applied at store time)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int i = threadIdx.x + u * kTcThreads;
         const int b = i >> LOG2F4, jc = i & ((1 << LOG2F4) - 1);
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < kDwChunk && rows[b]) {
-            if (4 * jc < width) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[b]) + jc);
-            if (ones_col >= 0 && (ones_col >> 2) == jc) {       // K_real % 4 == 0 (tc_train_init): the ones column is component 0
-                v[u].x = 1.f;
-            }
-        }
+        const float *r = (b < kDwChunk) ? rows[b] : nullptr;
+        v[u] = (r && 4 * jc < width) ? __ldg(reinterpret_cast<const float4 *>(r) + jc) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
+// ones_col >= 0: that feature column (a multiple of 4: K_real % 4 == 0, tc_train_init) becomes 1 for valid samples
 template <int LOG2F4, int U>
-__device__ __forceinline__ void dw_store_rows(const float4 (&v)[U], unsigned char *hi, unsigned char *lo)
+__device__ __forceinline__ void dw_store_rows(const float4 (&v)[U], const float *const *rows, int ones_col, unsigned char *hi, unsigned char *lo)
 {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int i = threadIdx.x + u * kTcThreads;
         const int b = i >> LOG2F4, jc = i & ((1 << LOG2F4) - 1);
         if (b >= kDwChunk) continue;
+        float4 x = v[u];
+        if (ones_col >= 0 && (ones_col >> 2) == jc && rows[b]) x.x = 1.f;
         float4 h, l;
-        tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+        tf32_split(x.x, h.x, l.x); tf32_split(x.y, h.y, l.y); tf32_split(x.z, h.z, l.z); tf32_split(x.w, h.w, l.w);
         const uint32_t off = umma_mn_off(4 * jc, b, kDwBlk);
         *reinterpret_cast<float4 *>(hi + off) = h;
         *reinterpret_cast<float4 *>(lo + off) = l;
@@ -399,24 +399,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // whose products accumulate in the same TMEM columns -> one partial per slice however large the batch.
     float4 va[16], vb[8];
     auto load_chunk = [&](int buf) {
-        dw_load_rows<5, 16>(rows[buf], T.K_real, T.K_real, va);
+        dw_load_rows<5, 16>(rows[buf], T.K_real, va);
         if (T.N_pad == 32) {
 #pragma unroll
             for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dw_load_rows<3, 4>(drows[buf], 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+            dw_load_rows<3, 4>(drows[buf], 32, reinterpret_cast<float4 (&)[4]>(vb));
         } else {
-            dw_load_rows<4, 8>(drows[buf], 64, -1, vb);         // N_pad = 64: two 32-column blocks, kDwBlk apart
+            dw_load_rows<4, 8>(drows[buf], 64, vb);         // N_pad = 64: two 32-column blocks, kDwBlk apart
         }
     };
     if (l == 0) {                                              // replay rows first, dZ after the predecessor has finished
-        dw_load_rows<5, 16>(rows[0], T.K_real, T.K_real, va);
+        dw_load_rows<5, 16>(rows[0], T.K_real, va);
         pdl_wait(); pdl_trigger();
         if (T.N_pad == 32) {
 #pragma unroll
             for (int u = 4; u < 8; ++u) vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dw_load_rows<3, 4>(drows[0], 32, -1, reinterpret_cast<float4 (&)[4]>(vb));
+            dw_load_rows<3, 4>(drows[0], 32, reinterpret_cast<float4 (&)[4]>(vb));
         } else {
-            dw_load_rows<4, 8>(drows[0], 64, -1, vb);
+            dw_load_rows<4, 8>(drows[0], 64, vb);
         }
     } else {
         load_chunk(0);
@@ -426,9 +426,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     int it = 0;
     for (int c = slice; c < a.n_chunks; c += a.n_slices, ++it) {
         if (it > 0) { mbar_wait(&mbar, mphase); mphase ^= 1; tc_fence_after(); }     // the MMAs of the previous chunk have read SMEM
-        dw_store_rows<5, 16>(va, Ahi, Alo);
-        if (T.N_pad == 32) dw_store_rows<3, 4>(reinterpret_cast<float4 (&)[4]>(vb), Bhi, Blo);
-        else dw_store_rows<4, 8>(vb, Bhi, Blo);
+        dw_store_rows<5, 16>(va, rows[it & 1], T.K_real, Ahi, Alo);
+        if (T.N_pad == 32) dw_store_rows<3, 4>(reinterpret_cast<float4 (&)[4]>(vb), drows[it & 1], -1, Bhi, Blo);
+        else dw_store_rows<4, 8>(vb, drows[it & 1], -1, Bhi, Blo);
         const int cn = c + a.n_slices;
         resolve_chunk(cn, (it + 1) & 1);
         fence_proxy_async();

@@ -171,8 +171,7 @@ def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
     training chain R = 64, 94 / 157 weight-gradient chunks).  At this batch size two fp32 implementations differ by their
     summation order alone (the oracle adds 20 000 per-sample terms one after the other per thread; the kernels add 128-sample
     tensor-core partials), so a float64 numpy restatement arbitrates: the CUDA gradient (fp32 accumulation in TMEM, then a fixed-order
-    fp32 sum of the partials) must match float64 within 2e-4 relative / 2e-5 absolute on EVERY entry; the oracle, which accumulates
-    in double, must agree with it to 1e-6; against the oracle 99.9 % of the entries meet the same bound and none is off by more than 2e-4.  Parameters after each of 4 updates (incl. the
+    fp32 sum of the partials) must match float64 within 2e-4 relative / 2e-5 absolute on EVERY entry; against the oracle 99.9 % of the entries meet the same bound and none is off by more than 2e-4.  Parameters after each of 4 updates (incl. the
     hard update at epoch 3): within 2e-5 of the oracle's except where Adam divides a gradient that is itself inside the fp32
     summation noise (|g| < 1e-5: the step is +-lr whichever way the noise points), and never further than 4 lr."""
     from uavrl_b200 import engine
@@ -210,7 +209,9 @@ def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
         bound = 2e-4 * np.abs(g64) + 2e-5
         err_gpu, err_or = np.abs(gg - g64), np.abs(grads - g64)
         assert (err_gpu <= bound).all(), (step, float((err_gpu - bound).max()))
-        assert err_or.max() <= 1e-6                     # the oracle accumulates gradients in double: it IS the float64 answer
+        # (the oracle accumulates in double but evaluates the networks in fp32: it differs from float64 where a ReLU input is
+        # within fp32 noise of 0, by that unit's whole contribution)
+        assert err_or.max() <= 2e-4 and err_or.mean() <= 1e-7
         vs_or = np.abs(gg - grads)
         assert (vs_or <= 2e-4 * np.abs(grads) + 2e-5).mean() >= 0.999 and vs_or.max() <= 2e-4
         noisy |= np.abs(g64) < 1e-5
