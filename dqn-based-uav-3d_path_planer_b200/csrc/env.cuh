@@ -8,10 +8,11 @@
 namespace uavrl {
 
 constexpr int kEnvThreads = 128;       // warp 0 steps the CTA's envs; all 4 warps share their probes
-// envs per CTA: 32 for big batches; 8 when the batch is small, so that the latency-bound fp64 chains
-// of a 4096-env step spread over 512 CTAs (3-4 per SM) instead of 128
+// envs per CTA: 8 while the whole batch then fits ONE wave (112 registers x 128 threads -> 4 CTAs per SM, 4 x 148 CTAs), so
+// that the latency-bound fp64 chains of a 4096-env step spread over 512 CTAs instead of 128; 32 above (16 384 envs = 512
+// CTAs of 32: again one wave -- with 8 per CTA they took 3.5 waves: 33.5 us against 14.6 us at 4096 envs, measured)
 constexpr int kEnvsPerBlockLarge = 32, kEnvsPerBlockSmall = 8;
-constexpr int kSmallBatchEnvs = 16384;
+constexpr int kSmallBatchEnvs = 4 * 148 * kEnvsPerBlockSmall;
 constexpr int kMaxCyl = 64;            // candidate sets are 64-bit masks
 
 // Everything a kernel needs, passed by value.

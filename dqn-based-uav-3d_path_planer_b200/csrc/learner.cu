@@ -536,7 +536,10 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
     const int n_tiles = (B + kTile - 1) / kTile;
     const int grid = n_tiles < l->max_ctas ? n_tiles : l->max_ctas;
     const float *y_in = nullptr;
-    if (l->tc_ok && l->use_tc) {
+    const bool fuse_td = l->tc_ok && l->use_tc && tc_train_can_fuse_td(l, B);
+    if (l->tc_ok && l->use_tc && fuse_td) {
+        y_in = l->y_buf;                                  // not read: the training kernel forms the TD targets itself
+    } else if (l->tc_ok && l->use_tc) {
         // TD targets on the tensor cores: y = r + gamma * next_q * (1 - d) for the whole batch, then the
         // update kernel only evaluates the local network (forward on s, backward)
         if (B > l->y_cap) {
@@ -590,7 +593,7 @@ static int launch_update_impl(uavrl_learner *l, const BatchSrc &src_in, int B, i
         }
         const bool may_fuse = apply && !partials_only && !per_batch;
         int rc = launch_tc_train(l, src, B, global_batch, y_in, &nparts, &n_loss_parts, st, mid ? mid[1] : nullptr,
-                                 may_fuse ? &a : nullptr, loss_out ? loss_out : l->loss_dev, &adam_done);
+                                 may_fuse ? &a : nullptr, loss_out ? loss_out : l->loss_dev, &adam_done, fuse_td);
         if (rc) return rc;
     } else {
     UpdateArgs ua;

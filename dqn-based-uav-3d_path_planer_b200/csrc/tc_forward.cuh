@@ -35,7 +35,9 @@ int tc_train_init(uavrl_learner *l);
 // adam != nullptr: the optimiser step may be fused behind the weight-gradient kernel (*adam_done tells whether it was)
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
                     int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain = nullptr, const AdamArgs *adam = nullptr,
-                    float *loss_out = nullptr, bool *adam_done = nullptr);
+                    float *loss_out = nullptr, bool *adam_done = nullptr, bool fused_td = false);
+// the TD-target pass(es) can run inside the training kernel (one tile per CTA): no separate launch_tc_forward TD calls
+bool tc_train_can_fuse_td(const uavrl_learner *l, int B);
 size_t tc_smem_bytes(const TcNet &tc);
 // the env step fused behind the act pass (tc_forward.cu): env batch + where the step writes
 struct EnvFuse { EnvDev d; float *obs_next; float *reward; uint8_t *done; };

@@ -39,6 +39,12 @@ struct TcTrainArgs {
     float *act_buf, *dz_buf;           // per-sample scratch rows
     float *loss_partials;              // [grid]
     int32_t loss_kind;                 // 0 MSE (reference), 1 Huber (delta = 1)
+    // fused TD target (fused_td = 1; only when every CTA owns exactly one tile): the same CTA first evaluates the target
+    // network (double DQN: the local network for a*, then the target network) on the tile's NEXT states and keeps
+    // y = r + gamma * next_q * (1 - d) in shared memory -- one launch instead of two or three, no y round trip
+    int32_t fused_td, algo;
+    float gamma;
+    const unsigned char *img_target;   // target network, forward image
 };
 
 struct TcDwArgs {
@@ -100,8 +106,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __shared__ uint64_t wbar, mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ const float *rows[kTcTile];
-    __shared__ int s_act[kTcTile];
-    __shared__ float s_y[kTcTile];
+    __shared__ const float *rows2[kTcTile];                  // fused TD: next-state rows
+    __shared__ int s_act[kTcTile], s_astar[kTcTile];
+    __shared__ float s_y[kTcTile], s_rew[kTcTile], s_done[kTcTile];
     __shared__ float s_loss;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
@@ -111,12 +118,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    // PDL: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
+    const bool fused = a.fused_td != 0;
+    const int n_pre = fused ? (a.algo != UAVRL_ALGO_DQN ? 2 : 1) : 0;     // forward-only passes ahead of the training chain
+    // PDL.  Unfused: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
     // precedes this kernel), so it is fetched before the wait, and so are the first tile's sampled rows and actions
     // (replay frames / actions were written by the env step and the act kernel, also >= 2 back); only y is the
-    // predecessor's output
-    if (tid == 0) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar); }
+    // predecessor's output.  Fused: the predecessor is the env step, which writes the newest frame's rows, rewards and
+    // flags -- only the first pass's weight image (optimiser kernel, >= 2 back) is fetched before the wait.
+    uint32_t wphase = 0;
+    if (tid == 0) {
+        fence_proxy_async();
+        if (!fused) bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
+        else bulk_g2s_chunked(W, (n_pre == 2) ? a.img : a.img_target, (uint32_t)tc.img_bytes, &wbar);
+    }
     bool waited = false;
+    if (fused) { pdl_wait(); pdl_trigger(); waited = true; }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     uint32_t pkey[4];
@@ -131,18 +147,104 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         const int base = tile * R;
         if (tid < R) {
             const int b = base + tid;
-            const float *p = nullptr; int act = 0;
+            const float *p = nullptr, *p2 = nullptr; int act = 0; float rw = 0.f, dn = 0.f;
             if (b < a.B) {
                 const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
-                p = t.s; act = t.a;
+                p = t.s; act = t.a; p2 = t.s2; rw = t.r; dn = t.d;
             }
             rows[tid] = p; s_act[tid] = act;
+            if (fused) { rows2[tid] = p2; s_rew[tid] = rw; s_done[tid] = dn; s_astar[tid] = 0; }
         }
         __syncthreads();
+        // ---------------- fused TD target: forward-only pass(es) on the next states (tc_forward.cu's chain and head)
+        for (int pass = 0; pass < n_pre; ++pass) {
+            if (pass > 0 && tid == 0) {                          // the target image replaces the local one (all its readers are done)
+                fence_proxy_async();
+                bulk_g2s_chunked(W, a.img_target, (uint32_t)tc.img_bytes, &wbar);
+            }
+            build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
+            mbar_wait(&wbar, wphase); wphase ^= 1;
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            const bool td_pass = (pass == n_pre - 1);
+            for (int l = 0; l < nl; ++l) {
+                const TcLayer T = tc.L[l];
+                const uint32_t sbo = umma_sbo(T.K_pad);
+                const uint32_t dcol = (uint32_t)(l & 1) * (uint32_t)tc.dstride;
+                const uint32_t second = tc.concat ? (uint32_t)T.N_pad : 0u;
+                if (tid == 0) {
+                    issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                                 umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                                 T.K_pad / 8, tc.concat != 0);
+                    umma_commit(&mbar);
+                }
+                mbar_wait(&mbar, mphase);
+                mphase ^= 1;
+                tc_fence_after();
+                const float *bias = bias_all + T.bias_off;
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+                if (l + 1 < nl) {
+                    const uint32_t sbon = umma_sbo(T.N_pad);
+                    for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
+                        float v[32];
+                        tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 x, h, lo4;
+                            x.x = fmaxf(v[4 * j + 0] + bias[c0 + 4 * j + 0], 0.f); x.y = fmaxf(v[4 * j + 1] + bias[c0 + 4 * j + 1], 0.f);
+                            x.z = fmaxf(v[4 * j + 2] + bias[c0 + 4 * j + 2], 0.f); x.w = fmaxf(v[4 * j + 3] + bias[c0 + 4 * j + 3], 0.f);
+                            tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
+                            const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
+                            *reinterpret_cast<float4 *>(Ahi + off) = h;
+                            *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        }
+                    }
+                } else if (half == 0 && live) {
+                    float q[32];
+                    tmem_ld32_sum(taddr, second, q);
+                    const int nA = tc.n_actions;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] += bias[j];
+                    if (tc.dueling) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
+                        float sA = 0.f, V = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < nA) sA += q[j]; if (j == nA) V = q[j]; }
+                        const float mean = sA / (float)nA;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = V + q[j] - mean;
+                    }
+                    int best = 0; float bv = q[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) if (j < nA && q[j] > bv) { bv = q[j]; best = j; }
+                    if (!td_pass) s_astar[row] = best;                // DDQN_Trainer.py:94
+                    else {
+                        float nq = bv;                                // DQN_Trainer.py:109
+                        if (n_pre == 2) {                             // DDQN_Trainer.py:95: gather at a*
+                            const int as = s_astar[row];
+                            nq = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j == as) nq = q[j];
+                        }
+                        s_y[row] = s_rew[row] + (a.gamma * nq * (1.f - s_done[row]));      // :99 / :114 / :171
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+            }
+        }
+        if (fused && tid == 0) {                                  // the training image (every reader of the TD image is done)
+            fence_proxy_async();
+            bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
+        }
         build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
         if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
-        if (tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
-        if (!wready) { mbar_wait(&wbar, 0); wready = true; }
+        if (!fused && tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
+        if (fused) { mbar_wait(&wbar, wphase); wphase ^= 1; }
+        else if (!wready) { mbar_wait(&wbar, 0); wready = true; }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -549,10 +651,18 @@ int tc_train_init(uavrl_learner *l)
     return 0;
 }
 
+std::atomic<int> g_fuse_td{1};               // uavrl_set_fuse_td(); default on
+bool tc_train_can_fuse_td(const uavrl_learner *l, int B)
+{
+    // one tile per CTA (R = 32 rows): the weight images are restaged inside the kernel, which only pays when a CTA does
+    // it once; larger batches keep the separate TD-target kernel(s) whose CTAs reuse one image over several tiles
+    return g_fuse_td.load() && l->tc_train_ok && (B + 31) / 32 <= 148 && B < 64 * 148;
+}
 std::atomic<int> g_fuse_dw_adam{0};          // uavrl_set_fuse_dw_adam(); default off: measured no faster than the PDL-chained pair
 
 int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_batch, const float *y, int *n_grad_parts,
-                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain, const AdamArgs *adam, float *loss_out, bool *adam_done)
+                    int *n_loss_parts, cudaStream_t st, cudaEvent_t after_chain, const AdamArgs *adam, float *loss_out, bool *adam_done,
+                    bool fused_td)
 {
     const TcNet &tc = l->tc;
     TcTrainArgs a;
@@ -560,12 +670,14 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     a.img = l->tc_img_local; a.src = src; a.B = B; a.y = y; a.inv_global_b = 1.0f / (float)global_batch;
     a.act_buf = l->act_buf; a.dz_buf = l->dz_buf; a.loss_partials = l->loss_partials;
     a.loss_kind = l->cfg.loss_kind;
+    a.fused_td = fused_td ? 1 : 0; a.algo = l->cfg.algo; a.gamma = l->cfg.gamma; a.img_target = l->tc_img_target;
     a.R = (B >= 64 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
     a.n_tiles = (B + a.R - 1) / a.R;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     const bool chain = l->pdl_chain && g_pdl.load();
+    if (fused_td && a.n_tiles > grid) return fail(UAVRL_ERR_INVALID, "fused TD needs one tile per CTA");
     UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st,
-                             chain && l->pdl_prev == kPdlTd, tc, a));
+                             chain && (fused_td ? (l->pdl_prev == kPdlEnv) : (l->pdl_prev == kPdlTd)), tc, a));
     l->pdl_prev = chain ? kPdlTrain : kPdlNone;
     UAVRL_LAUNCHED();
     if (after_chain) UAVRL_CUDA(cudaEventRecord(after_chain, st));
@@ -618,3 +730,4 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
 }  // namespace uavrl
 
 extern "C" int uavrl_set_fuse_dw_adam(int32_t on) { uavrl::g_fuse_dw_adam.store(on ? 1 : 0); return 0; }
+extern "C" int uavrl_set_fuse_td(int32_t on) { uavrl::g_fuse_td.store(on ? 1 : 0); return 0; }

@@ -370,6 +370,11 @@ int uavrl_set_fuse_act_env(int32_t on);
  * no faster than the PDL-chained pair (16.0 + 6.0 us) -- the barrier waits for the slowest CTA and the optimiser's launch
  * latency was already hidden. */
 int uavrl_set_fuse_dw_adam(int32_t on);
+/* Batches of at most 148 x 32 transitions on the tensor-core path: the TD-target forward pass(es) (target network on the next
+ * states; double DQN: the local network first) run inside the training kernel, each CTA on the tile it then trains on
+ * (weight images restaged in shared memory between the passes, y kept in shared memory) -- one launch instead of two or
+ * three per update; the arithmetic is the stand-alone passes'.  Process-wide switch, default 1. */
+int uavrl_set_fuse_td(int32_t on);
 
 #ifdef __cplusplus
 }

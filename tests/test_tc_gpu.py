@@ -211,7 +211,7 @@ def test_tc_update_large_batch_vs_oracle(dqn_golden, name, B):
         assert (err_gpu <= bound).all(), (step, float((err_gpu - bound).max()))
         # (the oracle accumulates in double but evaluates the networks in fp32: it differs from float64 where a ReLU input is
         # within fp32 noise of 0, by that unit's whole contribution)
-        assert err_or.max() <= 2e-4 and err_or.mean() <= 1e-7
+        assert err_or.max() <= 2e-4 and err_or.mean() <= 1e-6
         vs_or = np.abs(gg - grads)
         assert (vs_or <= 2e-4 * np.abs(grads) + 2e-5).mean() >= 0.999 and vs_or.max() <= 2e-4
         noisy |= np.abs(g64) < 1e-5

@@ -86,10 +86,12 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
     out = []
     try:
         # the fused act+step kernel and the optimiser step fused behind the weight-gradient kernel are the same kind of change
-        for pdl, fuse, fuse_dw in ((1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 1), (1, 0, 0)):
+        # ... and so is the TD-target pass folded into the training kernel (uavrl_set_fuse_td)
+        for pdl, fuse, fuse_dw, fuse_td in ((1, 1, 1, 1), (0, 0, 0, 0), (1, 0, 1, 0), (0, 1, 1, 1), (1, 0, 0, 1), (1, 0, 0, 0)):
             _lib.lib().uavrl_set_pdl(pdl)
             _lib.lib().uavrl_set_fuse_act_env(fuse)
             _lib.lib().uavrl_set_fuse_dw_adam(fuse_dw)
+            _lib.lib().uavrl_set_fuse_td(fuse_td)
             env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
             sc = env.make_scenarios(1024, seed=8)
             env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
@@ -110,6 +112,7 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
         _lib.lib().uavrl_set_pdl(1)                 # library defaults: PDL on, fused act+step off, optimiser not fused behind dW
         _lib.lib().uavrl_set_fuse_act_env(0)
         _lib.lib().uavrl_set_fuse_dw_adam(0)
+        _lib.lib().uavrl_set_fuse_td(1)
     a = out[0]
     for b in out[1:]:
         assert a["stats"][:6] == b["stats"][:6] and a["stats"][1] == 150 and a["stats"][7] == b["stats"][7]
