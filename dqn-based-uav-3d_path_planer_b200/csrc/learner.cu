@@ -433,6 +433,71 @@ allreduce_adam_kernel(AdamArgs a, const float *recv, size_t stride, const unsign
     }
 }
 
+// ---- the same exchange in ONE kernel, block by block (default): block b owns parameters [64 b, 64 b + 64).  It reduces
+// its slice of this rank's partials, pushes the 64 values into slot `rank` of every rank's receive buffer, fences, and
+// raises the flag (rank, b) on every peer; then it waits -- in local memory -- for the `world` flags of ITS slice only,
+// sums the `world` slices in rank order and applies Adam.  No grid-wide completion, no second launch: a block never
+// waits for more than the matching block of each peer (all blocks of the grid are resident: 194 x 256 threads).
+__global__ void __launch_bounds__(256)
+dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *__restrict__ partials,
+                         const float *__restrict__ loss_partials, float *const *peer_recv, const float *recv_local, size_t stride,
+                         size_t parity_off, unsigned *const *peer_flags, const unsigned *my_flags, int rank, unsigned epoch,
+                         AdamPtrs q)
+{
+    __shared__ float red[4][64];
+    const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + ix;
+    const int nblk = gridDim.x;
+    pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
+    pdl_trigger();
+    float g = 0.f;
+    if (i < a.P) g = reduce_group(partials, a.P, nparts, i, cg);
+    red[cg][ix] = g;
+    __syncthreads();
+    const size_t slot = parity_off + (size_t)rank * stride;
+    if (i < a.P) {
+        const float gs = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
+        for (int w = cg; w < a.world; w += 4) peer_recv[w][slot + i] = gs;       // 64 consecutive floats per peer: 256 contiguous bytes
+    }
+    if (blockIdx.x == 0 && threadIdx.x >= 224) {                 // last warp of block 0: this rank's loss share
+        const int lane = threadIdx.x & 31;
+        float s = 0.f;
+        for (int c = lane; c < n_loss_parts; c += 32) s += loss_partials[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0)
+            for (int w = 0; w < a.world; ++w) peer_recv[w][slot + a.P] = s * a.inv_b;
+    }
+    __threadfence_system();                                      // this thread's remote stores are performed system-wide
+    __syncthreads();
+    if (threadIdx.x < a.world) {                                 // thread w: raise (rank, block) on peer w, then wait for peer w's
+        volatile unsigned *f = peer_flags[threadIdx.x] + 64 + (size_t)rank * nblk + blockIdx.x;   // [0, 64): the two-kernel pair's words
+        *f = epoch;
+        while (ld_acquire_sys(my_flags + (size_t)threadIdx.x * nblk + blockIdx.x) < epoch) { }
+    }
+    __syncthreads();
+    const float *recv = recv_local + parity_off;
+    if (cg == 0 && i < a.P) {
+        float gsum = 0.f;
+        int w = 0;
+        for (; w + 8 <= a.world; w += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = ld_relaxed_sys(recv + (size_t)(w + u) * stride + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) gsum += t[u];
+        }
+        for (; w < a.world; ++w) gsum += ld_relaxed_sys(recv + (size_t)w * stride + i);
+        q.grad[i] = gsum;
+        adam_update_one(a, q, i, gsum);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 255 && q.loss_out) {
+        float s = 0.f;
+        for (int w = 0; w < a.world; ++w) s += ld_relaxed_sys(recv + (size_t)w * stride + a.P);
+        *q.loss_out = s;
+    }
+}
+
 __global__ void copy_kernel(int n, const float *__restrict__ src, float *__restrict__ dst)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,14 +733,31 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
     const size_t stride = (size_t)P + 1;                                        // one rank's slot: gradient vector + loss share
     const size_t parity_off = (size_t)(l->flag_epoch & 1u) * (size_t)l->world * stride;
     const bool chain = l->pdl_chain && g_pdl.load();
-    UAVRL_CUDA(launch_kernel(reduce_publish_kernel, dim3((P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, P, l->last_nparts,
-                             l->last_n_loss_parts, 1.0f / (float)global_batch, l->partials, l->loss_partials, l->peer_grad_dev,
-                             parity_off + (size_t)l->rank * stride, l->comm_counter, l->peer_flag_dev, l->rank, l->world, l->flag_epoch));
-    UAVRL_LAUNCHED();
     AdamArgs a;
     memset(&a, 0, sizeof(a));
     a.P = P; a.apply = 1; a.world = l->world;
     fill_adam_args(l, a);
+    a.inv_b = 1.0f / (float)global_batch;
+    static const bool two_kernels = getenv("UAVRL_DP_TWO_KERNELS") != nullptr;     // the grid-wide publish + all-reduce pair
+    const int nblk = (P + 63) / 64;
+    if (!two_kernels && l->world * nblk <= l->comm_flag_words) {
+        AdamPtrs q;
+        q.partials = l->partials; q.loss_partials = l->loss_partials; q.grad = l->grad; q.local = l->local; q.m = l->m; q.v = l->v;
+        q.target = l->target; q.img_local = l->img_local; q.img_target = l->img_target; q.img_map = l->img_map;
+        q.tc_local = (float *)l->tc_img_local; q.tc_target = (float *)l->tc_img_target; q.tc_hi = l->tc_hi_map; q.tc_lo = l->tc_lo_map;
+        q.tc_hi2 = l->tc_hi2_map; q.tc_lo2 = l->tc_lo2_map; q.loss_out = loss_out ? loss_out : l->loss_dev;
+        UAVRL_CUDA(launch_kernel(dp_allreduce_adam_kernel, dim3(nblk), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a, l->last_nparts,
+                                 l->last_n_loss_parts, (const float *)l->partials, (const float *)l->loss_partials, l->peer_grad_dev,
+                                 (const float *)l->comm_grad, stride, parity_off, l->peer_flag_dev, (const unsigned *)l->comm_flags + 64,
+                                 l->rank, l->flag_epoch, q));
+        UAVRL_LAUNCHED();
+        l->pdl_prev = chain ? kPdlAdam : kPdlNone;
+        return 0;
+    }
+    UAVRL_CUDA(launch_kernel(reduce_publish_kernel, dim3((P + 63) / 64), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, P, l->last_nparts,
+                             l->last_n_loss_parts, 1.0f / (float)global_batch, l->partials, l->loss_partials, l->peer_grad_dev,
+                             parity_off + (size_t)l->rank * stride, l->comm_counter, l->peer_flag_dev, l->rank, l->world, l->flag_epoch));
+    UAVRL_LAUNCHED();
     UAVRL_CUDA(launch_kernel(allreduce_adam_kernel, dim3((P + 255) / 256), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a,
                              (const float *)(l->comm_grad + parity_off), stride, l->comm_flags, l->flag_epoch, l->grad, l->local, l->m, l->v,
                              l->target, l->img_local, l->img_target, l->img_map, (float *)l->tc_img_local, (float *)l->tc_img_target,
@@ -1060,8 +1142,10 @@ int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void 
         const size_t n = 2 * (size_t)world * ((size_t)l->net.P + 1);     // recv[2][world][P+1]
         UAVRL_CUDA(cudaMalloc((void **)&l->comm_grad, n * sizeof(float)));
         UAVRL_CUDA(cudaMemset(l->comm_grad, 0, n * sizeof(float)));
-        UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, 64 * sizeof(unsigned)));
-        UAVRL_CUDA(cudaMemset(l->comm_flags, 0, 64 * sizeof(unsigned)));
+        // flag words: [0, 64) one per rank (the two-kernel pair), then [64, 64 + world x blocks) one per (rank, 64-parameter block)
+        l->comm_flag_words = world * (int)((l->net.P + 63) / 64);
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, (size_t)(64 + l->comm_flag_words) * sizeof(unsigned)));
+        UAVRL_CUDA(cudaMemset(l->comm_flags, 0, (size_t)(64 + l->comm_flag_words) * sizeof(unsigned)));
         UAVRL_CUDA(cudaMalloc((void **)&l->comm_counter, sizeof(unsigned)));
         UAVRL_CUDA(cudaMemset(l->comm_counter, 0, sizeof(unsigned)));
     }

@@ -133,7 +133,7 @@ struct uavrl_learner {
     // data-parallel: one-shot NVLink all-reduce fused with Adam (symmetric buffers exchanged through CUDA IPC)
     int32_t rank = 0, world = 1;
     float *comm_grad = nullptr;       // own receive buffer recv[2][world][P+1]: slot q is written by rank q (remote stores)
-    int32_t comm_world = 0;
+    int32_t comm_world = 0, comm_flag_words = 0;
     unsigned *comm_flags = nullptr;   // own, [64]: slot q is raised by rank q
     unsigned *comm_counter = nullptr; // last-block detection of the publish kernel
     float **peer_grad_dev = nullptr;  // device array [world]: every rank's receive buffer as mapped on THIS device

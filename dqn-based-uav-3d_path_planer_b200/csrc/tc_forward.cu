@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     // computed from whatever SMEM follows the R-row operand (still inside this CTA's allocation) and are
     // never read.  Small batches use R = 32 so that 4096 samples spread over 128 CTAs instead of 32.
     const int R = a.rows_per_tile;
+    // R <= 64: stacked 3xTF32 (umma.cuh) -- A_lo lives in rows [R, 2R) of the Ahi buffer, the Alo buffer is the scratch through
+    // which the lo*hi block reaches the epilogue warps
+    const bool stack = (R <= 64) && tc.concat && tc.dstride <= 128;     // (the scratch rows hold 64 columns: layers up to 64 wide)
+    float *s_lo = reinterpret_cast<float *>(Alo);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int base = tile * R;
         if (tid < R) {
@@ -197,7 +201,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                         tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                         const uint32_t off = umma_off(r, 4 * j, sbo);
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        *reinterpret_cast<float4 *>(Alo + off) = l;
+                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + r, 4 * j, sbo)) = l;
+                        else *reinterpret_cast<float4 *>(Alo + off) = l;
                     }
                 }
             }
@@ -225,9 +230,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             if (tid == 0) {
                 // one thread issues the layer's MMAs.  Descriptors differ only in the 14-bit start-address field:
                 // the next K step (two 16-byte chunks = 2*LBO bytes) is +16 in units of 16 B.
-                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
-                             T.K_pad / 8, tc.concat != 0);
+                if (stack) issue_3xtf32_stacked(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(W + T.hi_off), sbo), kTcTile, T.N_pad, T.K_pad / 8);
+                else issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                                  umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                                  T.K_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             TC_TRACE(5 + 3 * l);
@@ -239,12 +245,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             const int row = quad * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             const bool live = quad * 32 < R;                       // this warp's TMEM quadrant holds real rows
+            if (stack) {                                           // the lo*hi block (rows [R, 2R)) -> scratch -> the hi warps
+                if (quad * 32 >= R && quad * 32 < 2 * R)
+                    for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                __syncthreads();
+            }
             if (l + 1 < tc.n_layers) {
                 // hidden layer epilogue: bias + ReLU, re-split, write the next A operand (K_next = N_pad)
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
                     tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                    if (stack) stack_add_lo(v, s_lo, row, c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 h, lo4;
@@ -253,7 +265,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                         tf32_split(x0, h.x, lo4.x); tf32_split(x1, h.y, lo4.y); tf32_split(x2, h.z, lo4.z); tf32_split(x3, h.w, lo4.w);
                         const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
+                        else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                     }
                 }
                 fence_proxy_async();
@@ -266,6 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                 if (half == 0 && live) {
                     float q[32];
                     tmem_ld32_sum(taddr, second, q);
+                    if (stack) stack_add_lo(q, s_lo, row, 0);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];

@@ -67,7 +67,7 @@ struct TcDwArgs {
 // is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.  Consecutive lanes take
 // consecutive rows of an 8-row group (same 16-byte chunk): a quarter-warp's 16-byte stores then cover one whole core
 // matrix column = 128 contiguous bytes (lanes walking along a row would all hit the same 4 banks).
-__device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo)
+__device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo, bool stack)
 {
     const int chunks = K0 / 4, total = R * chunks;
     const uint32_t sbo = umma_sbo(K0);
@@ -91,7 +91,8 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
                 tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                 const uint32_t off = umma_off(r, 4 * j, sbo);
                 *reinterpret_cast<float4 *>(Ahi + off) = h;
-                *reinterpret_cast<float4 *>(Alo + off) = l;
+                if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + r, 4 * j, sbo)) = l;   // stacked 3xTF32: A_lo in rows [R, 2R)
+                else *reinterpret_cast<float4 *>(Alo + off) = l;
             }
         }
     }
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     const int R = a.R;
     const uint32_t a_bytes = (uint32_t)(R / 8) * umma_sbo(tc.max_k);
     unsigned char *Ahi = smem, *Alo = smem + a_bytes, *W = smem + 2 * a_bytes;
+    // stacked 3xTF32 (umma.cuh; R is 32 or 64 here): A_lo occupies rows [R, 2R) of the operand that starts at Ahi (which runs on
+    // into the Alo buffer); the lo*hi accumulator block reaches the epilogue warps through a scratch behind the weight image
+    const bool stack = tc.concat != 0 && tc.dstride <= 128;          // (layers up to 64 wide: tc_train_init admits no others)
+    float *s_lo = reinterpret_cast<float *>(W + tc.train_img_bytes);
     __shared__ uint64_t wbar, mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ const float *rows[kTcTile];
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 fence_proxy_async();
                 bulk_g2s_chunked(W, a.img_target, (uint32_t)tc.img_bytes, &wbar);
             }
-            build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
+            build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
             mbar_wait(&wbar, wphase); wphase ^= 1;
             fence_proxy_async();
             tc_fence_before();
@@ -175,9 +180,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 const uint32_t dcol = (uint32_t)(l & 1) * (uint32_t)tc.dstride;
                 const uint32_t second = tc.concat ? (uint32_t)T.N_pad : 0u;
                 if (tid == 0) {
-                    issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                                 umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
-                                 T.K_pad / 8, tc.concat != 0);
+                    if (stack) issue_3xtf32_stacked(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(W + T.hi_off), sbo), kTcTile, T.N_pad, T.K_pad / 8);
+                    else issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                                      umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                                      T.K_pad / 8, tc.concat != 0);
                     umma_commit(&mbar);
                 }
                 mbar_wait(&mbar, mphase);
@@ -185,11 +191,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 tc_fence_after();
                 const float *bias = bias_all + T.bias_off;
                 const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+                if (stack) {                                       // lo*hi block (rows [R, 2R)) -> scratch
+                    if (quad * 32 >= R && quad * 32 < 2 * R)
+                        for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                    __syncthreads();
+                }
                 if (l + 1 < nl) {
                     const uint32_t sbon = umma_sbo(T.N_pad);
                     for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                         float v[32];
                         tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                        if (stack) stack_add_lo(v, s_lo, row, c0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 x, h, lo4;
@@ -198,12 +210,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                             tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
                             const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
                             *reinterpret_cast<float4 *>(Ahi + off) = h;
-                            *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                            if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
+                            else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                         }
                     }
                 } else if (half == 0 && live) {
                     float q[32];
                     tmem_ld32_sum(taddr, second, q);
+                    if (stack) stack_add_lo(q, s_lo, row, 0);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             fence_proxy_async();
             bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
         }
-        build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo);
+        build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
         if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
         if (!fused && tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
         if (fused) { mbar_wait(&wbar, wphase); wphase ^= 1; }
@@ -259,9 +273,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             const uint32_t dcol = (uint32_t)(l & 1) * (uint32_t)tc.dstride;
             const uint32_t second = tc.concat ? (uint32_t)T.N_pad : 0u;
             if (tid == 0) {
-                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                             umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
-                             T.K_pad / 8, tc.concat != 0);
+                if (stack) issue_3xtf32_stacked(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(W + T.hi_off), sbo), kTcTile, T.N_pad, T.K_pad / 8);
+                else issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                                  umma_desc(smem_u32(W + T.hi_off), sbo), umma_desc(smem_u32(W + T.lo_off), sbo), kTcTile, T.N_pad,
+                                  T.K_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             mbar_wait(&mbar, mphase);
@@ -269,12 +284,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             tc_fence_after();
             const float *bias = bias_all + T.bias_off;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            if (stack) {                                           // lo*hi block (rows [R, 2R)) -> scratch
+                if (quad * 32 >= R && quad * 32 < 2 * R)
+                    for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                __syncthreads();
+            }
             if (l + 1 < nl) {
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 float *act_row = a.act_buf + (size_t)gb * tc.act_stride + tc.L[l + 1].act_off;
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
                     tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                    if (stack) stack_add_lo(v, s_lo, row, c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 x, h, lo4;
@@ -283,7 +304,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
                         const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
+                        else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                         if (mine) *reinterpret_cast<float4 *>(act_row + c0 + 4 * j) = x;      // kept for ReLU' and dW
                     }
                 }
@@ -293,6 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 if (half == 0 && live) {
                     float q[32];
                     tmem_ld32_sum(taddr, second, q);
+                    if (stack) stack_add_lo(q, s_lo, row, 0);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -338,7 +361,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
                         const uint32_t off = umma_off(row, 4 * j, sbon);
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, 4 * j, sbon)) = lo4;
+                        else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                         if (mine) *reinterpret_cast<float4 *>(dz_row + 4 * j) = x;
                     }
                 }
@@ -356,9 +380,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             const uint32_t dcol = (uint32_t)((l + 1) & 1) * (uint32_t)tc.dstride;     // the head used (nl-1)&1: alternate from there
             const uint32_t second = tc.concat ? (uint32_t)T.K_pad : 0u;
             if (tid == 0) {
-                issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
-                             umma_desc(smem_u32(W + T.t_hi_off), sbo), umma_desc(smem_u32(W + T.t_lo_off), sbo), kTcTile, T.K_pad,
-                             T.N_pad / 8, tc.concat != 0);
+                if (stack) issue_3xtf32_stacked(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(W + T.t_hi_off), sbo), kTcTile, T.K_pad, T.N_pad / 8);
+                else issue_3xtf32(tmem + dcol, umma_desc(smem_u32(Ahi), sbo), umma_desc(smem_u32(Alo), sbo),
+                                  umma_desc(smem_u32(W + T.t_hi_off), sbo), umma_desc(smem_u32(W + T.t_lo_off), sbo), kTcTile, T.K_pad,
+                                  T.N_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
             // H_l (this layer's input, written by the forward epilogue of the same thread) is needed for ReLU':
@@ -380,12 +405,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             const uint32_t sbon = umma_sbo(T.K_pad);
             float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + tc.L[l - 1].dz_off;
+            if (stack) {                                           // lo*hi block (rows [R, 2R)) -> scratch
+                if (quad * 32 >= R && quad * 32 < 2 * R)
+                    for (int c0 = half * 32; c0 < T.K_pad && c0 < 64; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                __syncthreads();
+            }
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int c0 = half * 32 + cc * 64;
                 if (!(live && c0 < T.K_pad)) continue;
                 float v[32];
                 tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                if (stack) stack_add_lo(v, s_lo, row, c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 hh = hpre[cc][j];
@@ -397,7 +428,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
                         const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
+                        else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                     }
                 }
             }
@@ -622,7 +654,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
 }
 
-static size_t train_smem_bytes(const TcNet &tc, int R) { return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes; }
+static size_t train_smem_bytes(const TcNet &tc, int R)
+{
+    return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes + (size_t)R * kLoLd * 4;   // + the stacked-3xTF32 scratch
+}
 static size_t dw_smem_bytes(const TcNet &tc)
 {
     int maxN = 32;

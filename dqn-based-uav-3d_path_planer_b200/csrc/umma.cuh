@@ -174,6 +174,40 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint64_t a_hi, uint64_t
     for (int k = 0; k < ksteps; ++k) { umma_tf32(d, da, db, idesc, 1u); da += kStep; db += kStep; }
 }
 
+// Stacked 3xTF32 for tiles of at most 64 real rows R (the M = 128 instruction costs the same however many rows are real, so the
+// idle rows carry the second operand half): the A operand holds A_hi in rows [0, R) and A_lo in rows [R, 2R) of ONE operand,
+// B = [B_hi ; B_lo] (2N rows, contiguous): a single instruction per K step yields
+//     rows [0, R):   columns [0, N) = hi*hi,   columns [N, 2N) = hi*lo
+//     rows [R, 2R):  columns [0, N) = lo*hi    (columns [N, 2N) = lo*lo: not needed)
+// -- half the instructions of issue_3xtf32.  The epilogue adds D[r][c] + D[r][N + c] + D[R + r][c]; the third term sits in
+// another TMEM lane quadrant and travels through a shared-memory scratch (stack_park_lo / stack_add_lo).
+__device__ __forceinline__ void issue_3xtf32_stacked(uint32_t d, uint64_t a, uint64_t b, int M, int N, int ksteps, uint32_t lbo = kUmmaLBO)
+{
+    const uint64_t kStep = (uint64_t)((2 * lbo) >> 4);
+    const uint32_t wide = umma_idesc_tf32(M, 2 * N);
+    umma_tf32(d, a, b, wide, 0u);
+    for (int k = 1; k < ksteps; ++k) { a += kStep; b += kStep; umma_tf32(d, a, b, wide, 1u); }
+}
+constexpr int kLoLd = 68;                          // floats per scratch row: 64 + 4, so 16-byte accesses of 8 lanes hit 32 banks
+// a warp of the lo quadrant(s): park D[R + r][c0 .. c0 + 32) (r = its row within the lo block) in the scratch
+__device__ __forceinline__ void stack_park_lo(uint32_t taddr, int c0, float *s_lo, int r)
+{
+    float v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    float4 *dst = reinterpret_cast<float4 *>(s_lo + r * kLoLd + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stack_add_lo(float (&v)[32], const float *s_lo, int r, int c0)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(s_lo + r * kLoLd + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = src[j];
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+}
+
 // The three TF32 products for operands that are BOTH MN-major (layout above), contraction over K = 8 * ksteps.  The k-th
 // step starts 2 * sbo further (two 4-k groups).  concat: [B_hi ; B_lo] are adjacent mn blocks (lbo apart), see issue_3xtf32.
 // accumulate != 0: add to what the accumulator already holds (a CTA summing several sample chunks into one partial).
