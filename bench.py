@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--tc", type=int, default=1, help="1 = tcgen05 3xTF32 tensor-core path for the Q-network (default), 0 = fp32 CUDA cores")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: fused = one-shot NVLink all-reduce inside the Adam kernel, nccl = torch.distributed")
+    ap.add_argument("--dp-self", type=int, default=0, help="diagnostic, 1 GPU only: run the data-parallel loop (local gradient -> all-reduce + Adam kernel) with world = 1")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
     ap.add_argument("--fuse", type=int, default=0, help="1 = get_action + env step as one kernel on the tensor-core path, 0 = two PDL-chained kernels (default, faster)")
     ap.add_argument("--per", type=int, default=0, help="1 = prioritised replay (device SumTree equivalent) instead of uniform sampling")
@@ -303,6 +304,8 @@ class Workload:
         self.tc_on = self.L.set_tensor_cores(bool(a.tc))
         if world > 1 and a.dp == "fused":
             self.L.connect_peers(dist, rank, world)
+        elif world == 1 and a.dp_self:
+            self.L.connect_self()
         ring_frames = (a.replay + N - 1) // N + 1
         engine.train_run(self.env, self.L, ring_frames, 1.0, 1, False, want_stats=False)     # prefill: sampling spans > L2 worth of rows
 
@@ -310,7 +313,9 @@ class Workload:
         """k lockstep iterations.  1 GPU: the fused C loop.  N GPUs: env/act/ring per rank, local gradient, then the fused
         one-shot NVLink all-reduce + Adam (or NCCL all-reduce + Adam with --dp nccl), identical step on every rank."""
         a, engine = self.a, self.engine
-        if self.world == 1:
+        if self.world == 1 and a.dp_self:
+            engine.train_run_dp(self.env, self.L, k, a.eps, a.batch)
+        elif self.world == 1:
             engine.train_run(self.env, self.L, k, a.eps, 1, True, want_stats=False)
         elif a.dp == "fused":
             engine.train_run_dp(self.env, self.L, k, a.eps, a.batch * self.world)

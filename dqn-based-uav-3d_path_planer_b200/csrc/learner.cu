@@ -442,18 +442,23 @@ __global__ void __launch_bounds__(256)
 dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *__restrict__ partials,
                          const float *__restrict__ loss_partials, float *const *peer_recv, const float *recv_local, size_t stride,
                          size_t parity_off, unsigned *const *peer_flags, const unsigned *my_flags, int rank, unsigned epoch,
-                         AdamPtrs q)
+                         AdamPtrs q, unsigned long long *trace)
 {
+    // trace (UAVRL_DP_TRACE=1): block 0 accumulates nanoseconds spent in {reduce, push + fence, flag wait, Adam} and a launch count
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
     const int nblk = gridDim.x;
     pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
     pdl_trigger();
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) t0 = now();
     float g = 0.f;
     if (i < a.P) g = reduce_group(partials, a.P, nparts, i, cg);
     red[cg][ix] = g;
     __syncthreads();
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) t1 = now();
     const size_t slot = parity_off + (size_t)rank * stride;
     if (i < a.P) {
         const float gs = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
@@ -470,12 +475,14 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
     }
     __threadfence_system();                                      // this thread's remote stores are performed system-wide
     __syncthreads();
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) t2 = now();
     if (threadIdx.x < a.world) {                                 // thread w: raise (rank, block) on peer w, then wait for peer w's
         volatile unsigned *f = peer_flags[threadIdx.x] + 64 + (size_t)rank * nblk + blockIdx.x;   // [0, 64): the two-kernel pair's words
         *f = epoch;
         while (ld_acquire_sys(my_flags + (size_t)threadIdx.x * nblk + blockIdx.x) < epoch) { }
     }
     __syncthreads();
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) t3 = now();
     const float *recv = recv_local + parity_off;
     if (cg == 0 && i < a.P) {
         float gsum = 0.f;
@@ -495,6 +502,13 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
         float s = 0.f;
         for (int w = 0; w < a.world; ++w) s += ld_relaxed_sys(recv + (size_t)w * stride + a.P);
         *q.loss_out = s;
+    }
+    if (trace && blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t4 = now();
+            trace[0] += t1 - t0; trace[1] += t2 - t1; trace[2] += t3 - t2; trace[3] += t4 - t3; trace[4] += 1;
+        }
     }
 }
 
@@ -739,6 +753,8 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
     fill_adam_args(l, a);
     a.inv_b = 1.0f / (float)global_batch;
     static const bool two_kernels = getenv("UAVRL_DP_TWO_KERNELS") != nullptr;     // the grid-wide publish + all-reduce pair
+    static const bool dp_trace = getenv("UAVRL_DP_TRACE") != nullptr;
+    if (dp_trace && !l->dp_trace) { UAVRL_CUDA(cudaMalloc((void **)&l->dp_trace, 5 * 8)); UAVRL_CUDA(cudaMemsetAsync(l->dp_trace, 0, 40, st)); }
     const int nblk = (P + 63) / 64;
     if (!two_kernels && l->world * nblk <= l->comm_flag_words) {
         AdamPtrs q;
@@ -749,7 +765,7 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
         UAVRL_CUDA(launch_kernel(dp_allreduce_adam_kernel, dim3(nblk), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a, l->last_nparts,
                                  l->last_n_loss_parts, (const float *)l->partials, (const float *)l->loss_partials, l->peer_grad_dev,
                                  (const float *)l->comm_grad, stride, parity_off, l->peer_flag_dev, (const unsigned *)l->comm_flags + 64,
-                                 l->rank, l->flag_epoch, q));
+                                 l->rank, l->flag_epoch, q, l->dp_trace));
         UAVRL_LAUNCHED();
         l->pdl_prev = chain ? kPdlAdam : kPdlNone;
         return 0;
@@ -876,6 +892,13 @@ int uavrl_learner_destroy(uavrl_learner *l)
     if (!l) return 0;
     cudaSetDevice(l->cfg.device);
     cudaDeviceSynchronize();
+    if (l->dp_trace) {
+        unsigned long long h[5] = { 0, 0, 0, 0, 0 };
+        cudaMemcpy(h, l->dp_trace, sizeof(h), cudaMemcpyDeviceToHost);
+        if (h[4]) fprintf(stderr, "[dp_trace] rank %d/%d: %llu launches, block 0 mean ns: reduce %.0f  push+fence %.0f  flag wait %.0f  adam %.0f\n",
+                          l->rank, l->world, h[4], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4]);
+        cudaFree(l->dp_trace);
+    }
     for (int q = 0; q < l->world && l->comm_ready; ++q) {
         if (q == l->rank) continue;
         if (l->peer_grad_host[q]) cudaIpcCloseMemHandle(l->peer_grad_host[q]);

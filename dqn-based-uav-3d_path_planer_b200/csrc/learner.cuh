@@ -134,6 +134,7 @@ struct uavrl_learner {
     int32_t rank = 0, world = 1;
     float *comm_grad = nullptr;       // own receive buffer recv[2][world][P+1]: slot q is written by rank q (remote stores)
     int32_t comm_world = 0, comm_flag_words = 0;
+    unsigned long long *dp_trace = nullptr;    // UAVRL_DP_TRACE=1: phase times of the data-parallel optimiser kernel
     unsigned *comm_flags = nullptr;   // own, [64]: slot q is raised by rank q
     unsigned *comm_counter = nullptr; // last-block detection of the publish kernel
     float **peer_grad_dev = nullptr;  // device array [world]: every rank's receive buffer as mapped on THIS device

@@ -245,9 +245,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             const int row = quad * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             const bool live = quad * 32 < R;                       // this warp's TMEM quadrant holds real rows
+            float vpre[32];                                      // this warp's accumulator chunk, loaded while the lo warps park theirs
             if (stack) {                                           // the lo*hi block (rows [R, 2R)) -> scratch -> the hi warps
                 if (quad * 32 >= R && quad * 32 < 2 * R)
                     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                if (live && half * 32 < T.N_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
                 __syncthreads();
             }
             if (l + 1 < tc.n_layers) {
@@ -255,8 +257,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
-                    tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
-                    if (stack) stack_add_lo(v, s_lo, row, c0);
+                    if (stack) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = vpre[j];
+                        stack_add_lo(v, s_lo, row, c0);
+                    } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 h, lo4;
@@ -278,8 +283,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                 // head epilogue: Q row of this sample, then the mode's output
                 if (half == 0 && live) {
                     float q[32];
-                    tmem_ld32_sum(taddr, second, q);
-                    if (stack) stack_add_lo(q, s_lo, row, 0);
+                    if (stack) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = vpre[j];
+                        stack_add_lo(q, s_lo, row, 0);
+                    } else tmem_ld32_sum(taddr, second, q);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];

@@ -191,17 +191,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 tc_fence_after();
                 const float *bias = bias_all + T.bias_off;
                 const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+                float vpre[32];                                      // this warp's accumulator chunk, loaded while the lo warps park theirs
                 if (stack) {                                       // lo*hi block (rows [R, 2R)) -> scratch
                     if (quad * 32 >= R && quad * 32 < 2 * R)
                         for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                    if (live && half * 32 < T.N_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
                     __syncthreads();
                 }
                 if (l + 1 < nl) {
                     const uint32_t sbon = umma_sbo(T.N_pad);
                     for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                         float v[32];
-                        tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
-                        if (stack) stack_add_lo(v, s_lo, row, c0);
+                        if (stack) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = vpre[j];
+                            stack_add_lo(v, s_lo, row, c0);
+                        } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 x, h, lo4;
@@ -216,8 +221,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     }
                 } else if (half == 0 && live) {
                     float q[32];
-                    tmem_ld32_sum(taddr, second, q);
-                    if (stack) stack_add_lo(q, s_lo, row, 0);
+                    if (stack) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = vpre[j];
+                        stack_add_lo(q, s_lo, row, 0);
+                    } else tmem_ld32_sum(taddr, second, q);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -284,9 +292,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             tc_fence_after();
             const float *bias = bias_all + T.bias_off;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
+            float vpre[32];                                      // this warp's accumulator chunk, loaded while the lo warps park theirs
             if (stack) {                                           // lo*hi block (rows [R, 2R)) -> scratch
                 if (quad * 32 >= R && quad * 32 < 2 * R)
                     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                if (live && half * 32 < T.N_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
                 __syncthreads();
             }
             if (l + 1 < nl) {
@@ -294,8 +304,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 float *act_row = a.act_buf + (size_t)gb * tc.act_stride + tc.L[l + 1].act_off;
                 for (int c0 = half * 32; live && c0 < T.N_pad; c0 += 64) {
                     float v[32];
-                    tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
-                    if (stack) stack_add_lo(v, s_lo, row, c0);
+                    if (stack) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = vpre[j];
+                        stack_add_lo(v, s_lo, row, c0);
+                    } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 x, h, lo4;
@@ -314,8 +327,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 const uint32_t sbon = umma_sbo(T.N_pad);
                 if (half == 0 && live) {
                     float q[32];
-                    tmem_ld32_sum(taddr, second, q);
-                    if (stack) stack_add_lo(q, s_lo, row, 0);
+                    if (stack) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) q[j] = vpre[j];
+                        stack_add_lo(q, s_lo, row, 0);
+                    } else tmem_ld32_sum(taddr, second, q);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -405,9 +421,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             const uint32_t sbon = umma_sbo(T.K_pad);
             float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + tc.L[l - 1].dz_off;
+            float vpre[32];                                      // this warp's accumulator chunk, loaded while the lo warps park theirs
             if (stack) {                                           // lo*hi block (rows [R, 2R)) -> scratch
                 if (quad * 32 >= R && quad * 32 < 2 * R)
                     for (int c0 = half * 32; c0 < T.K_pad && c0 < 64; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
+                if (live && half * 32 < T.K_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
                 __syncthreads();
             }
 #pragma unroll
@@ -415,8 +433,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 const int c0 = half * 32 + cc * 64;
                 if (!(live && c0 < T.K_pad)) continue;
                 float v[32];
-                tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
-                if (stack) stack_add_lo(v, s_lo, row, c0);
+                if (stack) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = vpre[j];
+                    stack_add_lo(v, s_lo, row, c0);
+                } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 hh = hpre[cc][j];
