@@ -363,10 +363,10 @@ reduce_publish_kernel(int P, int nparts, int n_loss_parts, float inv_b, const fl
         if (lane == 0)
             for (int q = 0; q < world; ++q) peer_recv[q][slot_off + P] = s * inv_b;
     }
-    __threadfence_system();                                      // this thread's remote stores are performed system-wide
-    __syncthreads();
+    __syncthreads();                                             // every thread's remote stores are ordered before thread 0's fence
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence_system();                                  // ONE cumulative system fence per block (a fence in each of the 256
+                                                                 // threads cost ~6 us per launch: UAVRL_DP_TRACE, round-2 call 9)
         const unsigned prev = atomicAdd(counter, 1u);
         if (prev == gridDim.x - 1) {                             // every block's slice has been pushed to every peer
             *counter = 0u;
@@ -473,11 +473,12 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
         if (lane == 0)
             for (int w = 0; w < a.world; ++w) peer_recv[w][slot + a.P] = s * a.inv_b;
     }
-    __threadfence_system();                                      // this thread's remote stores are performed system-wide
-    __syncthreads();
+    __syncthreads();                                             // the block's remote stores are ordered before the fences below
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) t2 = now();
     if (threadIdx.x < a.world) {                                 // thread w: raise (rank, block) on peer w, then wait for peer w's
         volatile unsigned *f = peer_flags[threadIdx.x] + 64 + (size_t)rank * nblk + blockIdx.x;   // [0, 64): the two-kernel pair's words
+        __threadfence_system();                                  // cumulative: covers every thread's stores before the barrier.  Only
+                                                                 // `world` threads fence -- one per thread cost ~6 us (UAVRL_DP_TRACE)
         *f = epoch;
         while (ld_acquire_sys(my_flags + (size_t)threadIdx.x * nblk + blockIdx.x) < epoch) { }
     }
@@ -895,7 +896,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
     if (l->dp_trace) {
         unsigned long long h[5] = { 0, 0, 0, 0, 0 };
         cudaMemcpy(h, l->dp_trace, sizeof(h), cudaMemcpyDeviceToHost);
-        if (h[4]) fprintf(stderr, "[dp_trace] rank %d/%d: %llu launches, block 0 mean ns: reduce %.0f  push+fence %.0f  flag wait %.0f  adam %.0f\n",
+        if (h[4]) fprintf(stderr, "[dp_trace] rank %d/%d: %llu launches, block 0 mean ns: reduce %.0f  push %.0f  fence+flag wait %.0f  adam %.0f\n",
                           l->rank, l->world, h[4], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4]);
         cudaFree(l->dp_trace);
     }
