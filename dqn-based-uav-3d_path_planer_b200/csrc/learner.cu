@@ -433,24 +433,56 @@ allreduce_adam_kernel(AdamArgs a, const float *recv, size_t stride, const unsign
     }
 }
 
-// ---- the same exchange in ONE kernel, block by block (default): block b owns parameters [64 b, 64 b + 64).  It reduces
-// its slice of this rank's partials, pushes the 64 values into slot `rank` of every rank's receive buffer, fences, and
-// raises the flag (rank, b) on every peer; then it waits -- in local memory -- for the `world` flags of ITS slice only,
-// sums the `world` slices in rank order and applies Adam.  No grid-wide completion, no second launch: a block never
-// waits for more than the matching block of each peer (all blocks of the grid are resident: 194 x 256 threads).
+// ---- the same exchange in ONE kernel, block by block, with NO fence and NO flag words (default): block b owns parameters
+// [64 b, 64 b + 64).  It reduces its slice of this rank's partials and pushes each value into slot `rank` of every rank's
+// receive buffer as ONE 8-byte word {epoch : value} (a single-copy-atomic store: the value can never be seen without its
+// epoch -- the "LL" idea of NCCL's low-latency protocol).  Then the 64 threads of the block poll -- in local memory -- the
+// `world` words of their own parameter until every epoch matches, sum the values in rank order and apply Adam.  A
+// __threadfence_system() between data and flag cost 6.7 us per launch even on one GPU (UAVRL_DP_TRACE, round-2 calls 9/10);
+// here nothing orders two stores, so nothing needs a fence.  recv[2][world][P + 1] alternates by epoch parity: a sender can
+// overwrite a slot only two exchanges later, and it cannot finish the exchange in between before the receiver has read.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// sum over ranks (fixed order: every rank computes the same bits) of the words {epoch : value} at recv[w * stride]
+__device__ __forceinline__ float ll_gather_sum(const unsigned long long *recv, size_t stride, int world, unsigned epoch)
+{
+    float gsum = 0.f;
+    for (int w0 = 0; w0 < world; w0 += 8) {
+        unsigned long long t[8];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (w0 + u < world) ? ld_relaxed_sys_u64(recv + (size_t)(w0 + u) * stride) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ok = ok && (w0 + u >= world || (unsigned)(t[u] >> 32) == epoch);
+        } while (!ok);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (w0 + u < world) gsum += __uint_as_float((unsigned)t[u]);
+    }
+    return gsum;
+}
+
 __global__ void __launch_bounds__(256)
 dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *__restrict__ partials,
-                         const float *__restrict__ loss_partials, float *const *peer_recv, const float *recv_local, size_t stride,
-                         size_t parity_off, unsigned *const *peer_flags, const unsigned *my_flags, int rank, unsigned epoch,
+                         const float *__restrict__ loss_partials, unsigned long long *const *peer_recv,
+                         const unsigned long long *recv_local, size_t stride, size_t parity_off, int rank, unsigned epoch,
                          AdamPtrs q, unsigned long long *trace)
 {
-    // trace (UAVRL_DP_TRACE=1): block 0 accumulates nanoseconds spent in {reduce, push + fence, flag wait, Adam} and a launch count
+    // trace (UAVRL_DP_TRACE=1): block 0 accumulates nanoseconds spent in {reduce, push, wait for the peers' words, Adam} and a launch count
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
-    const int nblk = gridDim.x;
     pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
     pdl_trigger();
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) t0 = now();
@@ -460,9 +492,10 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
     __syncthreads();
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) t1 = now();
     const size_t slot = parity_off + (size_t)rank * stride;
+    const unsigned long long tag = (unsigned long long)epoch << 32;
     if (i < a.P) {
         const float gs = (red[0][ix] + red[1][ix]) + (red[2][ix] + red[3][ix]);
-        for (int w = cg; w < a.world; w += 4) peer_recv[w][slot + i] = gs;       // 64 consecutive floats per peer: 256 contiguous bytes
+        for (int w = cg; w < a.world; w += 4) st_relaxed_sys_u64(peer_recv[w] + slot + i, tag | __float_as_uint(gs));   // 512 contiguous bytes per peer
     }
     if (blockIdx.x == 0 && threadIdx.x >= 224) {                 // last warp of block 0: this rank's loss share
         const int lane = threadIdx.x & 31;
@@ -471,39 +504,17 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0)
-            for (int w = 0; w < a.world; ++w) peer_recv[w][slot + a.P] = s * a.inv_b;
+            for (int w = 0; w < a.world; ++w) st_relaxed_sys_u64(peer_recv[w] + slot + a.P, tag | __float_as_uint(s * a.inv_b));
     }
-    __syncthreads();                                             // the block's remote stores are ordered before the fences below
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) t2 = now();
-    if (threadIdx.x < a.world) {                                 // thread w: raise (rank, block) on peer w, then wait for peer w's
-        volatile unsigned *f = peer_flags[threadIdx.x] + 64 + (size_t)rank * nblk + blockIdx.x;   // [0, 64): the two-kernel pair's words
-        __threadfence_system();                                  // cumulative: covers every thread's stores before the barrier.  Only
-                                                                 // `world` threads fence -- one per thread cost ~6 us (UAVRL_DP_TRACE)
-        *f = epoch;
-        while (ld_acquire_sys(my_flags + (size_t)threadIdx.x * nblk + blockIdx.x) < epoch) { }
-    }
-    __syncthreads();
-    if (trace && blockIdx.x == 0 && threadIdx.x == 0) t3 = now();
-    const float *recv = recv_local + parity_off;
+    const unsigned long long *recv = recv_local + parity_off;
     if (cg == 0 && i < a.P) {
-        float gsum = 0.f;
-        int w = 0;
-        for (; w + 8 <= a.world; w += 8) {
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = ld_relaxed_sys(recv + (size_t)(w + u) * stride + i);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) gsum += t[u];
-        }
-        for (; w < a.world; ++w) gsum += ld_relaxed_sys(recv + (size_t)w * stride + i);
+        const float gsum = ll_gather_sum(recv + i, stride, a.world, epoch);
+        if (trace && blockIdx.x == 0 && threadIdx.x == 0) t3 = now();
         q.grad[i] = gsum;
         adam_update_one(a, q, i, gsum);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 255 && q.loss_out) {
-        float s = 0.f;
-        for (int w = 0; w < a.world; ++w) s += ld_relaxed_sys(recv + (size_t)w * stride + a.P);
-        *q.loss_out = s;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 255 && q.loss_out) *q.loss_out = ll_gather_sum(recv + a.P, stride, a.world, epoch);
     if (trace && blockIdx.x == 0) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -757,15 +768,15 @@ int launch_update_dp(uavrl_learner *l, const BatchSrc &src, int B, int global_ba
     static const bool dp_trace = getenv("UAVRL_DP_TRACE") != nullptr;
     if (dp_trace && !l->dp_trace) { UAVRL_CUDA(cudaMalloc((void **)&l->dp_trace, 5 * 8)); UAVRL_CUDA(cudaMemsetAsync(l->dp_trace, 0, 40, st)); }
     const int nblk = (P + 63) / 64;
-    if (!two_kernels && l->world * nblk <= l->comm_flag_words) {
+    if (!two_kernels) {
         AdamPtrs q;
         q.partials = l->partials; q.loss_partials = l->loss_partials; q.grad = l->grad; q.local = l->local; q.m = l->m; q.v = l->v;
         q.target = l->target; q.img_local = l->img_local; q.img_target = l->img_target; q.img_map = l->img_map;
         q.tc_local = (float *)l->tc_img_local; q.tc_target = (float *)l->tc_img_target; q.tc_hi = l->tc_hi_map; q.tc_lo = l->tc_lo_map;
         q.tc_hi2 = l->tc_hi2_map; q.tc_lo2 = l->tc_lo2_map; q.loss_out = loss_out ? loss_out : l->loss_dev;
         UAVRL_CUDA(launch_kernel(dp_allreduce_adam_kernel, dim3(nblk), dim3(256), 0, st, chain && l->pdl_prev == kPdlDw, a, l->last_nparts,
-                                 l->last_n_loss_parts, (const float *)l->partials, (const float *)l->loss_partials, l->peer_grad_dev,
-                                 (const float *)l->comm_grad, stride, parity_off, l->peer_flag_dev, (const unsigned *)l->comm_flags + 64,
+                                 l->last_n_loss_parts, (const float *)l->partials, (const float *)l->loss_partials,
+                                 (unsigned long long *const *)l->peer_grad_dev, (const unsigned long long *)l->comm_grad, stride, parity_off,
                                  l->rank, l->flag_epoch, q, l->dp_trace));
         UAVRL_LAUNCHED();
         l->pdl_prev = chain ? kPdlAdam : kPdlNone;
@@ -896,7 +907,7 @@ int uavrl_learner_destroy(uavrl_learner *l)
     if (l->dp_trace) {
         unsigned long long h[5] = { 0, 0, 0, 0, 0 };
         cudaMemcpy(h, l->dp_trace, sizeof(h), cudaMemcpyDeviceToHost);
-        if (h[4]) fprintf(stderr, "[dp_trace] rank %d/%d: %llu launches, block 0 mean ns: reduce %.0f  push %.0f  fence+flag wait %.0f  adam %.0f\n",
+        if (h[4]) fprintf(stderr, "[dp_trace] rank %d/%d: %llu launches, block 0 mean ns: reduce %.0f  push %.0f  wait for peers' words %.0f  adam %.0f\n",
                           l->rank, l->world, h[4], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4]);
         cudaFree(l->dp_trace);
     }
@@ -1163,13 +1174,14 @@ int uavrl_learner_comm_init(uavrl_learner *l, int32_t rank, int32_t world, void 
     }
     l->comm_world = world;
     if (!l->comm_grad) {
-        const size_t n = 2 * (size_t)world * ((size_t)l->net.P + 1);     // recv[2][world][P+1]
-        UAVRL_CUDA(cudaMalloc((void **)&l->comm_grad, n * sizeof(float)));
-        UAVRL_CUDA(cudaMemset(l->comm_grad, 0, n * sizeof(float)));
-        // flag words: [0, 64) one per rank (the two-kernel pair), then [64, 64 + world x blocks) one per (rank, 64-parameter block)
-        l->comm_flag_words = world * (int)((l->net.P + 63) / 64);
-        UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, (size_t)(64 + l->comm_flag_words) * sizeof(unsigned)));
-        UAVRL_CUDA(cudaMemset(l->comm_flags, 0, (size_t)(64 + l->comm_flag_words) * sizeof(unsigned)));
+        // recv[2][world][P+1] words of 8 bytes {epoch : value} (the default one-kernel exchange; epoch 0 = never written).  The
+        // two-kernel pair (UAVRL_DP_TWO_KERNELS=1) uses the first half as plain floats plus the flag words below.
+        const size_t n = 2 * (size_t)world * ((size_t)l->net.P + 1);
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_grad, n * sizeof(unsigned long long)));
+        UAVRL_CUDA(cudaMemset(l->comm_grad, 0, n * sizeof(unsigned long long)));
+        l->comm_flag_words = 0;
+        UAVRL_CUDA(cudaMalloc((void **)&l->comm_flags, (size_t)64 * sizeof(unsigned)));        // one flag per rank (the two-kernel pair)
+        UAVRL_CUDA(cudaMemset(l->comm_flags, 0, (size_t)64 * sizeof(unsigned)));
         UAVRL_CUDA(cudaMalloc((void **)&l->comm_counter, sizeof(unsigned)));
         UAVRL_CUDA(cudaMemset(l->comm_counter, 0, sizeof(unsigned)));
     }
