@@ -247,9 +247,7 @@ __device__ __forceinline__ float reduce_group(const float *__restrict__ partials
 
 __device__ __forceinline__ void tf32_split_f(float x, float &hi, float &lo)
 {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);     // = cvt.rna.tf32.f32 for finite x (umma.cuh: tf32_split)
     lo = x - hi;
 }
 

@@ -139,45 +139,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     // does not write them (act after the optimiser kernel: observations were written two kernels back).
     const bool early_w = (a.pdl & kPdlEarlyWeights) != 0;
     bool waited = (a.pdl & kPdlEarlyRows) == 0;
-    if (tid == 0 && early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    if (tid == kTcThreads - 32 && early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
     if (waited) {
         pdl_wait();
         pdl_trigger();
-        if (tid == 0 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+        if (tid == kTcThreads - 32 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
     }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
-    uint32_t pkey[4];
-    Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
+    // act mode: row b of the tile is simply obs[base + b] -- no replay sampling (Philox), no pointer table, no barrier
+    const bool direct = (a.mode == kTcAct);
+    uint32_t pkey[4] = {0u, 0u, 0u, 0u};
+    if (!direct) Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
     uint32_t mphase = 0;
     bool wready = false;
 
     // R = real rows per tile (32 / 64 / 128).  The MMA is always M = 128; accumulator rows >= R hold garbage
     // computed from whatever SMEM follows the R-row operand (still inside this CTA's allocation) and are
     // never read.  Small batches use R = 32 so that 4096 samples spread over 128 CTAs instead of 32.
-    const int R = a.rows_per_tile;
+    const int R = a.rows_per_tile, lgR = 31 - __clz(R);
     // R <= 64: stacked 3xTF32 (umma.cuh) -- A_lo lives in rows [R, 2R) of the Ahi buffer, the Alo buffer is the scratch through
     // which the lo*hi block reaches the epilogue warps
     const bool stack = (R <= 64) && tc.concat && tc.dstride <= 128;     // (the scratch rows hold 64 columns: layers up to 64 wide)
     float *s_lo = reinterpret_cast<float *>(Alo);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int base = tile * R;
-        if (tid < R) {
-            const int b = base + tid;
-            const float *p = nullptr;
-            float r = 0.f, d = 0.f;
-            if (b < a.n) {
-                if (a.mode == kTcAct) p = a.obs + (size_t)b * tc.in_dim;
-                else {
+        if (!direct) {
+            if (tid < R) {
+                const int b = base + tid;
+                const float *p = nullptr;
+                float r = 0.f, d = 0.f;
+                if (b < a.n) {
                     const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
                     p = a.use_next ? t.s2 : t.s; r = t.r; d = t.d;
                 }
+                rows[tid] = p; s_rew[tid] = r; s_done[tid] = d;
             }
-            rows[tid] = p; s_rew[tid] = r; s_done[tid] = d;
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout (4 loads in flight per thread;
-        //      lanes walk the 8 rows of a core-matrix column first: conflict-free 16-byte stores)
+        TC_TRACE(27);
+        // ---- A operand of layer 0: gathered rows -> TF32 hi/lo, canonical K-major layout (4 loads in flight per thread).
+        //      Item i = (chunk j = i / R, row r = i % R): consecutive lanes take consecutive rows of the same 16-byte chunk, so
+        //      a quarter-warp's 16-byte stores cover one whole core-matrix column = 128 contiguous bytes, and no division.
         {
             const int K0 = tc.L[0].K_pad, chunks = K0 / 4, total = R * chunks;
             const uint32_t sbo = umma_sbo(K0);
@@ -188,15 +191,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                     const int i = i0 + u * kTcThreads;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i < total) {
-                        const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
-                        if (rows[r] && 4 * j < tc.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
+                        const int r = i & (R - 1), j = i >> lgR;
+                        const float *rp = direct ? ((base + r < a.n) ? a.obs + (size_t)(base + r) * tc.in_dim : nullptr) : rows[r];
+                        if (rp && 4 * j < tc.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rp) + j);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = i0 + u * kTcThreads;
                     if (i < total) {
-                        const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
+                        const int r = i & (R - 1), j = i >> lgR;
                         float4 h, l;
                         tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                         const uint32_t off = umma_off(r, 4 * j, sbo);
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             pdl_wait();
             pdl_trigger();
             waited = true;
-            if (tid == 0 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+            if (tid == kTcThreads - 32 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
         }
         if (!wready) { mbar_wait(&wbar, 0); wready = true; }
         TC_TRACE(3);
@@ -250,7 +254,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                 if (quad * 32 >= R && quad * 32 < 2 * R)
                     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) stack_park_lo(taddr, c0, s_lo, row - R);
                 if (live && half * 32 < T.N_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
+                if (l == 0) TC_TRACE(22);
                 __syncthreads();
+                if (l == 0) TC_TRACE(23);
             }
             if (l + 1 < tc.n_layers) {
                 // hidden layer epilogue: bias + ReLU, re-split, write the next A operand (K_next = N_pad)
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                         for (int j = 0; j < 32; ++j) v[j] = vpre[j];
                         stack_add_lo(v, s_lo, row, c0);
                     } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                    if (l == 0) TC_TRACE(24);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 h, lo4;
@@ -274,7 +281,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                         else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                     }
                 }
+                if (l == 0) TC_TRACE(25);
                 fence_proxy_async();
+                if (l == 0) TC_TRACE(26);
                 tc_fence_before();
                 __syncthreads();
                 tc_fence_after();
@@ -394,7 +403,7 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st, con
         UAVRL_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(tr);
         fprintf(stderr, "[tc_trace] mode=%d n=%d R=%d grid=%d cycles since start:", a.mode, a.n, a.rows_per_tile, grid);
-        for (int i = 1; i < 22; ++i) if (h[i]) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
+        for (int i = 1; i < 32; ++i) if (h[i]) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
         fprintf(stderr, "\n");
     }
     return 0;

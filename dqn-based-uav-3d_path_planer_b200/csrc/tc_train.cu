@@ -45,7 +45,9 @@ struct TcTrainArgs {
     int32_t fused_td, algo;
     float gamma;
     const unsigned char *img_target;   // target network, forward image
+    long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
 };
+#define TR_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
 struct TcDwArgs {
     BatchSrc src;
@@ -64,12 +66,13 @@ struct TcDwArgs {
 #define DW_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[slot] = clock64(); } while (0)
 
 // Gather R rows (pointers in rows[]) into the layer-0 A operand.  All of a thread's loads are issued before any
-// is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.  Consecutive lanes take
-// consecutive rows of an 8-row group (same 16-byte chunk): a quarter-warp's 16-byte stores then cover one whole core
-// matrix column = 128 contiguous bytes (lanes walking along a row would all hit the same 4 banks).
+// is consumed (4 in flight), so the gather costs one L2 round trip instead of one per chunk.  Item i = (chunk j = i / R,
+// row r = i % R; R is a power of two): consecutive lanes take consecutive rows of the same 16-byte chunk, so a quarter-warp's
+// 16-byte stores cover one whole core matrix column = 128 contiguous bytes (lanes walking along a row would all hit the
+// same 4 banks) and the index needs no division.
 __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in_dim, int K0, unsigned char *Ahi, unsigned char *Alo, bool stack)
 {
-    const int chunks = K0 / 4, total = R * chunks;
+    const int chunks = K0 / 4, total = R * chunks, lgR = 31 - __clz(R);
     const uint32_t sbo = umma_sbo(K0);
     for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kTcThreads) {
         float4 v[4];
@@ -78,7 +81,7 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
             const int i = i0 + u * kTcThreads;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < total) {
-                const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
+                const int r = i & (R - 1), j = i >> lgR;
                 if (rows[r] && 4 * j < in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(rows[r]) + j);
             }
         }
@@ -86,7 +89,7 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kTcThreads;
             if (i < total) {
-                const int rg = i / (8 * chunks), tt = i - rg * 8 * chunks, r = 8 * rg + (tt & 7), j = tt >> 3;
+                const int r = i & (R - 1), j = i >> lgR;
                 float4 h, l;
                 tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
                 const uint32_t off = umma_off(r, 4 * j, sbo);
@@ -100,6 +103,7 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
 
 __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
 {
+    TR_TRACE(0);
     extern __shared__ __align__(1024) unsigned char smem[];
     const int R = a.R;
     const uint32_t a_bytes = (uint32_t)(R / 8) * umma_sbo(tc.max_k);
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    TR_TRACE(1);
     const bool fused = a.fused_td != 0;
     const int n_pre = fused ? (a.algo != UAVRL_ALGO_DQN ? 2 : 1) : 0;     // forward-only passes ahead of the training chain
     // PDL.  Unfused: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     // predecessor's output.  Fused: the predecessor is the env step, which writes the newest frame's rows, rewards and
     // flags -- only the first pass's weight image (optimiser kernel, >= 2 back) is fetched before the wait.
     uint32_t wphase = 0;
-    if (tid == 0) {
+    if (tid == kTcThreads - 32) {                                // (a lane of an otherwise idle warp: thread 0 resolves a sample meanwhile)
         fence_proxy_async();
         if (!fused) bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
         else bulk_g2s_chunked(W, (n_pre == 2) ? a.img : a.img_target, (uint32_t)tc.img_bytes, &wbar);
@@ -161,18 +166,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             if (fused) { rows2[tid] = p2; s_rew[tid] = rw; s_done[tid] = dn; s_astar[tid] = 0; }
         }
         __syncthreads();
+        TR_TRACE(2);
         // ---------------- fused TD target: forward-only pass(es) on the next states (tc_forward.cu's chain and head)
         for (int pass = 0; pass < n_pre; ++pass) {
-            if (pass > 0 && tid == 0) {                          // the target image replaces the local one (all its readers are done)
+            if (pass > 0 && tid == kTcThreads - 32) {                          // the target image replaces the local one (all its readers are done)
                 fence_proxy_async();
                 bulk_g2s_chunked(W, a.img_target, (uint32_t)tc.img_bytes, &wbar);
             }
             build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
+            if (pass == 0) TR_TRACE(3);
             mbar_wait(&wbar, wphase); wphase ^= 1;
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
+            if (pass == 0) TR_TRACE(4);
             const bool td_pass = (pass == n_pre - 1);
             for (int l = 0; l < nl; ++l) {
                 const TcLayer T = tc.L[l];
@@ -256,13 +264,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 tc_fence_before();
                 __syncthreads();
                 tc_fence_after();
+                if (pass == 0) TR_TRACE(5 + l);
             }
         }
-        if (fused && tid == 0) {                                  // the training image (every reader of the TD image is done)
+        if (fused && tid == kTcThreads - 32) {                                  // the training image (every reader of the TD image is done)
             fence_proxy_async();
             bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
         }
         build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
+        TR_TRACE(9);
         if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
         if (!fused && tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
         if (fused) { mbar_wait(&wbar, wphase); wphase ^= 1; }
@@ -271,6 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        TR_TRACE(10);
         const int gb = base + row;                          // this thread's sample (valid when live && gb < B)
         const bool mine = live && gb < a.B;
 
@@ -387,6 +398,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
+            TR_TRACE(11 + l);
         }
 
         // ---------------- dX chain: dZ_{l-1} = (dZ_l * W_l) .* (H_l > 0), l = nl-1 .. 1
@@ -458,8 +470,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
+            TR_TRACE(16 + l);
         }
     }
+    TR_TRACE(20);
     if (tid == 0) a.loss_partials[blockIdx.x] = s_loss;
     tc_fence_before();
     __syncthreads();
@@ -732,6 +746,9 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     const bool chain = l->pdl_chain && g_pdl.load();
     if (fused_td && a.n_tiles > grid) return fail(UAVRL_ERR_INVALID, "fused TD needs one tile per CTA");
+    static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
+    long long *tr = nullptr;
+    if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 48 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 48 * sizeof(long long))); a.trace = tr + 16; }
     UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st,
                              chain && (fused_td ? (l->pdl_prev == kPdlEnv) : (l->pdl_prev == kPdlTd)), tc, a));
     l->pdl_prev = chain ? kPdlTrain : kPdlNone;
@@ -762,18 +779,19 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
         q.tc_local = (float *)l->tc_img_local; q.tc_target = (float *)l->tc_img_target; q.tc_hi = l->tc_hi_map; q.tc_lo = l->tc_lo_map;
         q.tc_hi2 = l->tc_hi2_map; q.tc_lo2 = l->tc_lo2_map; q.loss_out = loss_out;
     }
-    static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
-    long long *tr = nullptr;
-    if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); d.trace = tr; }
+    if (trace_on) d.trace = tr;
     UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(dw_grid), dim3(kTcThreads), dw_smem_bytes(tc), st,
                              chain && !after_chain, tc, d));
     l->pdl_prev = chain ? (fuse ? kPdlAdam : kPdlDw) : kPdlNone;
     UAVRL_LAUNCHED();
     if (trace_on) {
-        long long h[16];
+        long long h[48];
         UAVRL_CUDA(cudaStreamSynchronize(st));
         UAVRL_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(tr);
+        fprintf(stderr, "[train_trace] B=%d R=%d fused_td=%d cycles since start:", B, a.R, a.fused_td);
+        for (int i = 1; i < 32; ++i) if (h[16 + i]) fprintf(stderr, " [%d]=%lld", i, h[16 + i] - h[16]);
+        fprintf(stderr, "\n");
         fprintf(stderr, "[dw_trace] B=%d chunks=%d (CTA 0 = layer 0) cycles since start:", B, d.n_chunks);
         for (int i = 1; i < 9; ++i) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
         fprintf(stderr, "\n");

@@ -140,11 +140,13 @@ __device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t second_of
 
 // 3xTF32 split: hi = x rounded to TF32 (10-bit mantissa), lo = x - hi (exact).  hi*hi + hi*lo + lo*hi
 // reproduces the fp32 product to ~2^-21.
+// Round-to-nearest, ties away (cvt.rna.tf32.f32) on the bit pattern: add half an ulp of the 10-bit mantissa to the magnitude
+// and clear the 13 dropped bits -- two integer instructions.  ptxas expands the cvt into the same two plus an |x| < inf
+// test and a select per element (inf/NaN kept verbatim); for every finite x that does not round up to inf the result is
+// bit-identical, inf stays inf, and the epilogues run this 32 times per thread per layer.
 __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
 {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = x - hi;
 }
 
