@@ -19,6 +19,8 @@
 //            80 x 26 loop.
 //   phase 3  the CTA's 32 x 100 fp32 observation tile (12.8 KB, contiguous in HBM) is written
 //            with 16-byte stores, fully coalesced; this is the only large traffic of the step.
+#include <stdlib.h>
+#include <stdio.h>
 #include "env.cuh"
 #include "env_block.cuh"
 
@@ -82,9 +84,25 @@ __global__ void threat_kernel(EnvDev d, int n, const double *__restrict__ pts, u
     out[i] = (uint8_t)hit;
 }
 
-int launch_env_step(const EnvDev &d, int action_kind, const void *actions, float *obs, float *reward,
+int launch_env_step(const EnvDev &d_in, int action_kind, const void *actions, float *obs, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *coll, uint8_t *ended, cudaStream_t st, bool pdl)
 {
+    EnvDev d = d_in;
+    static const bool trace_on = getenv("UAVRL_ENV_TRACE") != nullptr;
+    static long long *tr = nullptr;
+    static int n_traced = 0;
+    if (trace_on) {
+        if (!tr) { UAVRL_CUDA(cudaMalloc((void **)&tr, 16 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 16 * sizeof(long long))); }
+        else if (++n_traced % 64 == 0) {                         // print the PREVIOUS launch's stamps every 64 launches
+            long long h[16];
+            UAVRL_CUDA(cudaStreamSynchronize(st));
+            UAVRL_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[env_trace] n=%d cycles since start:", d.n);
+            for (int i = 1; i < 12; ++i) fprintf(stderr, " [%d]=%lld", i, h[i] - h[0]);
+            fprintf(stderr, "\n");
+        }
+        d.trace = tr;
+    }
     if (d.extras) {                                              // optional models: the EXTRAS instantiation (never inside a PDL chain)
         const int blocks = (d.n + kEnvsPerBlockSmall - 1) / kEnvsPerBlockSmall;
         UAVRL_CUDA(launch_kernel(env_kernel<true, kEnvsPerBlockSmall, true>, dim3(blocks), dim3(kEnvThreads), 0, st, pdl, d, action_kind, actions, obs,

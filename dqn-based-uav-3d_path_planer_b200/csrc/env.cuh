@@ -43,6 +43,7 @@ struct EnvDev {
     int32_t *path_n;                    // [2][track_n] points recorded (buffer 0/1)
     int32_t *path_cur;                  // [track_n] buffer holding the episode in progress
     int32_t track_n, track_cap;
+    long long *trace;                   // debug (UAVRL_ENV_TRACE): CTA 0 / thread 0 stage timestamps
 };
 constexpr int kExtraEnergy = 1, kExtraApf = 2, kExtraTrack = 4;
 

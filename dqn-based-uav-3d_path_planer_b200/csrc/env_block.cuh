@@ -113,6 +113,8 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                                           uint8_t *__restrict__ done_out, uint8_t *__restrict__ info_out,
                                           uint8_t *__restrict__ coll_out, uint8_t *__restrict__ ended_out)
 {
+#define ENV_TRACE(slot) do { if (d.trace && blockIdx.x == 0 && tid == 0) d.trace[slot] = clock64(); } while (0)
+    ENV_TRACE(0);
     Cyl *s_cyl = sm.cyl;
     uint8_t *sm_flags = EXTRAS ? sm.flags : nullptr;
     if (EXTRAS && tid < EPB) sm.flags[tid] = 0;
@@ -156,6 +158,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     for (int i = tid; i < d.k.n_cyl * 6; i += NT)
         reinterpret_cast<double *>(s_cyl)[i] = reinterpret_cast<const double *>(d.cyl)[i];
     __syncthreads();
+    ENV_TRACE(1);
     if (USE_PDL && wp >= NW1) { pdl_wait(); pdl_trigger(); }
 
     if (wp < NW1) {
@@ -164,6 +167,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
         int n_stepped = 0, n_ended = 0, n_coll = 0, n_succ = 0, n_lose = 0;
         // exact candidate cull, shared by the whole warp (the lanes beyond LPW would otherwise idle)
         mask = cull_mask_coop<LPW>(d, s_cyl, s.px, s.py, ln);
+        ENV_TRACE(2);
         if (valid) {
             if (DO_STEP) {
                 if (USE_PDL) { pdl_wait(); pdl_trigger(); }
@@ -172,6 +176,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 else if (action_kind == UAVRL_ACT_CONT_F64) act = static_cast<const double *>(actions)[e];
                 else if (action_kind == UAVRL_ACT_CONT_F32X2) act = (double)static_cast<const float *>(actions)[2 * e];
                 else act = (double)static_cast<const int32_t *>(actions)[e];
+                ENV_TRACE(3);
                 const int mode = (action_kind == UAVRL_ACT_DISCRETE27) ? 1 : 0;
                 const bool apf_on = EXTRAS && (d.extras & kExtraApf);
                 const double *q = apf_on ? d.sub_env + (size_t)e * d.K * 3 : d.pool_sub + (size_t)scen * d.K * 3;
@@ -195,6 +200,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 } else {
                     step_core(d.k, s, mode, act, sub, threat, o);
                 }
+                ENV_TRACE(4);
                 if (EXTRAS) {
                     if (d.extras & kExtraEnergy) {
                         const double pw = fly_power(d.pw, s.V);
@@ -237,6 +243,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 d.step[e] = s.step; d.cursor[e] = s.cursor;
                 d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
             }
+            ENV_TRACE(5);
             if (obs) {
                 const bool apf_on = EXTRAS && (d.extras & kExtraApf);
                 // APF: an env that did not restart reads its own queue, whose entries phase 1b shifts right after this
@@ -256,6 +263,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 };
                 obs_scalars(s, sub, &s_obs[le][0]);
             }
+            ENV_TRACE(6);
             px = s.px; py = s.py; pz = s.pz;
         }
         if (ln < LPW) {
@@ -288,7 +296,9 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             }
         }
     }
+    ENV_TRACE(7);
     __syncthreads();
+    ENV_TRACE(8);
     if (EXTRAS && DO_STEP && (d.extras & kExtraApf)) {
         // phase 1b, all threads: UAV.Adjust_subgoal (UAV.py:156-166) for the stored queues -- every entry moves by the
         // force at its (pre-step) position; an env that restarted takes its new scenario's queue instead
@@ -323,7 +333,9 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
         }
         s_obs[le][po.slot] = hit ? 1.0f : 0.0f;
     }
+    ENV_TRACE(9);
     __syncthreads();
+    ENV_TRACE(10);
 
     // phase 3: coalesced 16-byte stores of the contiguous [nvalid][100] tile
     const int nvalid = min(EPB, d.n - e0);
@@ -331,6 +343,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)e0 * kObsDim);
     const float4 *src = reinterpret_cast<const float4 *>(&s_obs[0][0]);
     for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+    ENV_TRACE(11);
 }
 
 }  // namespace uavrl

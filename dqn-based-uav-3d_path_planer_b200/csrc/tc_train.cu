@@ -101,6 +101,38 @@ __device__ __forceinline__ void build_a0(const float *const *rows, int R, int in
     }
 }
 
+// The same gather in two halves for a tile of at most 4 * kTcThreads items (R = 32: 832): the loads are issued long before the
+// operand buffer is free (the fused TD pre-pass runs in between), so the HBM latency of the sampled rows is off the chain.
+__device__ __forceinline__ void a0_load(const float *const *rows, int R, int in_dim, int K0, float4 (&v)[4])
+{
+    const int total = R * (K0 / 4), lgR = 31 - __clz(R);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * kTcThreads;
+        const int r = i & (R - 1), j = i >> lgR;
+        const float *rp = (i < total) ? rows[r] : nullptr;
+        v[u] = (rp && 4 * j < in_dim) ? __ldg(reinterpret_cast<const float4 *>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void a0_store(const float4 (&v)[4], int R, int K0, unsigned char *Ahi, unsigned char *Alo, bool stack)
+{
+    const int total = R * (K0 / 4), lgR = 31 - __clz(R);
+    const uint32_t sbo = umma_sbo(K0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * kTcThreads;
+        if (i < total) {
+            const int r = i & (R - 1), j = i >> lgR;
+            float4 h, l;
+            tf32_split(v[u].x, h.x, l.x); tf32_split(v[u].y, h.y, l.y); tf32_split(v[u].z, h.z, l.z); tf32_split(v[u].w, h.w, l.w);
+            const uint32_t off = umma_off(r, 4 * j, sbo);
+            *reinterpret_cast<float4 *>(Ahi + off) = h;
+            if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + r, 4 * j, sbo)) = l;
+            else *reinterpret_cast<float4 *>(Alo + off) = l;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
 {
     TR_TRACE(0);
@@ -152,6 +184,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     const int nl = tc.n_layers;
     const int row = quad * 32 + lane;
     const bool live = quad * 32 < R;
+    // ReLU' for the dX chain: bit j of hmK = (H_K[row][half * 32 + j] > 0), kept from the forward epilogue of the same thread
+    // (hidden layers are at most 64 wide here: one 32-column chunk per thread) -- no reload of H from global memory
+    uint32_t hm1 = 0u, hm2 = 0u, hm3 = 0u, hm4 = 0u;
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int base = tile * R;
@@ -167,6 +202,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         }
         __syncthreads();
         TR_TRACE(2);
+        // the training rows are requested now and consumed after the TD pre-pass (a0_load / a0_store)
+        const bool early_rows = n_pre > 0 && R * (tc.L[0].K_pad / 4) <= 4 * kTcThreads;
+        float4 vmain[4];
+        if (early_rows) a0_load(rows, R, tc.in_dim, tc.L[0].K_pad, vmain);
         // ---------------- fused TD target: forward-only pass(es) on the next states (tc_forward.cu's chain and head)
         for (int pass = 0; pass < n_pre; ++pass) {
             if (pass > 0 && tid == kTcThreads - 32) {                          // the target image replaces the local one (all its readers are done)
@@ -271,7 +310,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             fence_proxy_async();
             bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
         }
-        build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
+        if (early_rows) a0_store(vmain, R, tc.L[0].K_pad, Ahi, Alo, stack);
+        else build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
         TR_TRACE(9);
         if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
         if (!fused && tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
@@ -320,6 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         for (int j = 0; j < 32; ++j) v[j] = vpre[j];
                         stack_add_lo(v, s_lo, row, c0);
                     } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
+                    uint32_t mk = 0u;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 x, h, lo4;
@@ -330,8 +371,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         *reinterpret_cast<float4 *>(Ahi + off) = h;
                         if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
                         else *reinterpret_cast<float4 *>(Alo + off) = lo4;
-                        if (mine) *reinterpret_cast<float4 *>(act_row + c0 + 4 * j) = x;      // kept for ReLU' and dW
+                        if (mine) *reinterpret_cast<float4 *>(act_row + c0 + 4 * j) = x;      // kept for dW
+                        mk |= ((x.x > 0.f ? 1u : 0u) | (x.y > 0.f ? 2u : 0u) | (x.z > 0.f ? 4u : 0u) | (x.w > 0.f ? 8u : 0u)) << (4 * j);
                     }
+                    if (!mine) mk = 0u;
+                    if (l == 0) hm1 = mk; else if (l == 1) hm2 = mk; else if (l == 2) hm3 = mk; else hm4 = mk;
                 }
             } else {
                 // head: Q(s, .), loss, dLoss/dHead -> next A operand (K = 32) and the dz scratch
@@ -358,20 +402,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     float qa = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (j == act) qa = q[j];
-                    float gq = 0.f;
+                    float gq = 0.f, lterm = 0.f;
                     if (mine) {
                         const float diff = qa - s_y[row];
                         const float wb = a.src.is_w ? a.src.is_w[gb] : 1.f;
                         if (a.src.abs_err) a.src.abs_err[gb] = fabsf(diff);
                         if (a.loss_kind == 0) {                       // MSELoss (BaseTrainer.py:40)
-                            atomicAdd(&s_loss, wb * (diff * diff));
+                            lterm = wb * (diff * diff);
                             gq = (2.f * diff * wb) * a.inv_global_b;
                         } else {                                      // SmoothL1Loss(beta = 1)
                             const float ad = fabsf(diff);
-                            atomicAdd(&s_loss, wb * (ad < 1.f ? 0.5f * (diff * diff) : ad - 0.5f));
+                            lterm = wb * (ad < 1.f ? 0.5f * (diff * diff) : ad - 0.5f);
                             gq = (fminf(fmaxf(diff, -1.f), 1.f) * wb) * a.inv_global_b;
                         }
                     }
+                    // the warp's 32 loss terms: butterfly sum, ONE shared-memory add per warp (an atomicAdd per lane on the same
+                    // word is a 32-deep compare-and-swap chain: 6 k cycles in the round-2 stage trace) -- and a fixed order
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) lterm += __shfl_xor_sync(0xffffffffu, lterm, off);
+                    if (lane == 0) atomicAdd(&s_loss, lterm);
                     float g[32];
                     const float inv = 1.f / (float)nA;
 #pragma unroll
@@ -414,19 +463,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                                   T.N_pad / 8, tc.concat != 0);
                 umma_commit(&mbar);
             }
-            // H_l (this layer's input, written by the forward epilogue of the same thread) is needed for ReLU':
-            // fetch it while the MMA runs.  K_pad <= 128 -> at most two 32-column chunks per thread.
-            const float *act_row = a.act_buf + (size_t)gb * tc.act_stride + T.act_off;
-            float4 hpre[2][8];
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = half * 32 + cc * 64;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hpre[cc][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (mine && c0 < T.K_pad) hpre[cc][j] = *reinterpret_cast<const float4 *>(act_row + c0 + 4 * j);
-                }
-            }
+            // ReLU'(H_l): the sign mask this thread kept in the forward epilogue (K_pad <= 64: one 32-column chunk per thread)
+            const uint32_t hmask = (l == 1) ? hm1 : (l == 2) ? hm2 : (l == 3) ? hm3 : hm4;
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
@@ -440,29 +478,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 if (live && half * 32 < T.K_pad) tmem_ld32_sum(taddr + (uint32_t)(half * 32), second, vpre);
                 __syncthreads();
             }
+            {
+                const int c0 = half * 32;
+                if (live && c0 < T.K_pad) {
+                    float v[32];
+                    if (stack) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = half * 32 + cc * 64;
-                if (!(live && c0 < T.K_pad)) continue;
-                float v[32];
-                if (stack) {
+                        for (int j = 0; j < 32; ++j) v[j] = vpre[j];
+                        stack_add_lo(v, s_lo, row, c0);
+                    } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = vpre[j];
-                    stack_add_lo(v, s_lo, row, c0);
-                } else tmem_ld32_sum(taddr + (uint32_t)c0, second, v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 hh = hpre[cc][j];
-                    float4 x, h, lo4;
-                    x.x = hh.x > 0.f ? v[4 * j + 0] : 0.f; x.y = hh.y > 0.f ? v[4 * j + 1] : 0.f;
-                    x.z = hh.z > 0.f ? v[4 * j + 2] : 0.f; x.w = hh.w > 0.f ? v[4 * j + 3] : 0.f;
-                    if (mine) *reinterpret_cast<float4 *>(dz_row + c0 + 4 * j) = x;
-                    if (l > 1) {
-                        tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
-                        const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
-                        *reinterpret_cast<float4 *>(Ahi + off) = h;
-                        if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
-                        else *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t m4 = hmask >> (4 * j);
+                        float4 x, h, lo4;
+                        x.x = (m4 & 1u) ? v[4 * j + 0] : 0.f; x.y = (m4 & 2u) ? v[4 * j + 1] : 0.f;
+                        x.z = (m4 & 4u) ? v[4 * j + 2] : 0.f; x.w = (m4 & 8u) ? v[4 * j + 3] : 0.f;
+                        if (mine) *reinterpret_cast<float4 *>(dz_row + c0 + 4 * j) = x;
+                        if (l > 1) {
+                            tf32_split(x.x, h.x, lo4.x); tf32_split(x.y, h.y, lo4.y); tf32_split(x.z, h.z, lo4.z); tf32_split(x.w, h.w, lo4.w);
+                            const uint32_t off = umma_off(row, c0 + 4 * j, sbon);
+                            *reinterpret_cast<float4 *>(Ahi + off) = h;
+                            if (stack) *reinterpret_cast<float4 *>(Ahi + umma_off(R + row, c0 + 4 * j, sbon)) = lo4;
+                            else *reinterpret_cast<float4 *>(Alo + off) = lo4;
+                        }
                     }
                 }
             }
