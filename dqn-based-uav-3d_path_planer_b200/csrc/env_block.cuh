@@ -30,6 +30,8 @@ struct EnvSmem {
     double pos[3][EPB];
     unsigned long long mask[EPB];
     uint8_t flags[EPB];                 // EXTRAS/APF: 1 = shift this env's sub-goal queue, 2 = reload it from the pool
+    double st_rew[EPB];                 // statistics parked by phase 1 (reward, flags: stepped | ended<<1 | collision<<2 | success<<3 | lose<<4)
+    uint8_t st_flags[EPB];
     uint8_t safe[EPB];                  // 1: none of this env's 75 planar probes can be out of bounds (phase 2 skips the test)
     ProbeOff probe[80];
 };
@@ -119,6 +121,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     uint8_t *sm_flags = EXTRAS ? sm.flags : nullptr;
     if (EXTRAS && tid < EPB) sm.flags[tid] = 0;
     if (tid < 80) sm.probe[tid] = probe_offset(tid);
+    if (DO_STEP && tid < EPB) { sm.st_flags[tid] = 0; sm.st_rew[tid] = 0.0; }
     float (*s_obs)[kObsDim] = sm.obs;
     double (*s_pos)[EPB] = sm.pos;
     unsigned long long *s_mask = sm.mask;
@@ -275,25 +278,10 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             sm.safe[le] = (uint8_t)(!(dadd(px, -20.0) < 0.0) && !(dadd(px, 20.0) > d.k.width) && !(dadd(py, -20.0) < 0.0) &&
                                     !(dadd(py, 20.0) > d.k.width) && !(pz < 0.0) && !(pz > d.k.h));
         }
-        if (DO_STEP) {
-            const unsigned full = 0xffffffffu;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                n_stepped += __shfl_xor_sync(full, n_stepped, off);
-                n_ended += __shfl_xor_sync(full, n_ended, off);
-                n_coll += __shfl_xor_sync(full, n_coll, off);
-                n_succ += __shfl_xor_sync(full, n_succ, off);
-                n_lose += __shfl_xor_sync(full, n_lose, off);
-                rew += __shfl_xor_sync(full, rew, off);
-            }
-            if (ln == 0 && n_stepped) {
-                atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
-                if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
-                if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);
-                if (n_succ) atomicAdd(&d.stat_counts[3], (unsigned long long)n_succ);
-                if (n_lose) atomicAdd(&d.stat_counts[4], (unsigned long long)n_lose);
-                atomicAdd(d.stat_reward, rew);
-            }
+        // running statistics: parked per env, reduced by the last warp after the observation tile is out (off the chain)
+        if (DO_STEP && valid) {
+            sm.st_rew[le] = rew;
+            sm.st_flags[le] = (uint8_t)(n_stepped | (n_ended << 1) | (n_coll << 2) | (n_succ << 3) | (n_lose << 4));
         }
     }
     ENV_TRACE(7);
@@ -315,7 +303,31 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
             }
         }
     }
-    if (!obs) return;
+    auto flush_stats = [&]() {
+        if (!DO_STEP || wp != NT / 32 - 1) return;
+        const unsigned full = 0xffffffffu;
+        const int fl = (ln < EPB) ? (int)sm.st_flags[ln] : 0;
+        double rew = (ln < EPB) ? sm.st_rew[ln] : 0.0;
+        int n_stepped = fl & 1, n_ended = (fl >> 1) & 1, n_coll = (fl >> 2) & 1, n_succ = (fl >> 3) & 1, n_lose = (fl >> 4) & 1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            n_stepped += __shfl_xor_sync(full, n_stepped, off);
+            n_ended += __shfl_xor_sync(full, n_ended, off);
+            n_coll += __shfl_xor_sync(full, n_coll, off);
+            n_succ += __shfl_xor_sync(full, n_succ, off);
+            n_lose += __shfl_xor_sync(full, n_lose, off);
+            rew += __shfl_xor_sync(full, rew, off);
+        }
+        if (ln == 0 && n_stepped) {
+            atomicAdd(&d.stat_counts[0], (unsigned long long)n_stepped);
+            if (n_ended) atomicAdd(&d.stat_counts[1], (unsigned long long)n_ended);
+            if (n_coll) atomicAdd(&d.stat_counts[2], (unsigned long long)n_coll);
+            if (n_succ) atomicAdd(&d.stat_counts[3], (unsigned long long)n_succ);
+            if (n_lose) atomicAdd(&d.stat_counts[4], (unsigned long long)n_lose);
+            atomicAdd(d.stat_reward, rew);
+        }
+    };
+    if (!obs) { flush_stats(); return; }
 
     // phase 2: occupancy probes
     for (int idx = tid; idx < EPB * 80; idx += NT) {
@@ -343,6 +355,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)e0 * kObsDim);
     const float4 *src = reinterpret_cast<const float4 *>(&s_obs[0][0]);
     for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+    flush_stats();
     ENV_TRACE(11);
 }
 

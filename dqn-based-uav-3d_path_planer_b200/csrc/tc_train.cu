@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
+            if (l < 4) TR_TRACE(27 + l);
             const float *bias = bias_all + T.bias_off;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
             float vpre[32];                                      // this warp's accumulator chunk, loaded while the lo warps park theirs
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         for (int j = 0; j < 32; ++j) q[j] = vpre[j];
                         stack_add_lo(q, s_lo, row, 0);
                     } else tmem_ld32_sum(taddr, second, q);
+                    TR_TRACE(21);
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     float qa = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (j == act) qa = q[j];
+                    TR_TRACE(22);
                     float gq = 0.f, lterm = 0.f;
                     if (mine) {
                         const float diff = qa - s_y[row];
@@ -420,7 +423,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     // word is a 32-deep compare-and-swap chain: 6 k cycles in the round-2 stage trace) -- and a fixed order
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) lterm += __shfl_xor_sync(0xffffffffu, lterm, off);
+                    TR_TRACE(23);
                     if (lane == 0) atomicAdd(&s_loss, lterm);
+                    TR_TRACE(24);
                     float g[32];
                     const float inv = 1.f / (float)nA;
 #pragma unroll
@@ -430,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         else gj = (j == act) ? gq : 0.f;
                         g[j] = gj;
                     }
+                    TR_TRACE(25);
                     float *dz_row = a.dz_buf + (size_t)gb * tc.dz_stride + T.dz_off;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -441,6 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                         else *reinterpret_cast<float4 *>(Alo + off) = lo4;
                         if (mine) *reinterpret_cast<float4 *>(dz_row + 4 * j) = x;
                     }
+                    TR_TRACE(26);
                 }
             }
             fence_proxy_async();
