@@ -796,6 +796,10 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 48 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 48 * sizeof(long long))); a.trace = tr + 16; }
     UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st,
                              chain && (fused_td ? (l->pdl_prev == kPdlEnv) : (l->pdl_prev == kPdlTd)), tc, a));
+    // experiment (with UAVRL_TC_TRACE): the same launch again, back to back -- the kernel is idempotent, the second run finds
+    // its code in the instruction caches, and the stage trace printed below is the second run's
+    static const bool twice = trace_on && getenv("UAVRL_TRAIN_TWICE") != nullptr;
+    if (twice) UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st, false, tc, a));
     l->pdl_prev = chain ? kPdlTrain : kPdlNone;
     UAVRL_LAUNCHED();
     if (after_chain) UAVRL_CUDA(cudaEventRecord(after_chain, st));
