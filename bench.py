@@ -559,9 +559,16 @@ def run_ours(a):
         if fused:
             for dct in (alg_flops, alg_bytes):
                 dct["act+env_step_fused"] = dct["act_eps_greedy"] + dct["env_step"]
+        td_fused = tc_on and L.td_fused(B)
+        if td_fused:
+            # the TD-target pass(es) run inside the training kernel (uavrl_set_fuse_td): one launch carries both rows' work;
+            # the profile's td_target slot then brackets no launch at all (event overhead only) and is dropped
+            names = tuple("td_target+fwd_bwd" if n_ == "fwd_bwd" else n_ for n_ in names)
+            for dct in (alg_flops, alg_bytes):
+                dct["td_target+fwd_bwd"] = dct["td_target"] + dct["fwd_bwd"]
         kernels = {}
         for n_, t_ in zip(names, kp):
-            if t_ <= 0:
+            if t_ <= 0 or (td_fused and n_ == "td_target"):
                 continue
             kernels[n_] = {"ms": float(t_), "share": float(t_ / kp.sum()), "GBps": alg_bytes[n_] / (t_ * 1e-3) / 1e9,
                            "TFLOPs": alg_flops[n_] / (t_ * 1e-3) / 1e12}

@@ -15,6 +15,7 @@
 //                       critics to the action inputs, through tanh / softplus / the reparameterisation to the actor
 // then reduce_adam_kernel per network and sac_finish_kernel (alpha step, soft target update).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -361,9 +362,20 @@ __global__ void sac_finish_kernel(SacFinishArgs f, const float *__restrict__ sta
         const float a1 = t1[i] * (1.0f - f.tau) + c1[i] * f.tau, a2 = t2[i] * (1.0f - f.tau) + c2[i] * f.tau;
         t1[i] = a1; t2[i] = a2; img_t1[im] = a1; img_t2[im] = a2;
     }
-    if (i == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // the per-CTA loss / entropy partials: lane-strided sums, then a butterfly (one thread walking all of them serially cost
+        // 40 us at 512 partials -- a chain of dependent global loads)
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        for (int c = 0; c < f.nparts; ++c) { s0 += stat[4 * c]; s1 += stat[4 * c + 1]; s2 += stat[4 * c + 2]; s3 += stat[4 * c + 3]; }
+        for (int c = threadIdx.x; c < f.nparts; c += 32) {
+            const float4 t = *reinterpret_cast<const float4 *>(stat + 4 * c);
+            s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+        }
+        if (threadIdx.x != 0) return;
         // alpha_loss = mean((entropy - target_entropy).detach() * exp(log_alpha))  (:372-376), Adam on log_alpha
         const float alpha = expf(scal[0]);
         const float g = (s3 * f.inv_n - f.target_entropy) * alpha;
@@ -422,7 +434,7 @@ struct uavrl_sac {
     int32_t *map_a = nullptr, *map_c = nullptr;
     float *part[3] = { nullptr };                          // gradient partials
     float *stat = nullptr, *scal = nullptr, *out = nullptr, *td = nullptr, *lossbuf = nullptr;
-    int32_t td_cap = 0, max_ctas = 4 * 148;
+    int32_t td_cap = 0, max_ctas = 4 * 148;      // uavrl_sac_create: one CTA per SM (the tile kernels' shared memory admits no more)
     int64_t epoch = 0, adam_t = 0;
     uint64_t calls = 0;
     // lockstep replay ring (continuous actions)
@@ -522,6 +534,14 @@ int uavrl_sac_create(const uavrl_sac_config *cfg, uavrl_sac **out)
     UAVRL_CUDA(cudaSetDevice(cfg->device));
     uavrl_sac *s = new uavrl_sac();
     s->cfg = *cfg;
+    {   // persistent tile kernels: one CTA per SM (143-204 KB of shared memory each), every CTA loops over its tiles and
+        // accumulates ONE gradient partial -- the weight images are staged once per CTA and the optimiser kernels reduce
+        // n_sm partials instead of one per tile (512 at batch 16 384)
+        int n_sm = 0;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) s->max_ctas = n_sm;
+        const char *ov = getenv("UAVRL_SAC_MAX_CTAS");            // tests: force the multi-tile (accumulating) path on a small batch
+        if (ov && atoi(ov) > 0) s->max_ctas = atoi(ov);
+    }
     int rc;
     const int32_t ha[1] = { cfg->hidden }, hc[2] = { cfg->hidden, cfg->hidden };
     if ((rc = build_mlp(cfg->obs_dim, 1, ha, kSacA, kSacA, s->actor))) return rc;              // fc1 -> {fc_mu ; fc_std}
@@ -647,7 +667,8 @@ int uavrl_sac_act(uavrl_sac *s, const float *obs_dev, int32_t n, const float *ep
     BatchSrc none;
     memset(&none, 0, sizeof(none));
     sac_fill_args(s, a, none, n, eps_dev, 0x8000000000000000ull | s->calls++);
-    const int grid = a.n_tiles < s->max_ctas ? a.n_tiles : s->max_ctas;
+    const int act_cap = 4 * s->max_ctas;                       // the actor alone is small: several CTAs per SM
+    const int grid = a.n_tiles < act_cap ? a.n_tiles : act_cap;
     sac_act_kernel<<<grid, kNetThreads, smem_act(s), (cudaStream_t)stream>>>(a, obs_dev, n, actions_dev);
     UAVRL_LAUNCHED();
     return 0;

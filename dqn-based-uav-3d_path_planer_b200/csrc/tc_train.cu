@@ -854,3 +854,4 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
 
 extern "C" int uavrl_set_fuse_dw_adam(int32_t on) { uavrl::g_fuse_dw_adam.store(on ? 1 : 0); return 0; }
 extern "C" int uavrl_set_fuse_td(int32_t on) { uavrl::g_fuse_td.store(on ? 1 : 0); return 0; }
+extern "C" int uavrl_learner_td_fused(const uavrl_learner *l, int32_t batch) { return (l && l->tc_ok && l->use_tc && uavrl::tc_train_can_fuse_td(l, batch)) ? 1 : 0; }

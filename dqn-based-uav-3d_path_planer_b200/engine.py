@@ -402,6 +402,10 @@ class Learner:
         """True = tcgen05 3xTF32 forward passes (default when the net fits), False = fp32 CUDA cores."""
         return bool(_lib.lib().uavrl_learner_set_tensor_cores(self.h, int(bool(enable))))
 
+    def td_fused(self, batch=None):
+        """True when an update of `batch` transitions runs its TD-target pass(es) inside the training kernel."""
+        return bool(_lib.lib().uavrl_learner_td_fused(self.h, int(self.cfg.batch_size if batch is None else batch)))
+
     def lockstep_restart(self):
         check(_lib.lib().uavrl_learner_lockstep_restart(self.h))
 

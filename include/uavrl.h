@@ -375,6 +375,8 @@ int uavrl_set_fuse_dw_adam(int32_t on);
  * (weight images restaged in shared memory between the passes, y kept in shared memory) -- one launch instead of two or
  * three per update; the arithmetic is the stand-alone passes'.  Process-wide switch, default 1. */
 int uavrl_set_fuse_td(int32_t on);
+/* 1 if an update of `batch` transitions on this learner runs the TD-target pass(es) inside the training kernel (see above). */
+int uavrl_learner_td_fused(const uavrl_learner *l, int32_t batch);
 
 #ifdef __cplusplus
 }

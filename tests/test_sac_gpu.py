@@ -57,8 +57,13 @@ def test_sac_update_matches_reference_trainer():
     S.close()
 
 
-def test_sac_ragged_batch_vs_oracle_and_philox_noise():
+@pytest.mark.parametrize("max_ctas", [0, 3])
+def test_sac_ragged_batch_vs_oracle_and_philox_noise(max_ctas, monkeypatch):
+    """max_ctas = 3: 7 tiles on 3 persistent CTAs (3 + 2 + 2 tiles) -- the accumulating multi-tile path every batch above
+    32 x #SMs samples takes (BASELINE configs[4]: 16 384 samples = 512 tiles on 148 CTAs)."""
     from uavrl_b200 import engine
+    if max_ctas:
+        monkeypatch.setenv("UAVRL_SAC_MAX_CTAS", str(max_ctas))
     g = np.load(os.path.join(GOLDEN, "sac_golden.npz"))
     rng = np.random.default_rng(2)
     B = 200                                         # not a multiple of the 32-sample tile
