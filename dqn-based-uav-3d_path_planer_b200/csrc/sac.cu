@@ -434,7 +434,7 @@ struct uavrl_sac {
     int32_t *map_a = nullptr, *map_c = nullptr;
     float *part[3] = { nullptr };                          // gradient partials
     float *stat = nullptr, *scal = nullptr, *out = nullptr, *td = nullptr, *lossbuf = nullptr;
-    int32_t td_cap = 0, max_ctas = 4 * 148;      // uavrl_sac_create: one CTA per SM (the tile kernels' shared memory admits no more)
+    int32_t td_cap = 0, max_ctas = 4 * 148;
     int64_t epoch = 0, adam_t = 0;
     uint64_t calls = 0;
     // lockstep replay ring (continuous actions)
@@ -534,11 +534,9 @@ int uavrl_sac_create(const uavrl_sac_config *cfg, uavrl_sac **out)
     UAVRL_CUDA(cudaSetDevice(cfg->device));
     uavrl_sac *s = new uavrl_sac();
     s->cfg = *cfg;
-    {   // persistent tile kernels: one CTA per SM (143-204 KB of shared memory each), every CTA loops over its tiles and
-        // accumulates ONE gradient partial -- the weight images are staged once per CTA and the optimiser kernels reduce
-        // n_sm partials instead of one per tile (512 at batch 16 384)
-        int n_sm = 0;
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) s->max_ctas = n_sm;
+    {   // grid cap of the tile kernels: 4 CTAs per SM's worth of tiles, i.e. one tile per CTA up to batch 18 944.  (One CTA per
+        // SM looping over its tiles and accumulating ONE partial was measured slower at 16 384 samples -- 721 vs 667 us per
+        // iteration: the read-modify-write of the global partial per tile costs more than the 512-partial reduction saves.)
         const char *ov = getenv("UAVRL_SAC_MAX_CTAS");            // tests: force the multi-tile (accumulating) path on a small batch
         if (ov && atoi(ov) > 0) s->max_ctas = atoi(ov);
     }
@@ -667,8 +665,7 @@ int uavrl_sac_act(uavrl_sac *s, const float *obs_dev, int32_t n, const float *ep
     BatchSrc none;
     memset(&none, 0, sizeof(none));
     sac_fill_args(s, a, none, n, eps_dev, 0x8000000000000000ull | s->calls++);
-    const int act_cap = 4 * s->max_ctas;                       // the actor alone is small: several CTAs per SM
-    const int grid = a.n_tiles < act_cap ? a.n_tiles : act_cap;
+    const int grid = a.n_tiles < s->max_ctas ? a.n_tiles : s->max_ctas;
     sac_act_kernel<<<grid, kNetThreads, smem_act(s), (cudaStream_t)stream>>>(a, obs_dev, n, actions_dev);
     UAVRL_LAUNCHED();
     return 0;

@@ -127,19 +127,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     __shared__ float s_rew[kTcTile], s_done[kTcTile];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols);
-    if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
+    // The last warp is the control warp: it initialises the two mbarriers, issues the weight copies and allocates TMEM while
+    // the other warps already gather the first tile -- nobody needs TMEM or the barriers before the first MMA, so the CTA-wide
+    // barrier that publishes them is the one in front of the first weight wait (800 cycles of allocation off the chain).
+    constexpr int kCtl = kTcThreads - 32;
+    const bool early_w = (a.pdl & kPdlEarlyWeights) != 0;
+    if (tid == kCtl) {
+        mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init();
+        if (early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+    }
+    if (warp == kCtl / 32) { __syncwarp(); tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols); tc_fence_before(); }
+    uint32_t tmem = 0;
     TC_TRACE(1);
     // PDL prologue (common.cuh): the weight image may be fetched before the wait when the predecessor does not write
     // it (TD passes after the env step); the first tile's rows may be gathered before the wait when the predecessor
     // does not write them (act after the optimiser kernel: observations were written two kernels back).
-    const bool early_w = (a.pdl & kPdlEarlyWeights) != 0;
     bool waited = (a.pdl & kPdlEarlyRows) == 0;
-    if (tid == kTcThreads - 32 && early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
     if (waited) {
         pdl_wait();
         pdl_trigger();
@@ -218,7 +221,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             waited = true;
             if (tid == kTcThreads - 32 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
         }
-        if (!wready) { mbar_wait(&wbar, 0); wready = true; }
+        if (!wready) {                                           // first tile: the control warp's barriers and TMEM base become visible
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            tmem = tmem_base_s;
+            mbar_wait(&wbar, 0);
+            wready = true;
+        }
         TC_TRACE(3);
         fence_proxy_async();
         tc_fence_before();
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     TC_TRACE(20);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
+    if (warp == kCtl / 32) { tc_fence_after(); tmem_dealloc(tmem_base_s, (uint32_t)tc.tmem_cols); }
     TC_TRACE(21);
 }
 

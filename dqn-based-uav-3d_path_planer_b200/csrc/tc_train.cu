@@ -153,13 +153,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     __shared__ float s_loss;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols);
-    if (tid == 0) { mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init(); s_loss = 0.f; }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
-    TR_TRACE(1);
+    // control warp (the last one): barrier init, weight copies, TMEM allocation -- concurrently with warp 0 resolving the tile's
+    // samples; the first CTA-wide barrier (behind the sample table) publishes all of it (tc_forward.cu)
+    constexpr int kCtl = kTcThreads - 32;
+    if (tid == 0) s_loss = 0.f;
     const bool fused = a.fused_td != 0;
     const int n_pre = fused ? (a.algo != UAVRL_ALGO_DQN ? 2 : 1) : 0;     // forward-only passes ahead of the training chain
     // PDL.  Unfused: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
@@ -168,11 +165,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     // predecessor's output.  Fused: the predecessor is the env step, which writes the newest frame's rows, rewards and
     // flags -- only the first pass's weight image (optimiser kernel, >= 2 back) is fetched before the wait.
     uint32_t wphase = 0;
-    if (tid == kTcThreads - 32) {                                // (a lane of an otherwise idle warp: thread 0 resolves a sample meanwhile)
+    if (tid == kCtl) {
+        mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init();
         fence_proxy_async();
         if (!fused) bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
         else bulk_g2s_chunked(W, (n_pre == 2) ? a.img : a.img_target, (uint32_t)tc.img_bytes, &wbar);
     }
+    if (warp == kCtl / 32) { __syncwarp(); tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols); tc_fence_before(); }
+    uint32_t tmem = 0;
+    TR_TRACE(1);
     bool waited = false;
     if (fused) { pdl_wait(); pdl_trigger(); waited = true; }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
@@ -200,7 +201,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             rows[tid] = p; s_act[tid] = act;
             if (fused) { rows2[tid] = p2; s_rew[tid] = rw; s_done[tid] = dn; s_astar[tid] = 0; }
         }
-        __syncthreads();
+        tc_fence_before();
+        __syncthreads();                                         // the sample table -- and, first time round, barriers + TMEM base
+        tc_fence_after();
+        tmem = tmem_base_s;
         TR_TRACE(2);
         // the training rows are requested now and consumed after the TD pre-pass (a0_load / a0_store)
         const bool early_rows = n_pre > 0 && R * (tc.L[0].K_pad / 4) <= 4 * kTcThreads;
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     if (tid == 0) a.loss_partials[blockIdx.x] = s_loss;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.tmem_cols);
+    if (warp == kCtl / 32) { tc_fence_after(); tmem_dealloc(tmem_base_s, (uint32_t)tc.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ split-K weight gradients
@@ -584,8 +588,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
     DW_TRACE(0);
-    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride);
-    if (tid == 0) { mbar_init(&mbar, 1); fence_barrier_init(); }
+    // the last warp allocates TMEM and initialises the barrier while warps 0-3 resolve the first chunk's rows (tc_forward.cu)
+    constexpr int kCtl = kTcThreads - 32;
+    if (tid == kCtl) { mbar_init(&mbar, 1); fence_barrier_init(); }
+    if (warp == kCtl / 32) { __syncwarp(); tmem_alloc(&tmem_base_s, (uint32_t)tc.dstride); }
     uint32_t pkey[4];
     Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
     auto resolve_chunk = [&](int c, int buf) {                // row pointers of chunk c (128 samples)
@@ -690,7 +696,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     DW_TRACE(7);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tc.dstride);
+    if (warp == kCtl / 32) { tc_fence_after(); tmem_dealloc(tmem, (uint32_t)tc.dstride); }
     DW_TRACE(8);
     if (!a.fuse_adam) return;
     // ---- fused optimiser tail: grid barrier (every CTA of this launch is resident: grid <= SMs, one CTA per SM), then this
