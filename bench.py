@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--dp-self", type=int, default=0, help="diagnostic, 1 GPU only: run the data-parallel loop (local gradient -> all-reduce + Adam kernel) with world = 1")
     ap.add_argument("--pdl", type=int, default=1, help="1 = programmatic dependent launch inside the loop (default), 0 = fully serialised kernels")
     ap.add_argument("--fuse", type=int, default=0, help="1 = get_action + env step as one kernel on the tensor-core path, 0 = two PDL-chained kernels (default, faster)")
+    ap.add_argument("--fuse-dw", type=int, default=-1, help="1 = optimiser step inside the weight-gradient kernel (uavrl_set_fuse_dw_adam), 0 = separate kernel, -1 = library default")
     ap.add_argument("--per", type=int, default=0, help="1 = prioritised replay (device SumTree equivalent) instead of uniform sampling")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the K-step block is repeated until the timed region is at least this long")
     ap.add_argument("--max-repeats", type=int, default=4000)
@@ -494,6 +495,8 @@ def run_ours(a):
 
     _lib.lib().uavrl_set_pdl(int(a.pdl))
     _lib.lib().uavrl_set_fuse_act_env(int(a.fuse))
+    if a.fuse_dw >= 0:
+        _lib.lib().uavrl_set_fuse_dw_adam(int(a.fuse_dw))
     N, B = a.envs, a.batch
     stream = torch.cuda.current_stream(dev)
 

@@ -142,7 +142,7 @@ struct uavrl_learner {
     void *peer_grad_host[64] = { nullptr }, *peer_flag_host[64] = { nullptr };
     bool comm_ready = false;
     unsigned flag_epoch = 0;
-    unsigned long long *dw_bar = nullptr;      // grid-barrier counter of the fused weight-gradient + optimiser kernel
+    unsigned long long *dw_bar = nullptr;      // fused weight-gradient + optimiser kernel: {epoch : value} partials [slices][P]
     unsigned long long dw_bar_total = 0;
     int last_nparts = 0, last_n_loss_parts = 0;
     int last_global_batch = 0;
@@ -183,6 +183,33 @@ __device__ __forceinline__ uint64_t perm_index(uint64_t i, uint64_t M, const uin
 
 // batch position gb -> the transition's state row, next-state row and metadata
 struct Transition { const float *s, *s2; int a; float r, d, ax, ay; };
+// the two halves of resolve_transition: (1) where the rows are -- index arithmetic only, nothing a predecessor kernel writes is
+// read (an index tape, when present, comes from a kernel that is never a programmatic-launch predecessor); (2) the
+// transition's action / reward / done, which the env step of the same iteration may just have written
+__device__ __forceinline__ int64_t resolve_rows(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4], const float *&s, const float *&s2)
+{
+    if (src.mode == kBatchExplicit) {
+        s = src.frames + (size_t)gb * in_dim; s2 = src.s2_rows + (size_t)gb * in_dim;
+        return gb;
+    }
+    const uint64_t j = src.idx_tape ? (uint64_t)src.idx_tape[gb] : perm_index((uint64_t)gb, (uint64_t)src.count, pkey);
+    int64_t slot, row, row2;
+    if (src.mode == kReplayLockstep) {
+        const int64_t f = src.idx_is_slot ? (int64_t)(j / src.n_envs) : (src.oldest + (int64_t)(j / src.n_envs)) % src.cap;
+        const int64_t e = (int64_t)(j % src.n_envs);
+        slot = f * src.n_envs + e; row = slot;
+        row2 = ((f + 1) % src.cap) * src.n_envs + e;
+    } else {
+        slot = src.idx_is_slot ? (int64_t)j : (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+    }
+    s = src.frames + (size_t)row * in_dim; s2 = src.frames + (size_t)row2 * in_dim;
+    return slot;
+}
+__device__ __forceinline__ void load_meta(const BatchSrc &src, int64_t slot, int &a, float &r, float &d)
+{
+    a = src.act ? src.act[slot] : 0; r = src.rew[slot];
+    d = (src.mode == kBatchExplicit) ? src.done_f32[slot] : (src.done_u8[slot] ? 1.f : 0.f);
+}
 __device__ __forceinline__ Transition resolve_transition(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4])
 {
     Transition t;

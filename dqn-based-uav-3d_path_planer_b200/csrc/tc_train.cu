@@ -56,10 +56,11 @@ struct TcDwArgs {
     const float *act_buf, *dz_buf;
     float *partials;                   // [n_slices][P]
     long long *trace;                  // debug (UAVRL_TC_TRACE): CTA 0 / thread 0 stage timestamps
-    // fused optimiser tail (fuse_adam = 1, only when every CTA of the grid is resident at once)
+    // fused optimiser tail (fuse_adam = 1, only when every CTA of the grid is resident at once): the partials travel as 8-byte
+    // words {epoch : value} (part64 [n_slices][P]); a reader polls the word itself -- no grid barrier, no fence, no flag
     int32_t fuse_adam;
-    unsigned long long *bar_count;     // monotonic arrival counter of the grid barrier
-    unsigned long long bar_target;     // value the counter reaches when every CTA of THIS launch has arrived
+    unsigned long long *part64;
+    uint32_t ll_epoch;                 // this launch's tag (never 0: the buffer starts zeroed)
     AdamArgs adam;
     AdamPtrs ptrs;
 };
@@ -175,7 +176,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     uint32_t tmem = 0;
     TR_TRACE(1);
     bool waited = false;
-    if (fused) { pdl_wait(); pdl_trigger(); waited = true; }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     uint32_t pkey[4];
@@ -191,20 +191,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int base = tile * R;
+        // where the tile's rows are: index arithmetic only (resolve_rows), so with the fused TD pass it runs BEFORE the wait for
+        // the env step; the transitions' action / reward / done are requested right after the wait and parked in shared memory
+        // once the first gather has been issued (they are first read in a head epilogue)
+        int64_t my_slot = -1;
         if (tid < R) {
             const int b = base + tid;
-            const float *p = nullptr, *p2 = nullptr; int act = 0; float rw = 0.f, dn = 0.f;
-            if (b < a.B) {
-                const Transition t = resolve_transition(a.src, b, tc.in_dim, pkey);
-                p = t.s; act = t.a; p2 = t.s2; rw = t.r; dn = t.d;
-            }
-            rows[tid] = p; s_act[tid] = act;
-            if (fused) { rows2[tid] = p2; s_rew[tid] = rw; s_done[tid] = dn; s_astar[tid] = 0; }
+            const float *p = nullptr, *p2 = nullptr;
+            if (b < a.B) my_slot = resolve_rows(a.src, b, tc.in_dim, pkey, p, p2);
+            rows[tid] = p;
+            if (fused) { rows2[tid] = p2; s_astar[tid] = 0; }
         }
         tc_fence_before();
         __syncthreads();                                         // the sample table -- and, first time round, barriers + TMEM base
         tc_fence_after();
         tmem = tmem_base_s;
+        if (fused && !waited) { pdl_wait(); pdl_trigger(); waited = true; }
+        int m_act = 0; float m_rew = 0.f, m_done = 0.f;
+        if (my_slot >= 0) load_meta(a.src, my_slot, m_act, m_rew, m_done);
+        auto park_meta = [&]() { if (tid < R) { s_act[tid] = m_act; if (fused) { s_rew[tid] = m_rew; s_done[tid] = m_done; } } };
         TR_TRACE(2);
         // the training rows are requested now and consumed after the TD pre-pass (a0_load / a0_store)
         const bool early_rows = n_pre > 0 && R * (tc.L[0].K_pad / 4) <= 4 * kTcThreads;
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                 bulk_g2s_chunked(W, a.img_target, (uint32_t)tc.img_bytes, &wbar);
             }
             build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
-            if (pass == 0) TR_TRACE(3);
+            if (pass == 0) { park_meta(); TR_TRACE(3); }
             mbar_wait(&wbar, wphase); wphase ^= 1;
             fence_proxy_async();
             tc_fence_before();
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         else build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
         TR_TRACE(9);
         if (!waited) { pdl_wait(); pdl_trigger(); waited = true; }
+        if (n_pre == 0) park_meta();
         if (!fused && tid < R) s_y[tid] = (base + tid < a.B) ? a.y[base + tid] : 0.f;      // visible after the barrier below
         if (fused) { mbar_wait(&wbar, wphase); wphase ^= 1; }
         else if (!wready) { mbar_wait(&wbar, 0); wready = true; }
@@ -669,27 +675,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     DW_TRACE(6);
     // epilogue: accumulator row f = input feature (or the ones column), column o = output unit.  Lanes hold consecutive f:
     // every store instruction writes 32 consecutive floats of one weight row.
+    // Partial slice `chunk`: plain floats for the separate optimiser kernel, or 8-byte words {epoch : value} for the fused tail.
+    // Lanes hold consecutive f, so every store instruction writes 32 consecutive elements of one weight row; the 32 columns of a
+    // thread walk the rows with a pointer increment and a predicate each (the address arithmetic used to dominate this epilogue).
     float *part = a.partials + (size_t)chunk * a.P;
+    unsigned long long *part64 = a.fuse_adam ? a.part64 + (size_t)chunk * a.P : nullptr;
+    const unsigned long long tag = (unsigned long long)a.ll_epoch << 32;
     const int f = quad * 32 + lane;
     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
         if (quad * 32 >= rowsA) break;
         float v[32];
         tmem_ld32_sum(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, tc.concat ? (uint32_t)T.N_pad : 0u, v);
-        if (f < T.K_real) {
-            float *wrow = part + T.w_off + f;                                            // + o * K_real
-            float *vrow = part + (T.w2_off >= 0 ? T.w2_off : 0) + f - T.out_main * T.K_real;  // dueling value head rows
+        const int n_main = min(max(T.out_main - c0, 0), 32), n_all = min(max(T.N_real - c0, 0), 32);   // columns [0, n_main): main block, [n_main, n_all): value head
+        if (f > T.K_real) continue;
+        const bool brow = (f == T.K_real);                       // the ones column: bias gradients (stride 1), else weight row f (stride K_real)
+        const int stride = brow ? 1 : T.K_real;
+        const int i_main = brow ? T.b_off + c0 : T.w_off + f + c0 * T.K_real;
+        const int i_val = brow ? T.b2_off + (c0 - T.out_main) : (T.w2_off >= 0 ? T.w2_off : 0) + f + (c0 - T.out_main) * T.K_real;
+        if (part64) {
+            unsigned long long *p = part64 + i_main;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int o = c0 + j;                                                    // warp-uniform
-                if (o < T.out_main) wrow[o * T.K_real] = v[j];
-                else if (o < T.N_real) vrow[o * T.K_real] = v[j];
+                if (j < n_main) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(tag | __float_as_uint(v[j])) : "memory");
+                p += stride;
             }
-        } else if (f == T.K_real) {                                                      // the ones column: bias gradients
+            if (n_all > n_main) {
+                unsigned long long *q = part64 + i_val;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= n_main && j < n_all) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(q), "l"(tag | __float_as_uint(v[j])) : "memory");
+                    q += stride;
+                }
+            }
+        } else {
+            float *p = part + i_main;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int o = c0 + j;
-                if (o < T.out_main) part[T.b_off + o] = v[j];
-                else if (o < T.N_real) part[T.b2_off + (o - T.out_main)] = v[j];
+                if (j < n_main) *p = v[j];
+                p += stride;
+            }
+            if (n_all > n_main) {
+                float *q = part + i_val;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= n_main && j < n_all) *q = v[j];
+                    q += stride;
+                }
             }
         }
     }
@@ -699,20 +730,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     if (warp == kCtl / 32) { tc_fence_after(); tmem_dealloc(tmem, (uint32_t)tc.dstride); }
     DW_TRACE(8);
     if (!a.fuse_adam) return;
-    // ---- fused optimiser tail: grid barrier (every CTA of this launch is resident: grid <= SMs, one CTA per SM), then this
-    // CTA reduces its slice of the parameter vector over all partials in reduce_adam_kernel's order and applies Adam
-    if (tid == 0) {
-        __threadfence();                                       // this CTA's partial slice is visible device-wide
-        atomicAdd(a.bar_count, 1ull);
-        while (*reinterpret_cast<volatile unsigned long long *>(a.bar_count) < a.bar_target) { }
-        __threadfence();
-    }
-    __syncthreads();
+    // ---- fused optimiser tail: this CTA reduces its slice of the parameter vector over all partials in reduce_adam_kernel's
+    // order and applies Adam.  Every word it needs is polled until it carries this launch's epoch (all CTAs are resident: grid
+    // <= SMs, one CTA per SM, and each writes its partial before it polls) -- nothing to fence, no barrier to wait at.
     const int per = (a.P + (int)gridDim.x - 1) / (int)gridDim.x;
     const int i_end = min(a.P, ((int)blockIdx.x + 1) * per);
     for (int i = (int)blockIdx.x * per + tid; i < i_end; i += kTcThreads) {
-        const float *pp = a.ptrs.partials;
-        // __ldcg: the partials were written by other SMs in this same launch (L1 holds nothing of them, but be explicit)
+        const unsigned long long *pp = a.part64 + i;
+        const uint32_t ep = a.ll_epoch;
+        auto poll = [ep](const unsigned long long *q) {
+            unsigned long long w;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(q) : "memory");
+            return w;
+        };
         float g4[4];
 #pragma unroll
         for (int cg = 0; cg < 4; ++cg) {
@@ -721,10 +751,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
             for (int u = 0; u < 8; ++u) acc[u] = 0.f;
             int c = cg;
             for (; c + 28 < a.adam.nparts; c += 32) {
+                unsigned long long w[8];
+                bool ok;
+                do {
+                    ok = true;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] += __ldcg(pp + (size_t)(c + 4 * u) * a.P + i);
+                    for (int u = 0; u < 8; ++u) w[u] = poll(pp + (size_t)(c + 4 * u) * a.P);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ok = ok && (uint32_t)(w[u] >> 32) == ep;
+                } while (!ok);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += __uint_as_float((uint32_t)w[u]);
             }
-            for (; c < a.adam.nparts; c += 4) acc[0] += __ldcg(pp + (size_t)c * a.P + i);
+            for (; c < a.adam.nparts; c += 4) {
+                unsigned long long w;
+                do { w = poll(pp + (size_t)c * a.P); } while ((uint32_t)(w >> 32) != ep);
+                acc[0] += __uint_as_float((uint32_t)w);
+            }
             g4[cg] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
         }
         const float g = (g4[0] + g4[1]) + (g4[2] + g4[3]);
@@ -824,9 +867,15 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     const bool fuse = adam != nullptr && g_fuse_dw_adam.load() && dw_grid <= n_sm;
     if (adam_done) *adam_done = fuse;
     if (fuse) {
-        if (!l->dw_bar) { UAVRL_CUDA(cudaMalloc((void **)&l->dw_bar, 8)); UAVRL_CUDA(cudaMemsetAsync(l->dw_bar, 0, 8, st)); l->dw_bar_total = 0; }
-        l->dw_bar_total += (unsigned long long)dw_grid;
-        d.fuse_adam = 1; d.bar_count = l->dw_bar; d.bar_target = l->dw_bar_total;
+        if (!l->dw_bar) {                                        // the {epoch : value} partial buffer [max_slices][P], zeroed once
+            const size_t n = (size_t)max_slices * (size_t)l->net.P * sizeof(unsigned long long);
+            UAVRL_CUDA(cudaMalloc((void **)&l->dw_bar, n));
+            UAVRL_CUDA(cudaMemsetAsync(l->dw_bar, 0, n, st));
+            l->dw_bar_total = 0;
+        }
+        l->dw_bar_total += 1;
+        if ((uint32_t)l->dw_bar_total == 0u) l->dw_bar_total += 1;     // tag 0 = "never written"
+        d.fuse_adam = 1; d.part64 = l->dw_bar; d.ll_epoch = (uint32_t)l->dw_bar_total;
         d.adam = *adam; d.adam.nparts = d.n_slices; d.adam.n_loss_parts = grid;
         AdamPtrs &q = d.ptrs;
         q.partials = l->partials; q.loss_partials = l->loss_partials; q.grad = l->grad; q.local = l->local; q.m = l->m; q.v = l->v;
