@@ -284,6 +284,13 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
+    AdamPtrs q;
+    q.partials = partials; q.loss_partials = loss_partials; q.grad = grad; q.local = local; q.m = m; q.v = v; q.target = target;
+    q.img_local = img_local; q.img_target = img_target; q.img_map = img_map; q.tc_local = tc_local; q.tc_target = tc_target;
+    q.tc_hi = tc_hi; q.tc_lo = tc_lo; q.tc_hi2 = tc_hi2; q.tc_lo2 = tc_lo2; q.loss_out = loss_out;
+    const bool mine = cg == 0 && i < a.P && a.apply;
+    AdamPre pre;
+    if (mine) pre = adam_prefetch(q, i);                 // moments, parameter, image indices: not the predecessor's output
     pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
     pdl_trigger();
     float g = 0.f;
@@ -297,13 +304,7 @@ reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *
         } else {
             g = grad[i];                                  // already reduced (and all-reduced) by the caller
         }
-        if (a.apply) {
-            AdamPtrs q;
-            q.partials = partials; q.loss_partials = loss_partials; q.grad = grad; q.local = local; q.m = m; q.v = v; q.target = target;
-            q.img_local = img_local; q.img_target = img_target; q.img_map = img_map; q.tc_local = tc_local; q.tc_target = tc_target;
-            q.tc_hi = tc_hi; q.tc_lo = tc_lo; q.tc_hi2 = tc_hi2; q.tc_lo2 = tc_lo2; q.loss_out = loss_out;
-            adam_update_one(a, q, i, g);
-        }
+        if (mine) adam_update_pre(a, q, i, g, pre);
     }
     if (blockIdx.x == 0 && threadIdx.x >= 224 && loss_out && a.nparts > 0) {     // last warp: loss = sum / B
         const int lane = threadIdx.x & 31;
@@ -483,6 +484,8 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
     __shared__ float red[4][64];
     const int ix = threadIdx.x & 63, cg = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + ix;
+    AdamPre pre;
+    if (cg == 0 && i < a.P) pre = adam_prefetch(q, i);   // before the wait: nothing here is the predecessor's output
     pdl_wait();                 // PDL (common.cuh): the gradient partials come from the predecessor
     pdl_trigger();
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) t0 = now();
@@ -512,7 +515,7 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
         const float gsum = ll_gather_sum(recv + i, stride, a.world, epoch);
         if (trace && blockIdx.x == 0 && threadIdx.x == 0) t3 = now();
         q.grad[i] = gsum;
-        adam_update_one(a, q, i, gsum);
+        adam_update_pre(a, q, i, gsum, pre);
     }
     if (blockIdx.x == 0 && threadIdx.x == 255 && q.loss_out) *q.loss_out = ll_gather_sum(recv + a.P, stride, a.world, epoch);
     if (trace && blockIdx.x == 0) {

@@ -186,8 +186,12 @@ struct Transition { const float *s, *s2; int a; float r, d, ax, ay; };
 // the two halves of resolve_transition: (1) where the rows are -- index arithmetic only, nothing a predecessor kernel writes is
 // read (an index tape, when present, comes from a kernel that is never a programmatic-launch predecessor); (2) the
 // transition's action / reward / done, which the env step of the same iteration may just have written
-__device__ __forceinline__ int64_t resolve_rows(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4], const float *&s, const float *&s2)
+// fresh: the next-state row lies in the frame the env step of the SAME iteration writes (lockstep ring: the frame behind the
+// newest transition group) -- the only sampled row a kernel launched programmatically behind that env step must not read early
+__device__ __forceinline__ int64_t resolve_rows(const BatchSrc &src, int gb, int in_dim, const uint32_t pkey[4], const float *&s, const float *&s2,
+                                                bool *fresh = nullptr)
 {
+    if (fresh) *fresh = false;
     if (src.mode == kBatchExplicit) {
         s = src.frames + (size_t)gb * in_dim; s2 = src.s2_rows + (size_t)gb * in_dim;
         return gb;
@@ -199,6 +203,7 @@ __device__ __forceinline__ int64_t resolve_rows(const BatchSrc &src, int gb, int
         const int64_t e = (int64_t)(j % src.n_envs);
         slot = f * src.n_envs + e; row = slot;
         row2 = ((f + 1) % src.cap) * src.n_envs + e;
+        if (fresh) *fresh = ((f + 1) % src.cap) == (src.oldest + src.count / src.n_envs) % src.cap;
     } else {
         slot = src.idx_is_slot ? (int64_t)j : (src.oldest + (int64_t)j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
     }
@@ -280,26 +285,37 @@ __device__ __forceinline__ void tf32_split_f(float x, float &hi, float &lo)
 
 // torch.optim.Adam single-tensor step for parameter i with gradient g (lerp, mul/addcmul, sqrt/div/add, addcdiv), the hard
 // target update (DuelingDQN_Trainer.py:199-202) and the refresh of the fp32 and tensor-core weight images
-__device__ __forceinline__ void adam_update_one(const AdamArgs &a, const AdamPtrs &q, int i, float g)
+// what the step reads besides the gradient: nothing a gradient-producing predecessor writes, so an optimiser kernel launched
+// programmatically behind one fetches it BEFORE griddepcontrol.wait (one memory round trip off the post-wait chain)
+struct AdamPre { float m, v, p; int im, ih, il, ih2, il2; };
+__device__ __forceinline__ AdamPre adam_prefetch(const AdamPtrs &q, int i)
+{
+    AdamPre r;
+    r.m = q.m[i]; r.v = q.v[i]; r.p = q.local[i]; r.im = q.img_map[i];
+    r.ih = r.il = r.ih2 = r.il2 = -1;
+    if (q.tc_local) { r.ih = q.tc_hi[i]; r.il = q.tc_lo[i]; r.ih2 = q.tc_hi2[i]; r.il2 = q.tc_lo2[i]; }
+    return r;
+}
+__device__ __forceinline__ void adam_update_pre(const AdamArgs &a, const AdamPtrs &q, int i, float g, const AdamPre &pre)
 {
     // every operation individually rounded (no FMA contraction): the optimiser kernels that share this function (stand-alone,
     // fused behind the weight-gradient kernel, all-reduce) then produce bit-identical parameters by construction
-    float mi = q.m[i], vi = q.v[i], p = q.local[i];
+    float mi = pre.m, vi = pre.v, p = pre.p;
     mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(g, mi), a.beta1_c));                                  // exp_avg.lerp_(grad, 1 - beta1)
     vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.beta2_c, g), g));               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
     const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), a.bc2_sqrt), a.eps);                 // (sqrt(v) / sqrt(bc2)).add_(eps)
     p = __fsub_rn(p, __fmul_rn(a.step_size, __fdiv_rn(mi, denom)));                              // param.addcdiv_(m, denom, -step_size)
     q.m[i] = mi; q.v[i] = vi; q.local[i] = p;
-    const int im = q.img_map[i];
+    const int im = pre.im;
     q.img_local[im] = p;
     if (a.hard) { q.target[i] = p; q.img_target[im] = p; }
     if (q.tc_local) {                                        // tensor-core images: TF32 hi/lo split of the new value
-        const int ih = q.tc_hi[i], il = q.tc_lo[i];
+        const int ih = pre.ih, il = pre.il;
         float hi = p, lo = 0.f;
         if (il >= 0) tf32_split_f(p, hi, lo);
         q.tc_local[ih] = hi;
         if (il >= 0) q.tc_local[il] = lo;
-        const int ih2 = q.tc_hi2[i], il2 = q.tc_lo2[i];
+        const int ih2 = pre.ih2, il2 = pre.il2;
         if (ih2 >= 0) { q.tc_local[ih2] = hi; q.tc_local[il2] = lo; }
         if (a.hard) {
             q.tc_target[ih] = hi;
@@ -307,6 +323,11 @@ __device__ __forceinline__ void adam_update_one(const AdamArgs &a, const AdamPtr
             if (ih2 >= 0) { q.tc_target[ih2] = hi; q.tc_target[il2] = lo; }
         }
     }
+}
+
+__device__ __forceinline__ void adam_update_one(const AdamArgs &a, const AdamPtrs &q, int i, float g)
+{
+    adam_update_pre(a, q, i, g, adam_prefetch(q, i));
 }
 
 __global__ void reduce_adam_kernel(AdamArgs a, const float *__restrict__ partials, const float *__restrict__ loss_partials,

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     TC_TRACE(0);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *Ahi = smem, *Alo = smem + tc.a_bytes, *W = smem + 2 * tc.a_bytes;
-    __shared__ uint64_t wbar, mbar;
+    __shared__ uint64_t wbar, wbar2, mbar;                   // weights of layer 0 | every other layer + the biases | MMA completion
     __shared__ uint32_t tmem_base_s;
     __shared__ const float *rows[kTcTile];
     __shared__ float s_rew[kTcTile], s_done[kTcTile];
@@ -132,9 +132,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     // barrier that publishes them is the one in front of the first weight wait (800 cycles of allocation off the chain).
     constexpr int kCtl = kTcThreads - 32;
     const bool early_w = (a.pdl & kPdlEarlyWeights) != 0;
+    // The image travels in two pieces: layer 0's hi|lo block first (all the first MMA needs), the other layers and the biases
+    // behind it on a second barrier that is first waited for in layer 0's epilogue -- when the image can only be requested
+    // after the dependent-launch wait (act after the optimiser step) half of its latency is covered by the first layer.
+    const uint32_t w_split = tc.n_layers > 1 ? (uint32_t)tc.L[1].hi_off : (uint32_t)tc.img_bytes;
+    auto stage_image = [&]() {
+        fence_proxy_async();
+        bulk_g2s_chunked(W, a.img, w_split, &wbar);
+        if (w_split < (uint32_t)tc.img_bytes) bulk_g2s_chunked(W + w_split, a.img + w_split, (uint32_t)tc.img_bytes - w_split, &wbar2);
+    };
     if (tid == kCtl) {
-        mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init();
-        if (early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+        mbar_init(&wbar, 1); mbar_init(&wbar2, 1); mbar_init(&mbar, 1); fence_barrier_init();
+        if (early_w) stage_image();
     }
     if (warp == kCtl / 32) { __syncwarp(); tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols); tc_fence_before(); }
     uint32_t tmem = 0;
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     if (waited) {
         pdl_wait();
         pdl_trigger();
-        if (tid == kTcThreads - 32 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+        if (tid == kCtl && !early_w) stage_image();
     }
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     uint32_t pkey[4] = {0u, 0u, 0u, 0u};
     if (!direct) Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
     uint32_t mphase = 0;
-    bool wready = false;
+    bool wready = false, w2ready = false;
 
     // R = real rows per tile (32 / 64 / 128).  The MMA is always M = 128; accumulator rows >= R hold garbage
     // computed from whatever SMEM follows the R-row operand (still inside this CTA's allocation) and are
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             pdl_wait();
             pdl_trigger();
             waited = true;
-            if (tid == kTcThreads - 32 && !early_w) { fence_proxy_async(); bulk_g2s_chunked(W, a.img, (uint32_t)tc.img_bytes, &wbar); }
+            if (tid == kCtl && !early_w) stage_image();
         }
         if (!wready) {                                           // first tile: the control warp's barriers and TMEM base become visible
             tc_fence_before();
@@ -254,6 +263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
+            if (!w2ready) { if (w_split < (uint32_t)tc.img_bytes) mbar_wait(&wbar2, 0); w2ready = true; }   // biases + the next layers' weights
             TC_TRACE(6 + 3 * l);
             const float *bias = bias_all + T.bias_off;
             const int row = quad * 32 + lane;

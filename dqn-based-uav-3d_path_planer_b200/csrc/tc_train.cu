@@ -115,6 +115,22 @@ __device__ __forceinline__ void a0_load(const float *const *rows, int R, int in_
         v[u] = (rp && 4 * j < in_dim) ? __ldg(reinterpret_cast<const float4 *>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
+// want_fresh = false: every row NOT flagged in fresh[] (everything else zero) -- may run before the dependent-launch wait;
+// want_fresh = true: only the flagged rows, read from L2 (the env step of this iteration has just written them), into the
+// same registers.
+__device__ __forceinline__ void a0_load_sel(const float *const *rows, const uint8_t *fresh, bool want_fresh, int R, int in_dim, int K0, float4 (&v)[4])
+{
+    const int total = R * (K0 / 4), lgR = 31 - __clz(R);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * kTcThreads;
+        const int r = i & (R - 1), j = i >> lgR;
+        const float *rp = (i < total) ? rows[r] : nullptr;
+        const bool take = rp && 4 * j < in_dim && ((fresh[r] != 0) == want_fresh);
+        if (!want_fresh) v[u] = take ? __ldg(reinterpret_cast<const float4 *>(rp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (take) v[u] = __ldcg(reinterpret_cast<const float4 *>(rp) + j);
+    }
+}
 __device__ __forceinline__ void a0_store(const float4 (&v)[4], int R, int K0, unsigned char *Ahi, unsigned char *Alo, bool stack)
 {
     const int total = R * (K0 / 4), lgR = 31 - __clz(R);
@@ -134,6 +150,8 @@ __device__ __forceinline__ void a0_store(const float4 (&v)[4], int R, int K0, un
     }
 }
 
+__device__ __forceinline__ uint32_t nl_split(const TcNet &tc) { return tc.n_layers > 1 ? (uint32_t)tc.L[1].hi_off : (uint32_t)tc.img_bytes; }
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
 {
     TR_TRACE(0);
@@ -145,11 +163,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     // into the Alo buffer); the lo*hi accumulator block reaches the epilogue warps through a scratch behind the weight image
     const bool stack = tc.concat != 0 && tc.dstride <= 128;          // (layers up to 64 wide: tc_train_init admits no others)
     float *s_lo = reinterpret_cast<float *>(W + tc.train_img_bytes);
-    __shared__ uint64_t wbar, mbar;
+    __shared__ uint64_t wbar, wbar2, wbar3, mbar;           // fused TD: training image in three pieces (below)
     __shared__ uint32_t tmem_base_s;
     __shared__ const float *rows[kTcTile];
     __shared__ const float *rows2[kTcTile];                  // fused TD: next-state rows
     __shared__ int s_act[kTcTile], s_astar[kTcTile];
+    __shared__ uint8_t s_fresh[kTcTile];                     // fused TD: the next-state row is being written by this iteration's env step
     __shared__ float s_y[kTcTile], s_rew[kTcTile], s_done[kTcTile];
     __shared__ float s_loss;
 
@@ -167,11 +186,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     // flags -- only the first pass's weight image (optimiser kernel, >= 2 back) is fetched before the wait.
     uint32_t wphase = 0;
     if (tid == kCtl) {
-        mbar_init(&wbar, 1); mbar_init(&mbar, 1); fence_barrier_init();
+        mbar_init(&wbar, 1); mbar_init(&wbar2, 1); mbar_init(&wbar3, 1); mbar_init(&mbar, 1); fence_barrier_init();
         fence_proxy_async();
         if (!fused) bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
-        else bulk_g2s_chunked(W, (n_pre == 2) ? a.img : a.img_target, (uint32_t)tc.img_bytes, &wbar);
+        else {
+            bulk_g2s_chunked(W, (n_pre == 2) ? a.img : a.img_target, (uint32_t)tc.img_bytes, &wbar);
+            // the transposed blocks of the training image (dX chain) lie behind the forward image the TD passes use: they are
+            // fetched now (written by the optimiser step, >= 2 kernels back) and first waited for in front of the dX chain
+            if (tc.train_img_bytes > tc.img_bytes)
+                bulk_g2s_chunked(W + tc.img_bytes, a.img + tc.img_bytes, (uint32_t)(tc.train_img_bytes - tc.img_bytes), &wbar3);
+        }
     }
+    // fused: after the TD passes the forward part of the training image comes in two pieces -- layer 0's block on wbar (all the
+    // first MMA needs), the other layers + biases on wbar2 (first waited for in layer 0's epilogue)
+    const uint32_t w_split = nl_split(tc);
     if (warp == kCtl / 32) { __syncwarp(); tmem_alloc(&tmem_base_s, (uint32_t)tc.tmem_cols); tc_fence_before(); }
     uint32_t tmem = 0;
     TR_TRACE(1);
@@ -198,30 +226,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         if (tid < R) {
             const int b = base + tid;
             const float *p = nullptr, *p2 = nullptr;
-            if (b < a.B) my_slot = resolve_rows(a.src, b, tc.in_dim, pkey, p, p2);
+            bool fr = false;
+            if (b < a.B) my_slot = resolve_rows(a.src, b, tc.in_dim, pkey, p, p2, &fr);
             rows[tid] = p;
-            if (fused) { rows2[tid] = p2; s_astar[tid] = 0; }
+            if (fused) { rows2[tid] = p2; s_astar[tid] = 0; s_fresh[tid] = fr ? 1 : 0; }
         }
         tc_fence_before();
         __syncthreads();                                         // the sample table -- and, first time round, barriers + TMEM base
         tc_fence_after();
         tmem = tmem_base_s;
+        // Fused TD (one tile per CTA, at most 4 items per thread): BOTH gathers are requested before the wait for the env step --
+        // the training rows (never younger than the previous iteration) and every next-state row outside the frame that env step
+        // is writing (all but ~N/count of them); the few fresh ones follow after the wait from L2.  The HBM latency of the
+        // sampled rows is then hidden behind the predecessor instead of heading this kernel's chain.
+        const bool early_rows = n_pre > 0 && R * (tc.L[0].K_pad / 4) <= 4 * kTcThreads;
+        float4 vmain[4], vnext[4];
+        if (early_rows) {
+            a0_load_sel(rows2, s_fresh, false, R, tc.in_dim, tc.L[0].K_pad, vnext);
+            a0_load(rows, R, tc.in_dim, tc.L[0].K_pad, vmain);
+        }
         if (fused && !waited) { pdl_wait(); pdl_trigger(); waited = true; }
         int m_act = 0; float m_rew = 0.f, m_done = 0.f;
         if (my_slot >= 0) load_meta(a.src, my_slot, m_act, m_rew, m_done);
+        if (early_rows) a0_load_sel(rows2, s_fresh, true, R, tc.in_dim, tc.L[0].K_pad, vnext);
         auto park_meta = [&]() { if (tid < R) { s_act[tid] = m_act; if (fused) { s_rew[tid] = m_rew; s_done[tid] = m_done; } } };
         TR_TRACE(2);
-        // the training rows are requested now and consumed after the TD pre-pass (a0_load / a0_store)
-        const bool early_rows = n_pre > 0 && R * (tc.L[0].K_pad / 4) <= 4 * kTcThreads;
-        float4 vmain[4];
-        if (early_rows) a0_load(rows, R, tc.in_dim, tc.L[0].K_pad, vmain);
         // ---------------- fused TD target: forward-only pass(es) on the next states (tc_forward.cu's chain and head)
         for (int pass = 0; pass < n_pre; ++pass) {
             if (pass > 0 && tid == kTcThreads - 32) {                          // the target image replaces the local one (all its readers are done)
                 fence_proxy_async();
                 bulk_g2s_chunked(W, a.img_target, (uint32_t)tc.img_bytes, &wbar);
             }
-            build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
+            if (pass == 0 && early_rows) a0_store(vnext, R, tc.L[0].K_pad, Ahi, Alo, stack);
+            else build_a0(rows2, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
             if (pass == 0) { park_meta(); TR_TRACE(3); }
             mbar_wait(&wbar, wphase); wphase ^= 1;
             fence_proxy_async();
@@ -317,7 +354,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
         }
         if (fused && tid == kTcThreads - 32) {                                  // the training image (every reader of the TD image is done)
             fence_proxy_async();
-            bulk_g2s_chunked(W, a.img, (uint32_t)tc.train_img_bytes, &wbar);
+            bulk_g2s_chunked(W, a.img, w_split, &wbar);
+            if (w_split < (uint32_t)tc.img_bytes) bulk_g2s_chunked(W + w_split, a.img + w_split, (uint32_t)tc.img_bytes - w_split, &wbar2);
         }
         if (early_rows) a0_store(vmain, R, tc.L[0].K_pad, Ahi, Alo, stack);
         else build_a0(rows, R, tc.in_dim, tc.L[0].K_pad, Ahi, Alo, stack);
@@ -351,6 +389,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             mbar_wait(&mbar, mphase);
             mphase ^= 1;
             tc_fence_after();
+            if (fused && l == 0 && w_split < (uint32_t)tc.img_bytes) mbar_wait(&wbar2, 0);     // biases + the later layers' weights
             if (l < 4) TR_TRACE(27 + l);
             const float *bias = bias_all + T.bias_off;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + dcol;
@@ -467,6 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
             TR_TRACE(11 + l);
         }
 
+        if (fused && tc.train_img_bytes > tc.img_bytes) mbar_wait(&wbar3, 0);                     // transposed blocks (requested at kernel start)
         // ---------------- dX chain: dZ_{l-1} = (dZ_l * W_l) .* (H_l > 0), l = nl-1 .. 1
         for (int l = nl - 1; l >= 1; --l) {
             const TcLayer T = tc.L[l];
