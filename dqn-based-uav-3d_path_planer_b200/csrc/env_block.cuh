@@ -136,6 +136,9 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     const int e = e0 + le;
     const bool valid = (wp < NW1) && (ln < LPW) && (e < d.n);
     EnvRegs s;
+    StepOut o;                                               // phase 1's outputs, written back behind the phase-1 barrier
+    o.reward = 0.0; o.done_ret = 0; o.info = 0; o.coll = 0;
+    uint8_t ended_flag = 0;
     int scen = 0;
     P3 sgc[3];                                               // sub-goal queue entries cursor, cursor + 1, cursor + 2 (prefetched)
     s.px = 0.0; s.py = 0.0;
@@ -196,7 +199,6 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 auto threat = [&kk, cyl, mask](double x, double y, double z) {
                     return threat_masked(kk, cyl, mask, x, y, z);
                 };
-                StepOut o;
                 if (apf_on) {
                     ApfDev apf; apf.ob = d.apf_obs; apf.n = d.k.n_cyl;
                     step_core_apf(d.k, s, mode, act, sub, threat, apf, o);
@@ -225,12 +227,7 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                 rew = o.reward;
                 n_stepped = 1; n_coll = o.coll; n_ended = s.done;
                 n_succ = (o.info == 1); n_lose = (o.info == 2);
-                if (reward) reward[e] = (float)o.reward;
-                d.rew64[e] = o.reward;
-                if (done_out) done_out[e] = (uint8_t)o.done_ret;
-                if (info_out) info_out[e] = (uint8_t)o.info;
-                if (coll_out) coll_out[e] = (uint8_t)o.coll;
-                if (ended_out) ended_out[e] = (uint8_t)s.done;
+                ended_flag = (uint8_t)s.done;
                 if (d.auto_reset && s.done) {                      // UAV.reset() at the episode boundary
                     scen = (int)(((long long)scen + d.n) % d.P);
                     if (EXTRAS && (d.extras & kExtraEnergy)) d.energy[e] = 0.0;
@@ -240,11 +237,6 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
                     d.gx[e] = s.gx; d.gy[e] = s.gy; d.gz[e] = s.gz;
                     d.n_sub[e] = s.n_sub;
                 }
-                d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
-                d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V; d.theta[e] = s.theta;
-                d.score[e] = s.score; d.total[e] = s.total; d.path_len[e] = s.path_len;
-                d.step[e] = s.step; d.cursor[e] = s.cursor;
-                d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
             }
             ENV_TRACE(5);
             if (obs) {
@@ -287,6 +279,21 @@ __device__ __forceinline__ void env_block(const EnvDev &d, EnvSmem<EPB> &sm, int
     ENV_TRACE(7);
     __syncthreads();
     ENV_TRACE(8);
+    // write-back of the stepped state and the step's outputs: behind the barrier, i.e. while the other warps already probe
+    // (these ~25 stores per env used to sit between the step and the barrier every warp of the CTA waits at)
+    if (DO_STEP && valid) {
+        if (reward) reward[e] = (float)o.reward;
+        d.rew64[e] = o.reward;
+        if (done_out) done_out[e] = (uint8_t)o.done_ret;
+        if (info_out) info_out[e] = (uint8_t)o.info;
+        if (coll_out) coll_out[e] = (uint8_t)o.coll;
+        if (ended_out) ended_out[e] = ended_flag;
+        d.px[e] = s.px; d.py[e] = s.py; d.pz[e] = s.pz;
+        d.vx[e] = s.vx; d.vy[e] = s.vy; d.V[e] = s.V; d.theta[e] = s.theta;
+        d.score[e] = s.score; d.total[e] = s.total; d.path_len[e] = s.path_len;
+        d.step[e] = s.step; d.cursor[e] = s.cursor;
+        d.done[e] = (uint8_t)s.done; d.alias[e] = (uint8_t)s.alias;
+    }
     if (EXTRAS && DO_STEP && (d.extras & kExtraApf)) {
         // phase 1b, all threads: UAV.Adjust_subgoal (UAV.py:156-166) for the stored queues -- every entry moves by the
         // force at its (pre-step) position; an env that restarted takes its new scenario's queue instead
