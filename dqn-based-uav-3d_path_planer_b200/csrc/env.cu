@@ -159,6 +159,10 @@ int uavrl_env_create(const uavrl_env_config *cfg, uavrl_env **out)
         return fail(UAVRL_ERR_INVALID, "n_buildings must be in [0,64] (candidate sets are 64-bit masks)");
     if (cfg->n_buildings > 0 && !cfg->buildings_host) return fail(UAVRL_ERR_INVALID, "buildings_host is null");
     if (cfg->max_step <= 0 || !(cfg->max_v > 0)) return fail(UAVRL_ERR_INVALID, "max_step and max_v must be > 0");
+    // RRT.py:69-71 makes sub_goals[0] the UAV's own position object: a collision on the very first step moves that entry with
+    // the UAV.  The kernel does not write the moved entry back to the queue -- immaterial while one step is shorter than the 7 m
+    // sub-goal radius (the entry is popped on that same step; reference Max_V = 1), a divergence from the reference beyond it.
+    if (!(cfg->max_v < 7.0)) return fail(UAVRL_ERR_INVALID, "max_v must be < 7 (sub-goal radius): larger steps are outside the validated model");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(UAVRL_ERR_CUDA, "no CUDA device: the UAV step has no CPU fallback");

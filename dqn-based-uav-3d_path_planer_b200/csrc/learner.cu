@@ -527,6 +527,32 @@ dp_allreduce_adam_kernel(AdamArgs a, int nparts, int n_loss_parts, const float *
     }
 }
 
+// uavrl_replay_gather: logical indices -> packed rows (one warp per transition)
+__global__ void gather_kernel(int n, int in, BatchSrc src, const int64_t *__restrict__ idx, const float *__restrict__ frames,
+                              const int32_t *__restrict__ r_act, const float *__restrict__ r_rew, const uint8_t *__restrict__ r_done,
+                              float *__restrict__ s, float *__restrict__ s2, int32_t *__restrict__ a, float *__restrict__ r, uint8_t *__restrict__ d)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int64_t j = idx[i];
+    int64_t slot, row, row2;
+    if (src.mode == kReplayLockstep) {
+        const int64_t f = (src.oldest + j / src.n_envs) % src.cap, e = j % src.n_envs;
+        slot = f * src.n_envs + e; row = slot; row2 = ((f + 1) % src.cap) * src.n_envs + e;
+    } else {
+        slot = (src.oldest + j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
+    }
+    for (int k = lane; k < in; k += 32) {
+        if (s) s[(size_t)i * in + k] = frames[(size_t)row * in + k];
+        if (s2) s2[(size_t)i * in + k] = frames[(size_t)row2 * in + k];
+    }
+    if (lane == 0) {
+        if (a) a[i] = r_act[slot];
+        if (r) r[i] = r_rew[slot];
+        if (d) d[i] = r_done[slot];
+    }
+}
+
 __global__ void copy_kernel(int n, const float *__restrict__ src, float *__restrict__ dst)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1014,25 +1040,30 @@ int uavrl_replay_gather(uavrl_learner *l, int32_t n, const int64_t *idx, float *
 {
     if (!l || n <= 0 || !idx) return fail(UAVRL_ERR_INVALID, "bad argument");
     UAVRL_CUDA(cudaSetDevice(l->cfg.device));
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= l->count) return fail(UAVRL_ERR_INVALID, "logical index out of range");
     UAVRL_CUDA(cudaDeviceSynchronize());
     const BatchSrc src = replay_source(l, nullptr);
     const size_t in = (size_t)l->net.in_dim;
-    for (int i = 0; i < n; ++i) {
-        const int64_t j = idx[i];
-        if (j < 0 || j >= l->count) return fail(UAVRL_ERR_INVALID, "logical index out of range");
-        int64_t slot, row, row2;
-        if (src.mode == kReplayLockstep) {
-            const int64_t f = (src.oldest + j / src.n_envs) % src.cap, e = j % src.n_envs;
-            slot = f * src.n_envs + e; row = slot; row2 = ((f + 1) % src.cap) * src.n_envs + e;
-        } else {
-            slot = (src.oldest + j) % src.cap; row = 2 * slot; row2 = 2 * slot + 1;
-        }
-        if (s) UAVRL_CUDA(cudaMemcpy(s + i * in, l->frames + row * in, in * 4, cudaMemcpyDeviceToHost));
-        if (s2) UAVRL_CUDA(cudaMemcpy(s2 + i * in, l->frames + row2 * in, in * 4, cudaMemcpyDeviceToHost));
-        if (a) UAVRL_CUDA(cudaMemcpy(a + i, l->r_act + slot, 4, cudaMemcpyDeviceToHost));
-        if (r) UAVRL_CUDA(cudaMemcpy(r + i, l->r_rew + slot, 4, cudaMemcpyDeviceToHost));
-        if (d) UAVRL_CUDA(cudaMemcpy(d + i, l->r_done + slot, 1, cudaMemcpyDeviceToHost));
-    }
+    // one gather kernel into a packed staging block, then one device->host copy per output array (round 1 issued 5 n
+    // synchronous cudaMemcpy calls)
+    int64_t *d_idx = nullptr; float *d_s = nullptr, *d_s2 = nullptr, *d_r = nullptr; int32_t *d_a = nullptr; uint8_t *d_d = nullptr;
+    struct Free { void **p[6]; ~Free() { for (auto q : p) if (q && *q) cudaFree(*q); } } guard{ { (void **)&d_idx, (void **)&d_s, (void **)&d_s2,
+                                                                                                 (void **)&d_r, (void **)&d_a, (void **)&d_d } };
+    UAVRL_CUDA(cudaMalloc((void **)&d_idx, (size_t)n * 8));
+    UAVRL_CUDA(cudaMemcpy(d_idx, idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (s) UAVRL_CUDA(cudaMalloc((void **)&d_s, (size_t)n * in * 4));
+    if (s2) UAVRL_CUDA(cudaMalloc((void **)&d_s2, (size_t)n * in * 4));
+    if (r) UAVRL_CUDA(cudaMalloc((void **)&d_r, (size_t)n * 4));
+    if (a) UAVRL_CUDA(cudaMalloc((void **)&d_a, (size_t)n * 4));
+    if (d) UAVRL_CUDA(cudaMalloc((void **)&d_d, (size_t)n));
+    gather_kernel<<<(n + 7) / 8, 256>>>(n, (int)in, src, d_idx, l->frames, l->r_act, l->r_rew, l->r_done, d_s, d_s2, d_a, d_r, d_d);
+    UAVRL_CUDA(cudaGetLastError());
+    if (s) UAVRL_CUDA(cudaMemcpy(s, d_s, (size_t)n * in * 4, cudaMemcpyDeviceToHost));
+    if (s2) UAVRL_CUDA(cudaMemcpy(s2, d_s2, (size_t)n * in * 4, cudaMemcpyDeviceToHost));
+    if (a) UAVRL_CUDA(cudaMemcpy(a, d_a, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (r) UAVRL_CUDA(cudaMemcpy(r, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (d) UAVRL_CUDA(cudaMemcpy(d, d_d, (size_t)n, cudaMemcpyDeviceToHost));
     return 0;
 }
 

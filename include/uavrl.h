@@ -54,7 +54,7 @@ typedef struct {
     int32_t n_envs;                  /* UAV instances stepped in lockstep */
     int32_t max_subgoals;            /* K: capacity of each sub-goal queue (RRT path length bound) */
     double len, width, h;            /* BaseClass/BaseEnv.py:19-21 (config/PathPlan_City.xml:4-6) */
-    double max_v, min_v;             /* config/UAV.xml:12-13 (Agents/UAV.py:25) */
+    double max_v, min_v;             /* config/UAV.xml:12-13 (Agents/UAV.py:25); 0 < max_v < 7 (the sub-goal radius: see uavrl_env_create) */
     double steering_angle;           /* radians: Steering_angle/180*pi (UAV.py:26) */
     int32_t max_step;                /* UAV.py:32 */
     double climb_rate;               /* discrete-27 extension only */
