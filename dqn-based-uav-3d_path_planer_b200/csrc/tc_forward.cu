@@ -115,7 +115,9 @@ size_t tc_smem_bytes(const TcNet &tc) { return (size_t)2 * tc.a_bytes + (size_t)
 
 // FUSE_ENV: after a tile's actions are written, the same CTA steps those R envs (env_block.cuh) -- the act -> step
 // dependency is per env, so no grid-wide boundary is needed between Trainer.get_action and BaseEnv.Move_Agent.
-template <bool FUSE_ENV>
+// ACT (a.mode == kTcAct), STACK (R <= 64 on the concatenated scheme) and DUELING are compile-time: the kernel a pass runs carries
+// no code of the other modes (tc_train.cu: instruction fetch was a third of the live warps' stalls in the generic kernels)
+template <bool FUSE_ENV, bool ACT, bool STACK, bool DUELING>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, TcArgs a, EnvFuse ef)
 {
     TC_TRACE(0);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     const float *bias_all = reinterpret_cast<const float *>(W + tc.bias_base);
 
     // act mode: row b of the tile is simply obs[base + b] -- no replay sampling (Philox), no pointer table, no barrier
-    const bool direct = (a.mode == kTcAct);
+    constexpr bool direct = ACT;
     uint32_t pkey[4] = {0u, 0u, 0u, 0u};
     if (!direct) Philox::gen(a.src.key, a.src.epoch, 0x5A17ull, pkey);
     uint32_t mphase = 0;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     const int R = a.rows_per_tile, lgR = 31 - __clz(R);
     // R <= 64: stacked 3xTF32 (umma.cuh) -- A_lo lives in rows [R, 2R) of the Ahi buffer, the Alo buffer is the scratch through
     // which the lo*hi block reaches the epilogue warps
-    const bool stack = (R <= 64) && tc.concat && tc.dstride <= 128;     // (the scratch rows hold 64 columns: layers up to 64 wide)
+    constexpr bool stack = STACK;                                       // = R <= 64 && tc.concat && tc.dstride <= 128 (launch_tc_forward)
     float *s_lo = reinterpret_cast<float *>(Alo);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int base = tile * R;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
-                    if (tc.dueling) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
+                    if (DUELING) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
                         float s = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (j < nA) s += q[j];
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
 #pragma unroll
                             for (int j = 0; j < 32; ++j) if (j < nA) a.q_out[(size_t)b * nA + j] = q[j];
                         }
-                        if (a.mode == kTcAct) {
+                        if (ACT) {
                             float u; int ra;
                             if (a.u_tape) { u = a.u_tape[b]; ra = a.rand_tape ? a.rand_tape[b] : 0; }
                             else {
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
                                 ra = (int)(((uint64_t)rr[1] * (uint64_t)nA) >> 32);
                             }
                             a.actions[b] = (u > a.eps || !a.is_train) ? best : ra;      // DuelingDQN_Trainer.py:89-97
-                        } else if (a.mode == kTcArgmax) {
+                        } else if (!ACT && a.mode == kTcArgmax) {
                             a.actions[b] = best;                                        // DDQN_Trainer.py:94
                         } else {
                             float nq = bv;                                              // DQN_Trainer.py:109
@@ -385,6 +387,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel_t(TcNet tc, T
     TC_TRACE(21);
 }
 
+typedef void (*ForwardKernel)(TcNet, TcArgs, EnvFuse);
+template <bool F, bool A, bool S>
+static ForwardKernel pick_fwd_d(bool dueling) { return dueling ? tc_forward_kernel_t<F, A, S, true> : tc_forward_kernel_t<F, A, S, false>; }
+template <bool F, bool A>
+static ForwardKernel pick_fwd_s(bool stack, bool dueling) { return stack ? pick_fwd_d<F, A, true>(dueling) : pick_fwd_d<F, A, false>(dueling); }
+// the fused act + env step variant exists for the act mode only
+static ForwardKernel pick_forward_kernel(bool fuse_env, bool act, bool stack, bool dueling)
+{
+    if (fuse_env) return pick_fwd_s<true, true>(stack, dueling);
+    return act ? pick_fwd_s<false, true>(stack, dueling) : pick_fwd_s<false, false>(stack, dueling);
+}
+
 int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st, const EnvFuse *fuse)
 {
     TcArgs a = a_in;
@@ -408,12 +422,13 @@ int launch_tc_forward(uavrl_learner *l, const TcArgs &a_in, cudaStream_t st, con
     }
     EnvFuse ef;
     memset(&ef, 0, sizeof(ef));
+    const bool stack = a.rows_per_tile <= 64 && l->tc.concat != 0 && l->tc.dstride <= 128;
     if (fuse) {
         ef = *fuse;
-        UAVRL_CUDA(launch_kernel(tc_forward_kernel_t<true>, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
+        UAVRL_CUDA(launch_kernel(pick_forward_kernel(true, a.mode == kTcAct, stack, l->tc.dueling != 0), dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
         l->pdl_prev = l->pdl_chain ? kPdlEnv : kPdlNone;
     } else {
-        UAVRL_CUDA(launch_kernel(tc_forward_kernel_t<false>, dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
+        UAVRL_CUDA(launch_kernel(pick_forward_kernel(false, a.mode == kTcAct, stack, l->tc.dueling != 0), dim3(grid), dim3(kTcThreads), tc_smem_bytes(l->tc), st, a.pdl != 0, l->tc, a, ef));
         l->pdl_prev = l->pdl_chain ? (a.mode == kTcAct ? kPdlAct : kPdlTd) : kPdlNone;
     }
     UAVRL_LAUNCHED();
@@ -449,13 +464,24 @@ int tc_init(uavrl_learner *l)
     }
     UAVRL_CUDA(cudaMalloc((void **)&l->y_buf, (size_t)l->cfg.batch_size * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->astar_buf, (size_t)l->cfg.batch_size * 4));
-    UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+    for (int ac = 0; ac < 2; ++ac)
+        for (int sk = 0; sk < 2; ++sk)
+            for (int du = 0; du < 2; ++du)
+                UAVRL_CUDA(cudaFuncSetAttribute(pick_forward_kernel(false, ac != 0, sk != 0, du != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tc_smem_bytes(l->tc)));
     {   // the fused act+step variant carries the env scratch as static shared memory on top: it must still fit one CTA
-        cudaFuncAttributes fa;
-        UAVRL_CUDA(cudaFuncGetAttributes(&fa, tc_forward_kernel_t<true>));
-        l->fuse_ok = fa.sharedSizeBytes + tc_smem_bytes(l->tc) <= (size_t)227 * 1024;
+        l->fuse_ok = true;
+        for (int sk = 0; sk < 2; ++sk)
+            for (int du = 0; du < 2; ++du) {
+                cudaFuncAttributes fa;
+                UAVRL_CUDA(cudaFuncGetAttributes(&fa, pick_forward_kernel(true, true, sk != 0, du != 0)));
+                if (fa.sharedSizeBytes + tc_smem_bytes(l->tc) > (size_t)227 * 1024) l->fuse_ok = false;
+            }
         if (l->fuse_ok)
-            UAVRL_CUDA(cudaFuncSetAttribute(tc_forward_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(l->tc)));
+            for (int sk = 0; sk < 2; ++sk)
+                for (int du = 0; du < 2; ++du)
+                    UAVRL_CUDA(cudaFuncSetAttribute(pick_forward_kernel(true, true, sk != 0, du != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)tc_smem_bytes(l->tc)));
     }
     l->y_cap = l->cfg.batch_size;
     l->tc_ok = true;

@@ -152,6 +152,10 @@ __device__ __forceinline__ void a0_store(const float4 (&v)[4], int R, int K0, un
 
 __device__ __forceinline__ uint32_t nl_split(const TcNet &tc) { return tc.n_layers > 1 ? (uint32_t)tc.L[1].hi_off : (uint32_t)tc.img_bytes; }
 
+// STACK / NPRE / DUELING are compile-time so that the kernel a configuration runs carries no code of the others: a third of the
+// live warps' stall samples of the generic kernel were instruction-fetch stalls (143 KB of code, executed once per CTA).
+// NPRE = forward-only TD passes ahead of the training chain (0: y comes from stand-alone passes, 1: DQN, 2: double DQN).
+template <bool STACK, int NPRE, bool DUELING>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTrainArgs a)
 {
     TR_TRACE(0);
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     unsigned char *Ahi = smem, *Alo = smem + a_bytes, *W = smem + 2 * a_bytes;
     // stacked 3xTF32 (umma.cuh; R is 32 or 64 here): A_lo occupies rows [R, 2R) of the operand that starts at Ahi (which runs on
     // into the Alo buffer); the lo*hi accumulator block reaches the epilogue warps through a scratch behind the weight image
-    const bool stack = tc.concat != 0 && tc.dstride <= 128;          // (layers up to 64 wide: tc_train_init admits no others)
+    constexpr bool stack = STACK;                                    // = tc.concat && tc.dstride <= 128 (launch_tc_train)
     float *s_lo = reinterpret_cast<float *>(W + tc.train_img_bytes);
     __shared__ uint64_t wbar, wbar2, wbar3, mbar;           // fused TD: training image in three pieces (below)
     __shared__ uint32_t tmem_base_s;
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
     // samples; the first CTA-wide barrier (behind the sample table) publishes all of it (tc_forward.cu)
     constexpr int kCtl = kTcThreads - 32;
     if (tid == 0) s_loss = 0.f;
-    const bool fused = a.fused_td != 0;
-    const int n_pre = fused ? (a.algo != UAVRL_ALGO_DQN ? 2 : 1) : 0;     // forward-only passes ahead of the training chain
+    constexpr bool fused = NPRE > 0;
+    constexpr int n_pre = NPRE;                                      // forward-only passes ahead of the training chain
     // PDL.  Unfused: the training image was written by the previous optimiser kernel (>= 2 kernels back: a TD pass always
     // precedes this kernel), so it is fetched before the wait, and so are the first tile's sampled rows and actions
     // (replay frames / actions were written by the env step and the act kernel, also >= 2 back); only y is the
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
-                    if (tc.dueling) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
+                    if (DUELING) {                                 // Q = V + A - mean(A)  (BaseCNN.py:138)
                         float sA = 0.f, V = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { if (j < nA) sA += q[j]; if (j == nA) V = q[j]; }
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
                     const int nA = tc.n_actions;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] += bias[j];
-                    if (tc.dueling) {
+                    if (DUELING) {
                         float s = 0.f, V = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { if (j < nA) s += q[j]; if (j == nA) V = q[j]; }
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_train_kernel(TcNet tc, TcTra
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float gj;
-                        if (tc.dueling) gj = (j < nA) ? gq * ((j == act ? 1.f : 0.f) - inv) : (j == nA ? gq : 0.f);
+                        if (DUELING) gj = (j < nA) ? gq * ((j == act ? 1.f : 0.f) - inv) : (j == nA ? gq : 0.f);
                         else gj = (j == act) ? gq : 0.f;
                         g[j] = gj;
                     }
@@ -616,6 +620,7 @@ __device__ __forceinline__ void dw_store_rows(const float4 (&v)[U], const float 
     }
 }
 
+template <bool FUSE_ADAM>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     // Lanes hold consecutive f, so every store instruction writes 32 consecutive elements of one weight row; the 32 columns of a
     // thread walk the rows with a pointer increment and a predicate each (the address arithmetic used to dominate this epilogue).
     float *part = a.partials + (size_t)chunk * a.P;
-    unsigned long long *part64 = a.fuse_adam ? a.part64 + (size_t)chunk * a.P : nullptr;
+    unsigned long long *part64 = FUSE_ADAM ? a.part64 + (size_t)chunk * a.P : nullptr;
     const unsigned long long tag = (unsigned long long)a.ll_epoch << 32;
     const int f = quad * 32 + lane;
     for (int c0 = half * 32; c0 < T.N_pad; c0 += 64) {
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
         const int stride = brow ? 1 : T.K_real;
         const int i_main = brow ? T.b_off + c0 : T.w_off + f + c0 * T.K_real;
         const int i_val = brow ? T.b2_off + (c0 - T.out_main) : (T.w2_off >= 0 ? T.w2_off : 0) + f + (c0 - T.out_main) * T.K_real;
-        if (part64) {
+        if (FUSE_ADAM) {
             unsigned long long *p = part64 + i_main;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -769,7 +774,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     __syncthreads();
     if (warp == kCtl / 32) { tc_fence_after(); tmem_dealloc(tmem, (uint32_t)tc.dstride); }
     DW_TRACE(8);
-    if (!a.fuse_adam) return;
+    if (!FUSE_ADAM) return;
     // ---- fused optimiser tail: this CTA reduces its slice of the parameter vector over all partials in reduce_adam_kernel's
     // order and applies Adam.  Every word it needs is polled until it carries this launch's epoch (all CTAs are resident: grid
     // <= SMs, one CTA per SM, and each writes its partial before it polls) -- nothing to fence, no barrier to wait at.
@@ -823,6 +828,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dw_kernel(TcNet tc, TcDwArgs
     }
 }
 
+typedef void (*TrainKernel)(TcNet, TcTrainArgs);
+template <bool S, int N>
+static TrainKernel pick_train_d(bool dueling) { return dueling ? tc_train_kernel<S, N, true> : tc_train_kernel<S, N, false>; }
+template <bool S>
+static TrainKernel pick_train_n(int npre, bool dueling) { return npre == 0 ? pick_train_d<S, 0>(dueling) : npre == 1 ? pick_train_d<S, 1>(dueling) : pick_train_d<S, 2>(dueling); }
+static TrainKernel pick_train_kernel(bool stack, int npre, bool dueling) { return stack ? pick_train_n<true>(npre, dueling) : pick_train_n<false>(npre, dueling); }
+
 static size_t train_smem_bytes(const TcNet &tc, int R)
 {
     return (size_t)2 * (R / 8) * umma_sbo(tc.max_k) + (size_t)tc.train_img_bytes + (size_t)R * kLoLd * 4;   // + the stacked-3xTF32 scratch
@@ -844,9 +856,13 @@ int tc_train_init(uavrl_learner *l)
     // which must still be inside the CTA's allocation
     if (train_smem_bytes(tc, 32) > 227 * 1024 || dw_smem_bytes(tc) > 227 * 1024) return 0;
     if (train_smem_bytes(tc, 32) < (size_t)(32 / 8) * umma_sbo(tc.max_k) + (size_t)16 * umma_sbo(tc.max_k)) return 0;
-    UAVRL_CUDA(cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
-    UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
+    for (int st = 0; st < 2; ++st)
+        for (int np = 0; np < 3; ++np)
+            for (int du = 0; du < 2; ++du)
+                UAVRL_CUDA(cudaFuncSetAttribute(pick_train_kernel(st != 0, np, du != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(train_smem_bytes(tc, 64) <= 227 * 1024 ? train_smem_bytes(tc, 64) : train_smem_bytes(tc, 32))));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
+    UAVRL_CUDA(cudaFuncSetAttribute(tc_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(tc)));
     const size_t cap = (size_t)l->cfg.batch_size;
     UAVRL_CUDA(cudaMalloc((void **)&l->act_buf, cap * (size_t)(tc.act_stride > 0 ? tc.act_stride : 4) * 4));
     UAVRL_CUDA(cudaMalloc((void **)&l->dz_buf, cap * (size_t)tc.dz_stride * 4));
@@ -883,12 +899,15 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     static const bool trace_on = getenv("UAVRL_TC_TRACE") != nullptr;
     long long *tr = nullptr;
     if (trace_on) { UAVRL_CUDA(cudaMalloc((void **)&tr, 48 * sizeof(long long))); UAVRL_CUDA(cudaMemset(tr, 0, 48 * sizeof(long long))); a.trace = tr + 16; }
-    UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st,
-                             chain && (fused_td ? (l->pdl_prev == kPdlEnv) : (l->pdl_prev == kPdlTd)), tc, a));
+    const bool use_pdl = chain && (fused_td ? (l->pdl_prev == kPdlEnv) : (l->pdl_prev == kPdlTd));
+    const bool stack = tc.concat != 0 && tc.dstride <= 128;
+    const int npre = fused_td ? (l->cfg.algo != UAVRL_ALGO_DQN ? 2 : 1) : 0;
+    auto train_fn = pick_train_kernel(stack, npre, tc.dueling != 0);
+    UAVRL_CUDA(launch_kernel(train_fn, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st, use_pdl, tc, a));
     // experiment (with UAVRL_TC_TRACE): the same launch again, back to back -- the kernel is idempotent, the second run finds
     // its code in the instruction caches, and the stage trace printed below is the second run's
     static const bool twice = trace_on && getenv("UAVRL_TRAIN_TWICE") != nullptr;
-    if (twice) UAVRL_CUDA(launch_kernel(tc_train_kernel, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st, false, tc, a));
+    if (twice) UAVRL_CUDA(launch_kernel(train_fn, dim3(grid), dim3(kTcThreads), train_smem_bytes(tc, a.R), st, false, tc, a));
     l->pdl_prev = chain ? kPdlTrain : kPdlNone;
     UAVRL_LAUNCHED();
     if (after_chain) UAVRL_CUDA(cudaEventRecord(after_chain, st));
@@ -924,7 +943,7 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
         q.tc_hi2 = l->tc_hi2_map; q.tc_lo2 = l->tc_lo2_map; q.loss_out = loss_out;
     }
     if (trace_on) d.trace = tr;
-    UAVRL_CUDA(launch_kernel(tc_dw_kernel, dim3(dw_grid), dim3(kTcThreads), dw_smem_bytes(tc), st,
+    UAVRL_CUDA(launch_kernel(fuse ? tc_dw_kernel<true> : tc_dw_kernel<false>, dim3(dw_grid), dim3(kTcThreads), dw_smem_bytes(tc), st,
                              chain && !after_chain, tc, d));
     l->pdl_prev = chain ? (fuse ? kPdlAdam : kPdlDw) : kPdlNone;
     UAVRL_LAUNCHED();
