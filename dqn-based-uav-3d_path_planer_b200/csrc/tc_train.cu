@@ -872,11 +872,19 @@ int tc_train_init(uavrl_learner *l)
 }
 
 std::atomic<int> g_fuse_td{1};               // uavrl_set_fuse_td(); default on
+// rows per tile of the training kernel: 32 while the batch fits one wave of 32-row tiles, else 64 (when the 64-row operands fit)
+static int train_rows_per_tile(const TcNet &tc, int B)
+{
+    return (B > 32 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
+}
 bool tc_train_can_fuse_td(const uavrl_learner *l, int B)
 {
-    // one tile per CTA (R = 32 rows): the weight images are restaged inside the kernel, which only pays when a CTA does
-    // it once; larger batches keep the separate TD-target kernel(s) whose CTAs reuse one image over several tiles
-    return g_fuse_td.load() && l->tc_train_ok && (B + 31) / 32 <= 148 && B < 64 * 148;
+    // one tile per CTA (32-row tiles up to 4 736 samples, 64-row tiles up to 9 472): the weight images are restaged inside the
+    // kernel, which only pays when a CTA does it once; larger batches keep the separate TD-target kernel(s) whose CTAs reuse
+    // one image over several tiles
+    if (!g_fuse_td.load() || !l->tc_train_ok) return false;
+    const int R = train_rows_per_tile(l->tc, B);
+    return (B + R - 1) / R <= 148;
 }
 std::atomic<int> g_fuse_dw_adam{0};          // uavrl_set_fuse_dw_adam(); default off: measured no faster than the PDL-chained pair
 
@@ -891,7 +899,7 @@ int launch_tc_train(uavrl_learner *l, const BatchSrc &src, int B, int global_bat
     a.act_buf = l->act_buf; a.dz_buf = l->dz_buf; a.loss_partials = l->loss_partials;
     a.loss_kind = l->cfg.loss_kind;
     a.fused_td = fused_td ? 1 : 0; a.algo = l->cfg.algo; a.gamma = l->cfg.gamma; a.img_target = l->tc_img_target;
-    a.R = (B >= 64 * 148 && train_smem_bytes(tc, 64) <= 227 * 1024) ? 64 : 32;
+    a.R = train_rows_per_tile(tc, B);
     a.n_tiles = (B + a.R - 1) / a.R;
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     const bool chain = l->pdl_chain && g_pdl.load();

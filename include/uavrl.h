@@ -370,7 +370,7 @@ int uavrl_set_fuse_act_env(int32_t on);
  * the reduction order is the optimiser kernel's).  Process-wide switch, default 0: measured on B200 the loop is 52.8 us per
  * iteration with it and 50.9 us with the PDL-chained pair -- the optimiser's launch latency was already hidden. */
 int uavrl_set_fuse_dw_adam(int32_t on);
-/* Batches of at most 148 x 32 transitions on the tensor-core path: the TD-target forward pass(es) (target network on the next
+/* Batches of at most 148 x 32 transitions (148 x 64 on 64-row tiles when the operands fit shared memory) on the tensor-core path: the TD-target forward pass(es) (target network on the next
  * states; double DQN: the local network first) run inside the training kernel, each CTA on the tile it then trains on
  * (weight images restaged in shared memory between the passes, y kept in shared memory) -- one launch instead of two or
  * three per update; the arithmetic is the stand-alone passes'.  Process-wide switch, default 1. */

@@ -119,3 +119,33 @@ def test_dependent_launch_overlap_changes_nothing(env_golden, env27_golden, algo
         assert abs(a["stats"][6] - b["stats"][6]) <= 1e-9 * abs(b["stats"][6])       # sum_reward: fp64 atomics, order-dependent
         for k in ("p", "t", "s", "a", "r", "d", "px", "step"):
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_fused_td_on_64_row_tiles_changes_nothing(env_golden, env27_golden):
+    """Batches between 4 737 and 9 472 samples (BASELINE configs[3]: 8 192 per GPU) train on 64-row tiles, one per CTA, with the
+    TD-target passes inside the training kernel; 40 double-DQN iterations end in the same bits as with stand-alone TD passes."""
+    from uavrl_b200 import _lib, engine
+    city, params, _, _ = city_and_params(env_golden, env27_golden)
+    N = 6144
+    out = []
+    try:
+        for fuse_td in (1, 0):
+            _lib.lib().uavrl_set_fuse_td(fuse_td)
+            env = engine.EnvBatch(city, params, N, max_subgoals=64, auto_reset=True)
+            sc = env.make_scenarios(1024, seed=8)
+            env.set_pool(sc["start"], sc["goal"], sc["heading"], sc["sub"], sc["n_sub"])
+            env.reset(0)
+            L = engine.Learner(100, [64, 64], 27, False, engine.ALGO_DDQN, batch_size=N, replay_capacity=N * 8, lockstep_envs=N, seed=1,
+                               update_loop=3)
+            L.init_params(0)
+            assert L.td_fused() == bool(fuse_td)
+            engine.train_run(env, L, 3, eps=1.0, do_update=False)
+            st = engine.train_run(env, L, 40, eps=0.2)
+            torch.cuda.synchronize()
+            out.append(dict(p=L.get_params(0), t=L.get_params(1), loss=st.last_loss, updates=st.updates))
+            env.close(); L.close()
+    finally:
+        _lib.lib().uavrl_set_fuse_td(1)
+    a, b = out
+    assert a["updates"] == b["updates"] == 40 and np.isfinite(a["p"]).all()
+    assert np.array_equal(a["p"], b["p"]) and np.array_equal(a["t"], b["t"]) and a["loss"] == b["loss"]
