@@ -80,3 +80,42 @@ def test_env_core_single_steps_next_to_every_decision_boundary(shim, env_golden,
     b, n = step_batch(g, prefix, city, params)
     rew, done, info, coll, obs = shim_step(shim, city, params, b, g[prefix + "action"].astype(np.float64), mode)
     check_step_outputs(g, prefix, b, rew, done, info, coll, obs32=obs, exact=False)
+
+
+def test_env_core_apf_matches_reference_goldens(shim):
+    """The kernel's APF source (step_core_apf + apf_force + the queue shift of env_block.cuh's phase 1b, host compile) on the 1 750
+    steps of the unmodified reference UAV with APF_Enabled = 1 over obstacles that carry a velocity (tests/golden/apf_golden.npz):
+    masks, counters and the whole shifted sub-goal queue exact, fp64 state / reward to 1e-12 (sincos / atan2 of the host libm),
+    occupancy bits exact."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "apf_golden.npz"))
+    d = g["dims"]
+    city = O.OracleCity(d[0], d[1], d[2], g["buildings"])
+    p = g["uav_params"]
+    params = O.UavParams(p[0], p[1], p[2], 1.0, int(p[3]))
+    ov = np.ascontiguousarray(g["obstacle_v"], np.float64)
+    total = 0
+    for i in range(int(g["epn_episodes"])):
+        ep = episode(g, i)
+        b = O.OracleBatch(city, params, 1, ep["sub"].shape[0])
+        b.reset(ep["start"][None], ep["goal"][None], [ep["heading"]], ep["sub"][None], [ep["n_sub"]], [ep["alias0"]])
+        for t in range(len(ep["action"])):
+            rew = np.zeros(1); done = np.zeros(1, np.uint8); info = np.zeros(1, np.uint8); coll = np.zeros(1, np.uint8)
+            obs = np.zeros((1, 100), np.float32)
+            st = b._struct()
+            acts = np.ascontiguousarray([ep["action"][t]], np.float64)
+            shim.shim_step_apf(C.c_double(city.c.width), C.c_double(city.c.h), C.c_int(city.buildings.shape[0]),
+                               O._p(city.buildings, C.c_double), O._p(ov, C.c_double), C.c_double(params.max_v), C.c_double(params.min_v),
+                               C.c_double(params.steering), C.c_double(params.climb_rate), C.c_int(params.max_step), C.c_int(0),
+                               C.byref(st), O._p(acts, C.c_double), O._p(rew, C.c_double), O._p(done, C.c_uint8), O._p(info, C.c_uint8),
+                               O._p(coll, C.c_uint8), O._p(obs, C.c_float))
+            assert abs(rew[0] - ep["reward"][t]) <= 1e-12 * max(1.0, abs(ep["reward"][t])), (i, t, rew[0], ep["reward"][t])
+            assert (done[0], info[0], coll[0]) == (ep["done_ret"][t], ep["info"][t], ep["collision"][t]), (i, t)
+            for k in ("px", "py", "pz", "vx", "vy", "V", "score", "total_score", "path_len"):
+                assert abs(getattr(b, k)[0] - ep[k][t]) <= 1e-12 * max(1.0, abs(ep[k][t])), (i, t, k)
+            assert b.step[0] == ep["step"][t] and b.cursor[0] == ep["cursor"][t] and b.done[0] == ep["done"][t]
+            nleft = int(b.n_sub[0] - b.cursor[0])
+            np.testing.assert_allclose(b.sub[0, b.cursor[0]:b.n_sub[0]], ep["subq"][t][:nleft], rtol=0, atol=1e-11, err_msg=str((i, t)))
+            np.testing.assert_allclose(obs[0], ep["obs"][t].astype(np.float32), rtol=0, atol=1e-6)
+            assert np.array_equal(obs[0, 11:86], ep["obs"][t][11:86]) and np.array_equal(obs[0, 90:95], ep["obs"][t][90:95])
+            total += 1
+    assert total == 1750
