@@ -143,4 +143,12 @@ void shim_step_apf(double width, double h, int n_cyl, const double *buildings, c
     }
 }
 
+// the kernel's Calc_Fly_Power (UAV.py:239-245)
+double shim_fly_power(double V, double P_i, double v_0, double d_0, double rho, double s, double A, double P_b, double F_b, double xi)
+{
+    PowerConst c;
+    c.P_i = P_i; c.v_0 = v_0; c.d_0 = d_0; c.rho = rho; c.s = s; c.A = A; c.P_b = P_b; c.F_b = F_b; c.xi = xi;
+    return fly_power(c, V);
+}
+
 }  // extern "C"

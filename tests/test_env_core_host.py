@@ -119,3 +119,23 @@ def test_env_core_apf_matches_reference_goldens(shim):
             assert np.array_equal(obs[0, 11:86], ep["obs"][t][11:86]) and np.array_equal(obs[0, 90:95], ep["obs"][t][90:95])
             total += 1
     assert total == 1750
+
+
+def test_env_core_fly_power_kat(shim):
+    """The kernel's fly_power (host compile) vs Agents/UAV.py:241-245 evaluated with Python float arithmetic as written there
+    (`**` = libm pow; the kernel forms V**2, V**3, V**4 by repeated multiplication -- within an ulp of pow each, which the cancellation in
+    sqrt(1 + V^4 / 4 v0^4) - V^2 / 2 v0^2 amplifies at high speed: 1e-14 relative is asserted, the oracle's libm version is exact),
+    constants of config/UAV.xml <Fly_power>."""
+    import math
+    shim.shim_fly_power.restype = C.c_double
+    shim.shim_fly_power.argtypes = [C.c_double] * 10
+    P_i, v_0, d_0, rho, s, A, P_b, F_b = 89.0, 4.05, 0.6, 1.225, 0.05, 0.5, 79.0, 120.0
+    for j in (0, 1, 3):
+        xi, Aj = 0.8 + 0.02 * j, A + 0.03 * j
+        for V in (0.0, 0.6, 0.8, 1.0, 2.5, 7.0, 15.0, 30.0):
+            induced = P_i * math.sqrt(math.sqrt(1 + (V ** 4) / (4 * (v_0 ** 4))) - (V ** 2) / (2 * (v_0 ** 2)))
+            parasite = 0.5 * d_0 * rho * s * Aj * (V ** 3)
+            blade = xi * P_b * (1 + 3 * (V ** 2) / (F_b ** 2))
+            want = induced + parasite + blade
+            got = shim.shim_fly_power(V, P_i, v_0, d_0, rho, s, Aj, P_b, F_b, xi)
+            assert abs(got - want) <= 1e-14 * abs(want), (j, V, got, want)
